@@ -1,0 +1,194 @@
+"""Generate golden vectors by running the UNMODIFIED reference in the build container.
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+Imports ``/root/reference/neural_jump_ode/models/jump_ode.py`` (the hot path) and
+``.../simulation/data_generation.py`` (the deterministic generators, seed=i per
+trajectory) directly by file path -- ``neural_jump_ode.utils`` needs matplotlib, which
+is not installed here, and is not on the path.  The reference does not exist on
+the GPU box, so the resulting ``*.npz`` files are committed next to this script.
+
+Each case stores: the model/loss configuration (json), packed inputs, the
+reference's state_dict, preds, preds_before, loss, every parameter gradient
+(``None`` gradients stored as zeros + a ``has_grad`` flag), and the float32
+(t_last, t_next) pair of every ``euler_step`` call in call order.
+"""
+import importlib.util
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = "/root/reference/neural_jump_ode"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def main():
+    sys.dont_write_bytecode = True
+    jo = _load("ref_jump_ode", f"{REF}/models/jump_ode.py")
+    dg = _load("ref_data_generation", f"{REF}/simulation/data_generation.py")
+
+    def data(kind, n, obs_fraction, **kw):
+        return dg.create_trajectory_batch(n, kind, obs_fraction=obs_fraction, **kw)
+
+    bs = dict(mu=0.1, sigma=0.5, T=1.0, n_steps=100, x0=1.0)          # experiment_black_scholes.py defaults
+    ou = dict(theta=1.0, mu=0.5, sigma=0.3, T=1.0, n_steps=100, x0=0.0)  # experiment_ou.py:65-70
+    heston = dict(mu=0.5, kappa=2.0, theta=0.04, xi=0.5, rho=-0.5, x0=1.0, v0=0.04, T=1.0)
+
+    hand_t = [torch.tensor([0.0, 0.5, 1.0]), torch.tensor([0.0, 0.3, 0.8])]    # tests/test_basic.py:47-51
+    hand_v = [torch.tensor([[1.0], [1.2], [0.9]]), torch.tensor([[0.5], [0.7], [0.6]])]
+
+    # ragged batch: different observation counts per trajectory (list API allows it)
+    rt, rv = [], []
+    for frac, n in ((0.05, 2), (0.1, 2), (0.2, 2)):
+        t, v = data("black_scholes", n, frac, **bs)
+        rt += t
+        rv += v
+    rt += hand_t
+    rv += hand_v
+
+    # edge cases: single observation, duplicate time (zero steps), gap < dt, exact multiples
+    et = [torch.tensor([0.25]),
+          torch.tensor([0.0, 0.1, 0.1, 0.104, 0.5]),
+          torch.tensor([0.0, 0.01, 0.02, 0.05]),
+          torch.tensor([0.3, 1.0])]
+    ev = [torch.tensor([[0.7]]),
+          torch.tensor([[1.0], [1.1], [0.9], [1.05], [1.2]]),
+          torch.tensor([[0.2], [-0.1], [0.0], [0.3]]),
+          torch.tensor([[2.0], [1.5]])]
+
+    # 2-d observations
+    g = torch.Generator().manual_seed(7)
+    t2, v2 = [], []
+    for n in (4, 6, 3):
+        tt = torch.sort(torch.rand(n, generator=g))[0]
+        tt[0] = 0.0
+        t2.append(tt)
+        v2.append(torch.randn(n, 2, generator=g) * 0.5 + 1.0)
+
+    cases = {
+        "bs_h32_sep_dt01": dict(
+            model=dict(input_dim=1, hidden_dim=32, output_dim=1, dt_ode_step=0.01, num_moments=2),
+            loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct"),
+            data=data("black_scholes", 6, 0.1, **bs)),
+        "bs_h32_sep_dtnone": dict(
+            model=dict(input_dim=1, hidden_dim=32, output_dim=1, dt_ode_step=None, num_moments=2),
+            loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct"),
+            data=data("black_scholes", 6, 0.1, **bs)),
+        "ou_h32_shared_dt01": dict(
+            model=dict(input_dim=1, hidden_dim=32, output_dim=1, dt_ode_step=0.01, num_moments=2,
+                       shared_network=True, activation="identity"),   # 'identity' -> ReLU (jump_ode.py:18)
+            loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct"),
+            data=data("ornstein_uhlenbeck", 6, 0.1, **ou)),
+        "ou_h32_shared_second_moment": dict(
+            model=dict(input_dim=1, hidden_dim=32, output_dim=1, dt_ode_step=0.01, num_moments=2,
+                       shared_network=True, variance_method="second_moment"),
+            loss=dict(ignore_first_continuity=False, moment_weights=[1.0, 3.0], variance_method="second_moment"),
+            data=data("ornstein_uhlenbeck", 5, 0.1, **ou)),
+        "ragged_h64_sep_dt01": dict(
+            model=dict(input_dim=1, hidden_dim=64, output_dim=1, dt_ode_step=0.01, num_moments=2),
+            loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct"),
+            data=(rt, rv)),
+        "heston_h128_l3_tanh": dict(
+            model=dict(input_dim=1, hidden_dim=128, output_dim=1, dt_ode_step=0.005, num_moments=2,
+                       n_hidden_layers=3, activation="tanh"),
+            loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct"),
+            data=data("heston", 3, 0.1, n_steps=50, **heston)),
+        "heston_h32_dt005": dict(
+            model=dict(input_dim=1, hidden_dim=32, output_dim=1, dt_ode_step=0.005, num_moments=2),
+            loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct"),
+            data=data("heston", 4, 0.1, n_steps=200, **heston)),
+        "m1_h16_l2_sigmoid_tanhscale": dict(
+            model=dict(input_dim=1, hidden_dim=16, output_dim=1, dt_ode_step=0.02, num_moments=1,
+                       n_hidden_layers=2, activation="sigmoid", input_scaling="tanh"),
+            loss=dict(ignore_first_continuity=False, moment_weights=None, variance_method="direct"),
+            data=(hand_t + rt[:2], hand_v + rv[:2])),
+        "m3_h24_elu_sigscale": dict(
+            model=dict(input_dim=1, hidden_dim=24, output_dim=1, dt_ode_step=0.01, num_moments=3,
+                       activation="elu", input_scaling="sigmoid"),
+            loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0, 5.0], variance_method="direct"),
+            data=data("ornstein_uhlenbeck", 4, 0.08, **ou)),
+        "m3_shared_h50_selu": dict(
+            model=dict(input_dim=1, hidden_dim=50, output_dim=1, dt_ode_step=0.01, num_moments=3,
+                       activation="selu", shared_network=True),
+            loss=dict(ignore_first_continuity=False, moment_weights=[2.0, 1.0, 1.0], variance_method="direct"),
+            data=data("black_scholes", 4, 0.1, **bs)),
+        "edge_leaky_h32": dict(
+            model=dict(input_dim=1, hidden_dim=32, output_dim=1, dt_ode_step=0.01, num_moments=2,
+                       activation="leaky_relu"),
+            loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct"),
+            data=(et, ev)),
+        "edge_dtnone_shared": dict(
+            model=dict(input_dim=1, hidden_dim=32, output_dim=1, dt_ode_step=None, num_moments=2,
+                       shared_network=True),
+            loss=dict(ignore_first_continuity=False, moment_weights=None, variance_method="direct"),
+            data=(et, ev)),
+        "d2_h32_l2_tanh": dict(
+            model=dict(input_dim=2, hidden_dim=32, output_dim=2, dt_ode_step=0.05, num_moments=2,
+                       n_hidden_layers=2, activation="tanh"),
+            loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 2.0], variance_method="direct"),
+            data=(t2, v2)),
+        "d2_shared_h32": dict(
+            model=dict(input_dim=2, hidden_dim=32, output_dim=2, dt_ode_step=0.05, num_moments=2,
+                       shared_network=True),
+            loss=dict(ignore_first_continuity=False, moment_weights=[1.0, 2.0], variance_method="second_moment"),
+            data=(t2, v2)),
+    }
+
+    for name, case in cases.items():
+        mk = dict(case["model"])
+        torch.manual_seed(0)
+        model = jo.NeuralJumpODE(**mk)
+        # make outputs less trivially small so relative errors mean something
+        bt, bv = case["data"]
+        bt = [t.to(torch.float32) for t in bt]
+        bv = [v.to(torch.float32) for v in bv]
+
+        log = []
+        orig = model.euler_step
+
+        def logged(h_list, x_last, t_last, t_next, _orig=orig, _log=log):
+            _log.append((np.float32(t_last.item()), np.float32(t_next.item())))
+            return _orig(h_list, x_last, t_last, t_next)
+
+        model.euler_step = logged
+        preds, preds_before = model(bt, bv)
+        lk = dict(case["loss"])
+        loss = jo.nj_ode_loss(bt, bv, preds, preds_before, **lk)
+        loss.backward()
+
+        n = [len(t) for t in bt]
+        off = np.zeros(len(n) + 1, np.int64)
+        off[1:] = np.cumsum(n)
+        out = {
+            "config_json": np.frombuffer(json.dumps(dict(model=mk, loss=lk)).encode(), dtype=np.uint8),
+            "times": torch.cat(bt).numpy(),
+            "values": torch.cat(bv).numpy(),
+            "offsets": off,
+            "preds": torch.cat([p.detach() for p in preds]).numpy(),
+            "preds_before": torch.cat([p.detach() for p in preds_before]).numpy(),
+            "loss": np.array(loss.item(), dtype=np.float32),
+            "step_log": np.array(log, dtype=np.float32).reshape(-1, 2),
+        }
+        for k, p in model.named_parameters():
+            out["param/" + k] = p.detach().numpy()
+            out["grad/" + k] = (torch.zeros_like(p) if p.grad is None else p.grad).numpy()
+            out["has_grad/" + k] = np.array(p.grad is not None)
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: B={len(bt)} N={off[-1]} steps={len(log)} loss={loss.item():.6f} "
+              f"params={sum(p.numel() for p in model.parameters())} -> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()
