@@ -1,0 +1,173 @@
+/*
+ * njode.h -- C-ABI of libnjode_b200.so: the Neural Jump ODE training hot path on B200 (sm_100a).
+ *
+ * Plain C, raw device pointers and sizes, no torch types.  Every entry point replaces a piece of
+ * the reference's Python hot path (file:line relative to the reference repository):
+ *
+ *   njode_schedule_*   the float32 Euler step rule            neural_jump_ode/models/jump_ode.py:188-203
+ *   njode_forward      NeuralJumpODE.forward / forward_single neural_jump_ode/models/jump_ode.py:142-233
+ *                      (JumpNN :15-26, ODEFunc :29-63, OutputNN :66-77, euler_step :122-140)
+ *   njode_loss         nj_ode_loss (value and d/dpreds)       neural_jump_ode/models/jump_ode.py:235-383
+ *   njode_backward     what loss.backward() does for this path neural_jump_ode/utils/training.py:69, :97
+ *   njode_adam_step    optimizer.step() on the flat buffer    neural_jump_ode/utils/training.py:98, :396
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless the name ends in _host.  The caller (PyTorch) owns
+ *     every buffer; the library allocates nothing persistent and keeps no thread-local state
+ *     except the last error string.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *     except where stated.
+ *   - Return value: 0 on success, negative NJODE_E* otherwise; njode_last_error() gives the text.
+ *     Nothing throws across the ABI.  There is no CPU fallback.
+ *   - "Observation unit" o in [0,N): one (trajectory, observation) pair of the packed batch.  Unit o
+ *     computes h=jump(x_o), preds[o]=out(h) and, if o is not the last observation of its trajectory,
+ *     integrates to t_{o+1} and writes preds_before[o+1]=out(h_end).  Units are independent
+ *     initial-value problems because the jump resets h from x_o alone (jump_ode.py:169, :176).
+ *
+ * Packed batch layout (all float32, C-contiguous)
+ *   times        (N)            observation times, trajectory after trajectory
+ *   values       (N, d_x)
+ *   obs_offsets  (B+1) int64    trajectory b owns observations [obs_offsets[b], obs_offsets[b+1])
+ *   preds, preds_before (N, d_y, M); preds_before[first observation of a trajectory] == 0
+ *
+ * Flat parameter layout (float32): for stack s = 0..S-1 (S = 1 if shared_network else num_moments):
+ *   jump net   layers i=0..L:  W (H x in_i) row-major, b (H);     in_0 = d_x,        in_i = H
+ *   ode  net   layers i=0..L:  W (H x in_i) row-major, b (H);     in_0 = H+d_x+2,    in_i = H
+ *                              columns of layer 0 = [h(0..H-1), x(0..d_x-1), t_cur, t_new-t_cur]
+ *   out  net   layers i=0..L:  W (out_i x H) row-major, b(out_i); out_i = H, out_L = O
+ *   O = d_y (separate networks) or d_y*M (shared; flat output index = d*M + m, jump_ode.py:172)
+ *   i.e. exactly the reference's nn.Linear weights (state_dict keys *.net.{3i}.{weight,bias}).
+ */
+#ifndef NJODE_H_
+#define NJODE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NJODE_ABI_VERSION 1
+
+enum {
+  NJODE_OK = 0,
+  NJODE_EINVAL = -1,      /* bad argument / unsupported configuration */
+  NJODE_ECUDA = -2,       /* CUDA runtime error */
+  NJODE_EWORKSPACE = -3   /* workspace too small */
+};
+
+/* jump_ode.py:6-13; unknown names map to RELU on the Python side (jump_ode.py:18) */
+enum { NJODE_ACT_RELU = 0, NJODE_ACT_TANH = 1, NJODE_ACT_SIGMOID = 2, NJODE_ACT_ELU = 3,
+       NJODE_ACT_LEAKY_RELU = 4, NJODE_ACT_SELU = 5 };
+/* jump_ode.py:43-50 */
+enum { NJODE_SCALE_IDENTITY = 0, NJODE_SCALE_TANH = 1, NJODE_SCALE_SIGMOID = 2 };
+/* jump_ode.py:333 / :346 */
+enum { NJODE_VAR_DIRECT = 0, NJODE_VAR_SECOND_MOMENT = 1 };
+/* kernel flavour: AUTO picks TILED when the shape is supported, else GENERIC */
+enum { NJODE_IMPL_AUTO = 0, NJODE_IMPL_GENERIC = 1, NJODE_IMPL_TILED = 2 };
+
+typedef struct NjodeDesc {
+  int32_t d_x;              /* input_dim */
+  int32_t d_y;              /* output_dim */
+  int32_t hidden;           /* hidden_dim H */
+  int32_t n_hidden_layers;  /* L >= 1 */
+  int32_t num_moments;      /* M >= 1 */
+  int32_t shared_network;   /* 0/1 */
+  int32_t activation;       /* NJODE_ACT_* */
+  int32_t input_scaling;    /* NJODE_SCALE_* */
+  int32_t has_dt;           /* 0: dt_ode_step is None -> one Euler step per interval */
+  float   dt;               /* dt_ode_step as float32 */
+  int32_t impl;             /* NJODE_IMPL_* */
+  int32_t reserved;
+} NjodeDesc;
+
+typedef struct NjodeLossDesc {
+  int32_t ignore_first_continuity;
+  int32_t variance_method;  /* NJODE_VAR_* */
+  float   eps;              /* 1e-10 in the reference */
+  float   w0, w1;           /* moment weights (1,1 when moment_weights is None) */
+  int32_t reserved;
+} NjodeLossDesc;
+
+/* schedule header written by njode_schedule_build (device int64[8]) */
+enum { NJODE_HDR_TOTAL_STEPS = 0,   /* sum over trajectories of Euler steps ("trajectory-ODE-steps") */
+       NJODE_HDR_TOTAL_SLOTS = 1,   /* checkpoint slots: sum over tiles of (kmax_tile + 1) */
+       NJODE_HDR_NUM_TILES = 2,
+       NJODE_HDR_KMAX = 3,
+       NJODE_HDR_WORDS = 8 };
+
+int32_t     njode_abi_version(void);
+const char* njode_last_error(void);
+
+/* number of float32 parameters of one stack / of the whole model; -1 on a bad descriptor */
+int64_t njode_params_per_stack(const NjodeDesc* desc);
+int64_t njode_param_count(const NjodeDesc* desc);
+int32_t njode_num_stacks(const NjodeDesc* desc);
+
+/* rows per tile of the kernel flavour that (desc) selects; the schedule is built for it */
+int32_t njode_tile_rows(const NjodeDesc* desc);
+
+/* ---- step schedule (jump_ode.py:188-203, float32 accumulation reproduced bit for bit) ---------
+ * build: kenc[o] = (K_o << 1) | has_next_o ; perm = units sorted by K descending, padded with -1
+ *        to n_tiles*tile_rows ; tile_kmax ; tile_slot_off = exclusive scan of (kmax+1) ; header.
+ * knots: knots[(slot_off[tile]+k)*tile_rows + r] = t_k of row r, k = 0..kmax_tile (float32);
+ *        t_0 = t_o, t_K = t_{o+1}; entries beyond a row's own K repeat t_K.
+ * The caller reads `header` back (one small D2H copy) to size knots / checkpoints. */
+size_t njode_schedule_workspace_bytes(int64_t B, int64_t N, int32_t tile_rows);
+int njode_schedule_build(const NjodeDesc* desc, const float* times, const int64_t* obs_offsets,
+                         int64_t B, int64_t N, int32_t tile_rows,
+                         int32_t* kenc, int32_t* perm, int32_t* tile_kmax, int64_t* tile_slot_off,
+                         int64_t* header, void* workspace, size_t workspace_bytes, void* stream);
+int njode_schedule_knots(const float* times, const int32_t* kenc, const int32_t* perm,
+                         const int32_t* tile_kmax, const int64_t* tile_slot_off,
+                         int64_t N, int64_t n_tiles, int32_t tile_rows, const NjodeDesc* desc,
+                         float* knots, void* stream);
+
+/* ---- forward sweep -----------------------------------------------------------------------------
+ * ckpt: float32 [S][total_slots][tile_rows][Hc] hidden state before every Euler step and after the
+ *       last one (Hc = njode_ckpt_row_floats); pass NULL for inference (no checkpoints written).
+ * workspace: njode_forward_workspace_bytes (re-laid-out weights). */
+int64_t njode_ckpt_row_floats(const NjodeDesc* desc);
+size_t  njode_forward_workspace_bytes(const NjodeDesc* desc);
+int njode_forward(const NjodeDesc* desc, const float* params, const float* times, const float* values,
+                  const int64_t* obs_offsets, int64_t B, int64_t N,
+                  const int32_t* kenc, const int32_t* perm, const int32_t* tile_kmax,
+                  const int64_t* tile_slot_off, const float* knots,
+                  int64_t n_tiles, int64_t total_slots, int32_t tile_rows,
+                  float* preds, float* preds_before, float* ckpt,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- loss: value and gradient w.r.t. preds / preds_before in one pass --------------------------
+ * loss_out: device float[1].  grad_* may be NULL (value only).  traj_scale = 1/B_global so that
+ * data-parallel ranks sum to the single-GPU loss (pass 1/B for one GPU).
+ * workspace: njode_loss_workspace_bytes(B). */
+size_t njode_loss_workspace_bytes(int64_t B);
+int njode_loss(const NjodeLossDesc* ldesc, const float* values, const float* preds,
+               const float* preds_before, const int64_t* obs_offsets, int64_t B, int64_t N,
+               int32_t d, int32_t M, float traj_scale,
+               float* loss_out, float* grad_preds, float* grad_preds_before,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- reverse sweep (discretise-then-optimise: exact adjoint of every Euler step) ----------------
+ * grad_params: float32 [njode_param_count], overwritten (not accumulated).
+ * workspace: njode_backward_workspace_bytes. */
+size_t njode_backward_workspace_bytes(const NjodeDesc* desc, int64_t n_tiles);
+int njode_backward(const NjodeDesc* desc, const float* params, const float* times, const float* values,
+                   const int64_t* obs_offsets, int64_t B, int64_t N,
+                   const int32_t* kenc, const int32_t* perm, const int32_t* tile_kmax,
+                   const int64_t* tile_slot_off, const float* knots,
+                   int64_t n_tiles, int64_t total_slots, int32_t tile_rows,
+                   const float* grad_preds, const float* grad_preds_before, const float* ckpt,
+                   float* grad_params, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- Adam on the flat parameter buffer (torch.optim.Adam semantics, weight_decay as L2-in-grad) --
+ * step is the 1-based step count AFTER this update. grad_scale multiplies grad first (e.g. 1.0). */
+int njode_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                    float lr, float beta1, float beta2, float eps, float weight_decay,
+                    int64_t step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NJODE_H_ */

@@ -1,0 +1,240 @@
+// njode_abi.cu -- extern "C" entry points of libnjode_b200.so (see include/njode.h).
+// Argument validation, flavour selection, weight re-layout and the deterministic reduction of the
+// per-CTA weight-gradient partial sums.  No torch headers, no persistent allocations.
+#include <stdarg.h>
+#include <string.h>
+
+#include "njode_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void njode_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* njode_last_error(void) { return g_err; }
+extern "C" int32_t njode_abi_version(void) { return NJODE_ABI_VERSION; }
+
+extern "C" int64_t njode_params_per_stack(const NjodeDesc* d) {
+  const char* why = nullptr;
+  if (!njode_desc_ok(d, &why)) { njode_set_error("njode_params_per_stack: %s", why); return -1; }
+  return njode_make_table(d).stack_floats;
+}
+extern "C" int32_t njode_num_stacks(const NjodeDesc* d) {
+  const char* why = nullptr;
+  if (!njode_desc_ok(d, &why)) { njode_set_error("njode_num_stacks: %s", why); return -1; }
+  return d->shared_network ? 1 : d->num_moments;
+}
+extern "C" int64_t njode_param_count(const NjodeDesc* d) {
+  const int64_t per = njode_params_per_stack(d);
+  return per < 0 ? -1 : per * njode_num_stacks(d);
+}
+
+// which flavour runs for this descriptor: 0 = error, NJODE_IMPL_GENERIC or NJODE_IMPL_TILED
+static int pick_impl(const NjodeDesc* d, const char** why) {
+  if (!njode_desc_ok(d, why)) return 0;
+  if (d->impl == NJODE_IMPL_TILED) {
+    if (!njode_tiled_supported(d)) { *why = "impl=TILED requested but this shape is not supported by the tiled kernels"; return 0; }
+    return NJODE_IMPL_TILED;
+  }
+  if (d->impl == NJODE_IMPL_AUTO && njode_tiled_supported(d)) return NJODE_IMPL_TILED;
+  if (d->impl != NJODE_IMPL_AUTO && d->impl != NJODE_IMPL_GENERIC) { *why = "unknown impl code"; return 0; }
+  if (!njode_generic_supported(d, why)) return 0;
+  return NJODE_IMPL_GENERIC;
+}
+
+extern "C" int32_t njode_tile_rows(const NjodeDesc* d) {
+  const char* why = nullptr;
+  const int impl = pick_impl(d, &why);
+  if (!impl) { njode_set_error("njode_tile_rows: %s", why); return -1; }
+  return impl == NJODE_IMPL_TILED ? NJODE_TILED_TILE_ROWS : NJODE_GENERIC_TILE_ROWS;
+}
+
+extern "C" int64_t njode_ckpt_row_floats(const NjodeDesc* d) {
+  const char* why = nullptr;
+  if (!njode_desc_ok(d, &why)) { njode_set_error("njode_ckpt_row_floats: %s", why); return -1; }
+  return d->hidden;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight re-layout: params_t holds every Linear weight input-major ((n_in) x (n_out)); biases copied
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool locate(const ParamTable& T, int e, int& net, int& l, bool& is_w) {
+  for (net = 0; net < 3; ++net)
+    for (l = 0; l <= T.L; ++l) {
+      const int nin = T.n_vec[net][l] + T.n_ext[net][l], nout = T.n_out[net][l];
+      if (e >= T.w_off[net][l] && e < T.w_off[net][l] + nin * nout) { is_w = true; return true; }
+      if (e >= T.b_off[net][l] && e < T.b_off[net][l] + nout) { is_w = false; return true; }
+    }
+  return false;
+}
+
+__global__ void k_transpose_params(ParamTable T, const float* __restrict__ p, float* __restrict__ pt, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t s = i / T.stack_floats;
+  const int e = (int)(i - s * T.stack_floats);      // index in input-major layout
+  int net, l;
+  bool is_w;
+  if (!locate(T, e, net, l, is_w)) return;
+  int64_t src = e;
+  if (is_w) {
+    const int nin = T.n_vec[net][l] + T.n_ext[net][l], nout = T.n_out[net][l];
+    const int rel = e - T.w_off[net][l];
+    const int k = rel / nout, j = rel - k * nout;
+    src = T.w_off[net][l] + j * nin + k;
+  }
+  pt[i] = p[s * T.stack_floats + src];
+}
+
+// grad[i] = sum over the workers of stack s (fixed order) of their partial; partials are input-major
+// (transposed = 1, generic flavour) or PyTorch layout (transposed = 0)
+__global__ void k_reduce_partials(ParamTable T, const float* __restrict__ partials, int n_workers, int transposed,
+                                  float* __restrict__ grad, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t s = i / T.stack_floats;
+  const int e = (int)(i - s * T.stack_floats);
+  float acc = 0.0f;
+  for (int w = (int)s; w < n_workers; w += T.S) acc += partials[(int64_t)w * T.stack_floats + e];
+  int64_t dst = e;
+  if (transposed) {
+    int net, l;
+    bool is_w;
+    if (!locate(T, e, net, l, is_w)) return;
+    if (is_w) {
+      const int nin = T.n_vec[net][l] + T.n_ext[net][l], nout = T.n_out[net][l];
+      const int rel = e - T.w_off[net][l];
+      const int k = rel / nout, j = rel - k * nout;
+      dst = T.w_off[net][l] + j * nin + k;
+    }
+  }
+  grad[s * T.stack_floats + dst] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int check_common(const char* fn, const NjodeDesc* desc, const float* params, const float* times,
+                        const float* values, int64_t B, int64_t N, int64_t n_tiles, int32_t tile_rows, int* impl) {
+  const char* why = nullptr;
+  *impl = pick_impl(desc, &why);
+  if (!*impl) NJODE_FAIL(NJODE_EINVAL, "%s: %s", fn, why);
+  if (!params || (N > 0 && (!times || !values))) NJODE_FAIL(NJODE_EINVAL, "%s: null input pointer", fn);
+  if (B < 0 || N < 0) NJODE_FAIL(NJODE_EINVAL, "%s: negative size", fn);
+  const int want = *impl == NJODE_IMPL_TILED ? NJODE_TILED_TILE_ROWS : NJODE_GENERIC_TILE_ROWS;
+  if (tile_rows != want) NJODE_FAIL(NJODE_EINVAL, "%s: schedule was built for tile_rows=%d, kernels need %d", fn, tile_rows, want);
+  if (n_tiles != (N + tile_rows - 1) / tile_rows) NJODE_FAIL(NJODE_EINVAL, "%s: n_tiles does not match N", fn);
+  return NJODE_OK;
+}
+
+static SweepArgs make_args(const NjodeDesc* desc, const float* params, const float* params_t, const float* times,
+                           const float* values, const int32_t* kenc, const int32_t* perm, const int32_t* tile_kmax,
+                           const int64_t* tile_slot_off, const float* knots, int64_t N, int64_t n_tiles,
+                           int64_t total_slots, int32_t tile_rows) {
+  SweepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.desc = *desc;
+  a.T = njode_make_table(desc);
+  a.params = params; a.params_t = params_t; a.times = times; a.values = values;
+  a.kenc = kenc; a.perm = perm; a.tile_kmax = tile_kmax; a.tile_slot_off = tile_slot_off; a.knots = knots;
+  a.N = N; a.n_tiles = n_tiles; a.total_slots = total_slots; a.tile_rows = tile_rows;
+  return a;
+}
+
+static size_t params_bytes(const NjodeDesc* d) {
+  return njode_align_up((size_t)njode_param_count(d) * sizeof(float), 256);
+}
+
+extern "C" size_t njode_forward_workspace_bytes(const NjodeDesc* desc) {
+  if (njode_param_count(desc) < 0) return 0;
+  return params_bytes(desc);
+}
+
+static int workers_for(const NjodeDesc* desc, int impl, int64_t n_tiles) {
+  return impl == NJODE_IMPL_TILED ? njode_tiled_workers(desc, n_tiles) : njode_generic_workers(desc, n_tiles);
+}
+
+extern "C" size_t njode_backward_workspace_bytes(const NjodeDesc* desc, int64_t n_tiles) {
+  const char* why = nullptr;
+  const int impl = pick_impl(desc, &why);
+  if (!impl) { njode_set_error("njode_backward_workspace_bytes: %s", why); return 0; }
+  const ParamTable T = njode_make_table(desc);
+  const int nw = workers_for(desc, impl, n_tiles);
+  return params_bytes(desc) + njode_align_up((size_t)nw * T.stack_floats * sizeof(float), 256);
+}
+
+static int relayout(const NjodeDesc* desc, const float* params, float* params_t, cudaStream_t st) {
+  const ParamTable T = njode_make_table(desc);
+  const int64_t total = (int64_t)T.stack_floats * T.S;
+  k_transpose_params<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(T, params, params_t, total);
+  NJODE_LAUNCH_OK("k_transpose_params");
+  return NJODE_OK;
+}
+
+extern "C" int njode_forward(const NjodeDesc* desc, const float* params, const float* times, const float* values,
+                             const int64_t* obs_offsets, int64_t B, int64_t N,
+                             const int32_t* kenc, const int32_t* perm, const int32_t* tile_kmax,
+                             const int64_t* tile_slot_off, const float* knots,
+                             int64_t n_tiles, int64_t total_slots, int32_t tile_rows,
+                             float* preds, float* preds_before, float* ckpt,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  int impl = 0;
+  int rc = check_common("njode_forward", desc, params, times, values, B, N, n_tiles, tile_rows, &impl);
+  if (rc) return rc;
+  (void)obs_offsets;
+  if (N > 0 && (!preds || !preds_before || !kenc || !perm || !tile_slot_off || !knots))
+    NJODE_FAIL(NJODE_EINVAL, "njode_forward: null schedule/output pointer");
+  if (workspace_bytes < njode_forward_workspace_bytes(desc)) NJODE_FAIL(NJODE_EWORKSPACE, "njode_forward: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N == 0) return NJODE_OK;
+  float* params_t = (float*)workspace;
+  rc = relayout(desc, params, params_t, st);
+  if (rc) return rc;
+  SweepArgs a = make_args(desc, params, params_t, times, values, kenc, perm, tile_kmax, tile_slot_off, knots, N, n_tiles,
+                          total_slots, tile_rows);
+  a.preds = preds; a.preds_before = preds_before; a.ckpt = ckpt;
+  a.n_workers = workers_for(desc, impl, n_tiles);
+  // preds_before of each trajectory's first observation stays 0 (jump_ode.py:161)
+  NJODE_CUDA_OK(cudaMemsetAsync(preds_before, 0, (size_t)N * desc->d_y * desc->num_moments * sizeof(float), st));
+  return impl == NJODE_IMPL_TILED ? njode_tiled_forward(a, st) : njode_generic_forward(a, st);
+}
+
+extern "C" int njode_backward(const NjodeDesc* desc, const float* params, const float* times, const float* values,
+                              const int64_t* obs_offsets, int64_t B, int64_t N,
+                              const int32_t* kenc, const int32_t* perm, const int32_t* tile_kmax,
+                              const int64_t* tile_slot_off, const float* knots,
+                              int64_t n_tiles, int64_t total_slots, int32_t tile_rows,
+                              const float* grad_preds, const float* grad_preds_before, const float* ckpt,
+                              float* grad_params, void* workspace, size_t workspace_bytes, void* stream) {
+  int impl = 0;
+  int rc = check_common("njode_backward", desc, params, times, values, B, N, n_tiles, tile_rows, &impl);
+  if (rc) return rc;
+  (void)obs_offsets;
+  if (!grad_params) NJODE_FAIL(NJODE_EINVAL, "njode_backward: null grad_params");
+  cudaStream_t st = (cudaStream_t)stream;
+  const ParamTable T = njode_make_table(desc);
+  const int64_t total = (int64_t)T.stack_floats * T.S;
+  if (N == 0) { NJODE_CUDA_OK(cudaMemsetAsync(grad_params, 0, total * sizeof(float), st)); return NJODE_OK; }
+  if (!grad_preds || !grad_preds_before || !ckpt || !kenc || !perm || !tile_slot_off || !knots)
+    NJODE_FAIL(NJODE_EINVAL, "njode_backward: null pointer (checkpoints are required; run forward with ckpt != NULL)");
+  if (workspace_bytes < njode_backward_workspace_bytes(desc, n_tiles))
+    NJODE_FAIL(NJODE_EWORKSPACE, "njode_backward: workspace too small");
+  float* params_t = (float*)workspace;
+  float* partials = (float*)((char*)workspace + params_bytes(desc));
+  rc = relayout(desc, params, params_t, st);
+  if (rc) return rc;
+  SweepArgs a = make_args(desc, params, params_t, times, values, kenc, perm, tile_kmax, tile_slot_off, knots, N, n_tiles,
+                          total_slots, tile_rows);
+  a.grad_preds = grad_preds; a.grad_preds_before = grad_preds_before; a.ckpt = const_cast<float*>(ckpt);
+  a.partials = partials;
+  a.n_workers = workers_for(desc, impl, n_tiles);
+  NJODE_CUDA_OK(cudaMemsetAsync(partials, 0, (size_t)a.n_workers * T.stack_floats * sizeof(float), st));
+  rc = impl == NJODE_IMPL_TILED ? njode_tiled_backward(a, st) : njode_generic_backward(a, st);
+  if (rc) return rc;
+  k_reduce_partials<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(T, partials, a.n_workers,
+                                                                    impl == NJODE_IMPL_GENERIC ? 1 : 0, grad_params, total);
+  NJODE_LAUNCH_OK("k_reduce_partials");
+  return NJODE_OK;
+}

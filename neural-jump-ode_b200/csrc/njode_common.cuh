@@ -1,0 +1,175 @@
+// njode_common.cuh -- shared host/device definitions for libnjode_b200 (sm_100a).
+// Parameter layout, activation maths and error plumbing.  See include/njode.h for the ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/njode.h"
+
+#define NJODE_LMAX 7          // n_hidden_layers <= 7  (L+1 <= 8 Linear layers per net)
+#define NJODE_WARP 32
+#define NJODE_FULL 0xffffffffu
+
+enum { NET_JUMP = 0, NET_ODE = 1, NET_OUT = 2 };
+
+// Offsets (in floats, relative to the start of one stack's block) and shapes of every Linear.
+// Layer (net,l): weight is (n_out x (n_vec+n_ext)) row-major; the first n_vec input columns are a
+// hidden vector, the last n_ext columns are per-row scalars (x for jump layer 0; x,t,dt for ode layer 0).
+struct ParamTable {
+  int32_t w_off[3][NJODE_LMAX + 1];
+  int32_t b_off[3][NJODE_LMAX + 1];
+  int32_t n_vec[3][NJODE_LMAX + 1];
+  int32_t n_ext[3][NJODE_LMAX + 1];
+  int32_t n_out[3][NJODE_LMAX + 1];
+  int32_t act[3][NJODE_LMAX + 1];   // activation applied after this layer?
+  int32_t stack_floats;             // parameters per stack
+  int32_t L, H, O, S, M, d_x, d_y;
+};
+
+static inline int njode_desc_ok(const NjodeDesc* d, const char** why) {
+  if (!d) { *why = "null descriptor"; return 0; }
+  if (d->d_x < 1 || d->d_y < 1 || d->hidden < 1 || d->num_moments < 1) { *why = "dimensions must be >= 1"; return 0; }
+  if (d->n_hidden_layers < 1 || d->n_hidden_layers > NJODE_LMAX) { *why = "n_hidden_layers must be in 1..7"; return 0; }
+  if (d->activation < 0 || d->activation > NJODE_ACT_SELU) { *why = "unknown activation code"; return 0; }
+  if (d->input_scaling < 0 || d->input_scaling > NJODE_SCALE_SIGMOID) { *why = "unknown input_scaling code"; return 0; }
+  if (d->has_dt && !(d->dt > 0.0f)) { *why = "dt_ode_step must be > 0"; return 0; }
+  return 1;
+}
+
+static inline ParamTable njode_make_table(const NjodeDesc* d) {
+  ParamTable T;
+  const int L = d->n_hidden_layers, H = d->hidden;
+  T.L = L; T.H = H; T.M = d->num_moments; T.d_x = d->d_x; T.d_y = d->d_y;
+  T.S = d->shared_network ? 1 : d->num_moments;
+  T.O = d->shared_network ? d->d_y * d->num_moments : d->d_y;
+  int off = 0;
+  for (int net = 0; net < 3; ++net) {
+    for (int l = 0; l <= NJODE_LMAX; ++l) {
+      T.w_off[net][l] = T.b_off[net][l] = T.n_vec[net][l] = T.n_ext[net][l] = T.n_out[net][l] = T.act[net][l] = 0;
+    }
+    for (int l = 0; l <= L; ++l) {
+      int n_vec = H, n_ext = 0, n_out = H, act = 1;
+      if (net == NET_JUMP) { if (l == 0) { n_vec = 0; n_ext = d->d_x; } act = 1; }
+      if (net == NET_ODE)  { if (l == 0) { n_ext = d->d_x + 2; } act = (l < L); }
+      if (net == NET_OUT)  { if (l == L) n_out = T.O; act = (l < L); }
+      T.n_vec[net][l] = n_vec; T.n_ext[net][l] = n_ext; T.n_out[net][l] = n_out; T.act[net][l] = act;
+      T.w_off[net][l] = off; off += n_out * (n_vec + n_ext);
+      T.b_off[net][l] = off; off += n_out;
+    }
+  }
+  T.stack_floats = off;
+  return T;
+}
+
+// ------------------------------------------------------------------------------------------------
+// activations (jump_ode.py:6-13) -- forward value and derivative expressed through the OUTPUT y,
+// so the reverse sweep only needs the recomputed / stored post-activation values.
+// ------------------------------------------------------------------------------------------------
+#define NJODE_SELU_LAMBDA 1.0507009873554804934193349852946f
+#define NJODE_SELU_ALPHA  1.6732632423543772848170429916717f
+
+template <int ACT>
+__device__ __forceinline__ float act_fwd(float a) {
+  if (ACT == NJODE_ACT_RELU) return fmaxf(a, 0.0f);
+  if (ACT == NJODE_ACT_TANH) return tanhf(a);
+  if (ACT == NJODE_ACT_SIGMOID) return 1.0f / (1.0f + expf(-a));
+  if (ACT == NJODE_ACT_ELU) return a > 0.0f ? a : expm1f(a);
+  if (ACT == NJODE_ACT_LEAKY_RELU) return a > 0.0f ? a : 0.01f * a;
+  /* SELU */ return NJODE_SELU_LAMBDA * (a > 0.0f ? a : NJODE_SELU_ALPHA * expm1f(a));
+}
+template <int ACT>
+__device__ __forceinline__ float act_grad_from_out(float y) {
+  if (ACT == NJODE_ACT_RELU) return y > 0.0f ? 1.0f : 0.0f;
+  if (ACT == NJODE_ACT_TANH) return 1.0f - y * y;
+  if (ACT == NJODE_ACT_SIGMOID) return y * (1.0f - y);
+  if (ACT == NJODE_ACT_ELU) return y > 0.0f ? 1.0f : y + 1.0f;
+  if (ACT == NJODE_ACT_LEAKY_RELU) return y > 0.0f ? 1.0f : 0.01f;
+  /* SELU */ return y > 0.0f ? NJODE_SELU_LAMBDA : y + NJODE_SELU_LAMBDA * NJODE_SELU_ALPHA;
+}
+__device__ __forceinline__ float act_fwd_rt(int act, float a) {
+  switch (act) {
+    case NJODE_ACT_RELU: return act_fwd<NJODE_ACT_RELU>(a);
+    case NJODE_ACT_TANH: return act_fwd<NJODE_ACT_TANH>(a);
+    case NJODE_ACT_SIGMOID: return act_fwd<NJODE_ACT_SIGMOID>(a);
+    case NJODE_ACT_ELU: return act_fwd<NJODE_ACT_ELU>(a);
+    case NJODE_ACT_LEAKY_RELU: return act_fwd<NJODE_ACT_LEAKY_RELU>(a);
+    default: return act_fwd<NJODE_ACT_SELU>(a);
+  }
+}
+__device__ __forceinline__ float act_grad_rt(int act, float y) {
+  switch (act) {
+    case NJODE_ACT_RELU: return act_grad_from_out<NJODE_ACT_RELU>(y);
+    case NJODE_ACT_TANH: return act_grad_from_out<NJODE_ACT_TANH>(y);
+    case NJODE_ACT_SIGMOID: return act_grad_from_out<NJODE_ACT_SIGMOID>(y);
+    case NJODE_ACT_ELU: return act_grad_from_out<NJODE_ACT_ELU>(y);
+    case NJODE_ACT_LEAKY_RELU: return act_grad_from_out<NJODE_ACT_LEAKY_RELU>(y);
+    default: return act_grad_from_out<NJODE_ACT_SELU>(y);
+  }
+}
+// input scaling s(.) of the ODE net (jump_ode.py:43-50, :57-58) and s' through the output
+__device__ __forceinline__ float scale_fwd_rt(int sc, float v) {
+  if (sc == NJODE_SCALE_TANH) return tanhf(v);
+  if (sc == NJODE_SCALE_SIGMOID) return 1.0f / (1.0f + expf(-v));
+  return v;
+}
+__device__ __forceinline__ float scale_grad_rt(int sc, float s) {
+  if (sc == NJODE_SCALE_TANH) return 1.0f - s * s;
+  if (sc == NJODE_SCALE_SIGMOID) return s * (1.0f - s);
+  return 1.0f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing (thread-local text, returned by njode_last_error)
+// ------------------------------------------------------------------------------------------------
+void njode_set_error(const char* fmt, ...);
+#define NJODE_FAIL(code, ...) do { njode_set_error(__VA_ARGS__); return (code); } while (0)
+#define NJODE_CUDA_OK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { \
+    njode_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    return NJODE_ECUDA; } } while (0)
+#define NJODE_LAUNCH_OK(what) do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) { \
+    njode_set_error("launch of %s failed: %s (%s:%d)", what, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    return NJODE_ECUDA; } } while (0)
+
+static inline size_t njode_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------
+// kernel flavours (implemented in njode_generic.cu / njode_tiled.cu)
+// ------------------------------------------------------------------------------------------------
+struct SweepArgs {
+  NjodeDesc desc;
+  ParamTable T;
+  const float* params;       // flat, PyTorch layout
+  const float* params_t;     // flat, every weight transposed to (in x out) ("kernel layout")
+  const float* times;
+  const float* values;
+  const int32_t* kenc;
+  const int32_t* perm;
+  const int32_t* tile_kmax;
+  const int64_t* tile_slot_off;
+  const float* knots;
+  int64_t N, n_tiles, total_slots;
+  int32_t tile_rows;
+  // forward outputs
+  float* preds;
+  float* preds_before;
+  float* ckpt;               // may be NULL in forward (inference)
+  // backward
+  const float* grad_preds;
+  const float* grad_preds_before;
+  float* partials;           // [n_workers][stack_floats] per-CTA weight-gradient partial sums
+  int32_t n_workers;         // CTAs (multiple of S); worker w serves stack w % S
+};
+
+#define NJODE_GENERIC_TILE_ROWS 32
+int  njode_generic_supported(const NjodeDesc* d, const char** why);
+int  njode_generic_workers(const NjodeDesc* d, int64_t n_tiles);
+int  njode_generic_forward(const SweepArgs& a, cudaStream_t st);
+int  njode_generic_backward(const SweepArgs& a, cudaStream_t st);
+
+#define NJODE_TILED_TILE_ROWS 128
+int  njode_tiled_supported(const NjodeDesc* d);
+int  njode_tiled_workers(const NjodeDesc* d, int64_t n_tiles);
+int  njode_tiled_forward(const SweepArgs& a, cudaStream_t st);
+int  njode_tiled_backward(const SweepArgs& a, cudaStream_t st);

@@ -1,0 +1,193 @@
+// njode_schedule.cu -- the float32 Euler step rule of the reference (jump_ode.py:188-203) on device,
+// and the K-descending tiling of observation units that the sweep kernels run on.
+//
+// The rule, reproduced bit for bit:   t = t_i;  while (fl32(t + dt) < t_next) t = fl32(t + dt);   // full steps
+//                                     if (t < t_next) one closing step to exactly t_next
+// About 65 % of intervals get a closing step of ~1e-8 because k float32 additions of dt land a few
+// ulp short of t_next; "observation indexing must be bit-exact" therefore means exact __fadd_rn and
+// the two exact comparisons -- never FMA contraction, never double.
+#include "njode_common.cuh"
+
+#define NJODE_BINS 2048
+#define NJODE_KCAP (1 << 24)
+
+__device__ __forceinline__ int count_steps(float t0, float t1, int has_dt, float dt) {
+  if (!has_dt) return 1;                               // jump_ode.py:188-190
+  int K = 0;
+  float t = t0;
+  while (true) {
+    const float tn = __fadd_rn(t, dt);
+    if (!(tn < t1)) break;                             // jump_ode.py:196
+    if (tn == t || K >= NJODE_KCAP) break;             // the reference would never terminate here
+    t = tn;
+    ++K;
+  }
+  if (t < t1) ++K;                                     // jump_ode.py:201
+  return K;
+}
+
+// one thread per trajectory: step counts of its intervals, histogram of counts, total step count
+__global__ void k_count_steps(const float* __restrict__ times, const int64_t* __restrict__ off, int64_t B,
+                              int has_dt, float dt, int32_t* __restrict__ kenc, int32_t* __restrict__ hist,
+                              unsigned long long* __restrict__ header) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long total = 0;
+  if (b < B) {
+    const int64_t lo = off[b], hi = off[b + 1];
+    for (int64_t o = lo; o < hi; ++o) {
+      int K = 0, has_next = 0;
+      if (o + 1 < hi) {
+        K = count_steps(times[o], times[o + 1], has_dt, dt);
+        has_next = 1;
+      }
+      kenc[o] = (K << 1) | has_next;
+      total += (unsigned long long)K;
+      atomicAdd(&hist[min(K, NJODE_BINS - 1)], 1);
+    }
+  }
+  // warp-reduce the step total before the single atomic
+  for (int s = 16; s > 0; s >>= 1) total += __shfl_xor_sync(NJODE_FULL, total, s);
+  if ((threadIdx.x & 31) == 0 && total) atomicAdd(&header[NJODE_HDR_TOTAL_STEPS], total);
+}
+
+// descending exclusive scan over the histogram: longest units first (longest-processing-time order)
+__global__ void k_scan_bins(const int32_t* __restrict__ hist, int32_t* __restrict__ start) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int acc = 0;
+    for (int b = NJODE_BINS - 1; b >= 0; --b) { start[b] = acc; acc += hist[b]; }
+  }
+}
+
+__global__ void k_scatter(const int32_t* __restrict__ kenc, int64_t N, int64_t Npad,
+                          const int32_t* __restrict__ start, int32_t* __restrict__ cursor,
+                          int32_t* __restrict__ perm) {
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o < N) {
+    const int bin = min(kenc[o] >> 1, NJODE_BINS - 1);
+    const int pos = start[bin] + atomicAdd(&cursor[bin], 1);
+    perm[pos] = (int32_t)o;
+  } else if (o < Npad) {
+    perm[o] = -1;
+  }
+}
+
+__global__ void k_tile_kmax(const int32_t* __restrict__ kenc, const int32_t* __restrict__ perm,
+                            int64_t n_tiles, int tile_rows, int32_t* __restrict__ tile_kmax) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  int km = 0;
+  for (int r = 0; r < tile_rows; ++r) {
+    const int u = perm[t * tile_rows + r];
+    if (u >= 0) km = max(km, kenc[u] >> 1);
+  }
+  tile_kmax[t] = km;
+}
+
+// single block: exclusive scan of (kmax+1) over tiles -> checkpoint slot offsets; header totals
+__global__ void k_tile_scan(const int32_t* __restrict__ tile_kmax, int64_t n_tiles,
+                            int64_t* __restrict__ slot_off, long long* __restrict__ header) {
+  __shared__ long long part[1024];
+  __shared__ int kmx[1024];
+  const int tid = threadIdx.x;
+  const int64_t chunk = (n_tiles + blockDim.x - 1) / blockDim.x;
+  const int64_t lo = min((int64_t)tid * chunk, n_tiles), hi = min(lo + chunk, n_tiles);
+  long long s = 0;
+  int km = 0;
+  for (int64_t t = lo; t < hi; ++t) { s += tile_kmax[t] + 1; km = max(km, tile_kmax[t]); }
+  part[tid] = s;
+  kmx[tid] = km;
+  __syncthreads();
+  if (tid == 0) {
+    long long acc = 0;
+    int m = 0;
+    for (int i = 0; i < (int)blockDim.x; ++i) { long long v = part[i]; part[i] = acc; acc += v; m = max(m, kmx[i]); }
+    slot_off[n_tiles] = acc;
+    header[NJODE_HDR_TOTAL_SLOTS] = acc;
+    header[NJODE_HDR_NUM_TILES] = n_tiles;
+    header[NJODE_HDR_KMAX] = m;
+  }
+  __syncthreads();
+  long long acc = part[tid];
+  for (int64_t t = lo; t < hi; ++t) { slot_off[t] = acc; acc += tile_kmax[t] + 1; }
+}
+
+// one thread per (tile,row): the float32 knots t_0..t_kmax of that row
+__global__ void k_fill_knots(const float* __restrict__ times, const int32_t* __restrict__ kenc,
+                             const int32_t* __restrict__ perm, const int32_t* __restrict__ tile_kmax,
+                             const int64_t* __restrict__ slot_off, int64_t Npad, int tile_rows,
+                             int has_dt, float dt, float* __restrict__ knots) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Npad) return;
+  const int64_t tile = idx / tile_rows;
+  const int r = (int)(idx - tile * tile_rows);
+  const int km = tile_kmax[tile];
+  float* dst = knots + slot_off[tile] * tile_rows + r;
+  const int u = perm[idx];
+  if (u < 0) {
+    for (int k = 0; k <= km; ++k) dst[(int64_t)k * tile_rows] = 0.0f;
+    return;
+  }
+  const int ke = kenc[u];
+  const int K = ke >> 1;
+  float t = times[u];
+  const float t1 = (ke & 1) ? times[u + 1] : t;
+  for (int k = 0; k <= km; ++k) {
+    dst[(int64_t)k * tile_rows] = t;
+    if (k < K) t = (k == K - 1) ? t1 : __fadd_rn(t, dt);   // closing step lands exactly on t_next
+  }
+  (void)has_dt;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t njode_schedule_workspace_bytes(int64_t B, int64_t N, int32_t tile_rows) {
+  (void)B; (void)N; (void)tile_rows;
+  return 3 * NJODE_BINS * sizeof(int32_t);
+}
+
+extern "C" int njode_schedule_build(const NjodeDesc* desc, const float* times, const int64_t* obs_offsets,
+                                    int64_t B, int64_t N, int32_t tile_rows,
+                                    int32_t* kenc, int32_t* perm, int32_t* tile_kmax, int64_t* tile_slot_off,
+                                    int64_t* header, void* workspace, size_t workspace_bytes, void* stream) {
+  const char* why = nullptr;
+  if (!njode_desc_ok(desc, &why)) NJODE_FAIL(NJODE_EINVAL, "njode_schedule_build: %s", why);
+  if (B < 0 || N < 0 || tile_rows < 1) NJODE_FAIL(NJODE_EINVAL, "njode_schedule_build: bad sizes");
+  if (N >= (1ll << 31) - 4096) NJODE_FAIL(NJODE_EINVAL, "njode_schedule_build: N must be < 2^31");
+  if (workspace_bytes < njode_schedule_workspace_bytes(B, N, tile_rows))
+    NJODE_FAIL(NJODE_EWORKSPACE, "njode_schedule_build: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n_tiles = (N + tile_rows - 1) / tile_rows;
+  const int64_t Npad = n_tiles * tile_rows;
+  int32_t* hist = (int32_t*)workspace;
+  int32_t* start = hist + NJODE_BINS;
+  int32_t* cursor = start + NJODE_BINS;
+  NJODE_CUDA_OK(cudaMemsetAsync(workspace, 0, 3 * NJODE_BINS * sizeof(int32_t), st));
+  NJODE_CUDA_OK(cudaMemsetAsync(header, 0, NJODE_HDR_WORDS * sizeof(int64_t), st));
+  if (N == 0) return NJODE_OK;
+  const int TB = 128;
+  k_count_steps<<<(unsigned)((B + TB - 1) / TB), TB, 0, st>>>(times, obs_offsets, B, desc->has_dt, desc->dt, kenc, hist,
+                                                             (unsigned long long*)header);
+  NJODE_LAUNCH_OK("k_count_steps");
+  k_scan_bins<<<1, 32, 0, st>>>(hist, start);
+  NJODE_LAUNCH_OK("k_scan_bins");
+  k_scatter<<<(unsigned)((Npad + 255) / 256), 256, 0, st>>>(kenc, N, Npad, start, cursor, perm);
+  NJODE_LAUNCH_OK("k_scatter");
+  k_tile_kmax<<<(unsigned)((n_tiles + 127) / 128), 128, 0, st>>>(kenc, perm, n_tiles, tile_rows, tile_kmax);
+  NJODE_LAUNCH_OK("k_tile_kmax");
+  k_tile_scan<<<1, 1024, 0, st>>>(tile_kmax, n_tiles, tile_slot_off, (long long*)header);
+  NJODE_LAUNCH_OK("k_tile_scan");
+  return NJODE_OK;
+}
+
+extern "C" int njode_schedule_knots(const float* times, const int32_t* kenc, const int32_t* perm,
+                                    const int32_t* tile_kmax, const int64_t* tile_slot_off,
+                                    int64_t N, int64_t n_tiles, int32_t tile_rows, const NjodeDesc* desc,
+                                    float* knots, void* stream) {
+  const char* why = nullptr;
+  if (!njode_desc_ok(desc, &why)) NJODE_FAIL(NJODE_EINVAL, "njode_schedule_knots: %s", why);
+  if (N == 0 || n_tiles == 0) return NJODE_OK;
+  const int64_t Npad = n_tiles * tile_rows;
+  k_fill_knots<<<(unsigned)((Npad + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      times, kenc, perm, tile_kmax, tile_slot_off, Npad, tile_rows, desc->has_dt, desc->dt, knots);
+  NJODE_LAUNCH_OK("k_fill_knots");
+  return NJODE_OK;
+}

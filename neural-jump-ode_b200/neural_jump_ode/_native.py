@@ -1,0 +1,103 @@
+"""ctypes binding of ``libnjode_b200.so`` (C-ABI declared in ``include/njode.h``).
+
+The library is the product path: if it is missing or does not export the expected symbols the
+import of the hot path fails loudly -- there is no CPU or eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get(
+    "NJODE_B200_LIB", os.path.normpath(os.path.join(_HERE, "..", "lib", "libnjode_b200.so")))
+
+ABI_VERSION = 1
+
+# enums (include/njode.h)
+ACT = {"relu": 0, "tanh": 1, "sigmoid": 2, "elu": 3, "leaky_relu": 4, "selu": 5}
+SCALE = {"identity": 0, "none": 0, "tanh": 1, "sigmoid": 2}
+VAR = {"direct": 0, "second_moment": 1}
+IMPL = {"auto": 0, "generic": 1, "tiled": 2}
+HDR_TOTAL_STEPS, HDR_TOTAL_SLOTS, HDR_NUM_TILES, HDR_KMAX, HDR_WORDS = 0, 1, 2, 3, 8
+
+
+class NjodeDesc(C.Structure):
+    _fields_ = [("d_x", C.c_int32), ("d_y", C.c_int32), ("hidden", C.c_int32),
+                ("n_hidden_layers", C.c_int32), ("num_moments", C.c_int32),
+                ("shared_network", C.c_int32), ("activation", C.c_int32),
+                ("input_scaling", C.c_int32), ("has_dt", C.c_int32), ("dt", C.c_float),
+                ("impl", C.c_int32), ("reserved", C.c_int32)]
+
+
+class NjodeLossDesc(C.Structure):
+    _fields_ = [("ignore_first_continuity", C.c_int32), ("variance_method", C.c_int32),
+                ("eps", C.c_float), ("w0", C.c_float), ("w1", C.c_float), ("reserved", C.c_int32)]
+
+
+_P = C.c_void_p
+_DESC = C.POINTER(NjodeDesc)
+_LDESC = C.POINTER(NjodeLossDesc)
+_I64, _I32, _SZ, _F = C.c_int64, C.c_int32, C.c_size_t, C.c_float
+
+# name -> (restype, argtypes); must list every symbol include/njode.h declares
+SIGNATURES = {
+    "njode_abi_version": (_I32, []),
+    "njode_last_error": (C.c_char_p, []),
+    "njode_params_per_stack": (_I64, [_DESC]),
+    "njode_param_count": (_I64, [_DESC]),
+    "njode_num_stacks": (_I32, [_DESC]),
+    "njode_tile_rows": (_I32, [_DESC]),
+    "njode_schedule_workspace_bytes": (_SZ, [_I64, _I64, _I32]),
+    "njode_schedule_build": (C.c_int, [_DESC, _P, _P, _I64, _I64, _I32, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "njode_schedule_knots": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I32, _DESC, _P, _P]),
+    "njode_ckpt_row_floats": (_I64, [_DESC]),
+    "njode_forward_workspace_bytes": (_SZ, [_DESC]),
+    "njode_forward": (C.c_int, [_DESC, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _I64, _I64, _I32,
+                                _P, _P, _P, _P, _SZ, _P]),
+    "njode_loss_workspace_bytes": (_SZ, [_I64]),
+    "njode_loss": (C.c_int, [_LDESC, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _F, _P, _P, _P, _P, _SZ, _P]),
+    "njode_backward_workspace_bytes": (_SZ, [_DESC, _I64]),
+    "njode_backward": (C.c_int, [_DESC, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _I64, _I64, _I32,
+                                 _P, _P, _P, _P, _P, _SZ, _P]),
+    "njode_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I64, _F, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise RuntimeError (never fall back) if it cannot be used."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"libnjode_b200.so not found at {LIB_PATH}. Build it with "
+            f"`python -c 'import __graft_entry__ as g; g.build()'` or `make -C neural-jump-ode_b200/csrc`. "
+            f"This package has no CPU / eager fallback for the hot path.")
+    import torch  # noqa: F401  (loads torch's libcudart first so both share one CUDA runtime)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise RuntimeError(f"{LIB_PATH} does not export {name}; rebuild the library") from e
+        fn.restype = res
+        fn.argtypes = args
+    v = lib.njode_abi_version()
+    if v != ABI_VERSION:
+        raise RuntimeError(f"{LIB_PATH} has ABI version {v}, this package needs {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().njode_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())

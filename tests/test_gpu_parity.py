@@ -1,0 +1,252 @@
+"""Parity of the CUDA hot path (through the C-ABI) with the reference's golden vectors and with the
+CPU oracle.  Needs a B200: `pytest -m gpu`.
+
+Stated tolerances (float32 path; two float32 summation orders of the reference itself already differ
+by ~2e-6):
+    preds / preds_before / every parameter gradient : 1e-5 max-norm relative per tensor
+    loss                                             : 5e-6 relative
+    per-observation Euler step counts, preds_before at each first observation == 0 : exact
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, golden_names, rel_err
+from oracle import njode_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+TOL_LOSS = 5e-6
+DEV = "cuda:0"
+
+
+def _model(g, impl="auto"):
+    from neural_jump_ode import NeuralJumpODE
+    m = NeuralJumpODE(**g["model"])
+    m.load_state_dict(g["params"])
+    m.kernel_impl = impl
+    return m.to(DEV)
+
+
+def _cfg(mk):
+    return orc.make_cfg(mk["input_dim"], mk["hidden_dim"], mk["output_dim"], mk.get("dt_ode_step"),
+                        mk.get("num_moments", 1), mk.get("n_hidden_layers", 1), mk.get("activation", "relu"),
+                        mk.get("shared_network", False), mk.get("input_scaling", "identity"))
+
+
+def _run(model, bt, bv, loss_kwargs):
+    from neural_jump_ode import nj_ode_loss
+    bt = [t.to(DEV) for t in bt]
+    bv = [v.to(DEV) for v in bv]
+    model.zero_grad()
+    preds, before = model(bt, bv)
+    loss = nj_ode_loss(bt, bv, preds, before, **loss_kwargs)
+    loss.backward()
+    return preds, before, loss
+
+
+@pytest.mark.parametrize("impl", ["generic", "auto"])
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_parity(name, impl):
+    """Same inputs and weights as the unmodified reference -> same preds, preds_before, loss, grads."""
+    g = load_golden(name)
+    model = _model(g, impl)
+    preds, before, loss = _run(model, g["batch_times"], g["batch_values"], g["loss"])
+    assert len(preds) == len(g["batch_times"])
+    assert [tuple(p.shape) for p in preds] == [(len(t), g["model"]["output_dim"], g["model"].get("num_moments", 1))
+                                               for t in g["batch_times"]]
+    assert rel_err(torch.cat(list(preds)).cpu(), g["preds"]) <= TOL
+    assert rel_err(torch.cat(list(before)).cpu(), g["preds_before"]) <= TOL
+    assert abs(loss.item() - g["ref_loss"]) <= TOL_LOSS * abs(g["ref_loss"])
+    first = torch.as_tensor(g["offsets"][:-1])
+    assert float(torch.cat(list(before)).cpu()[first].abs().max()) == 0.0
+    for k, p in model.named_parameters():
+        if not g["has_grad"][k]:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        assert p.grad is not None, k
+        assert rel_err(p.grad.cpu(), g["grads"][k]) <= TOL, k
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_step_counts_bit_exact(name):
+    """The device schedule takes exactly the Euler steps the reference took (float32 accumulation)."""
+    g = load_golden(name)
+    model = _model(g)
+    batch = model.pack([t.to(DEV) for t in g["batch_times"]], [v.to(DEV) for v in g["batch_values"]])
+    desc = model.descriptor()
+    K = batch.step_counts(desc).cpu().numpy()
+    want = np.concatenate([orc.step_counts(t.numpy(), g["model"].get("dt_ode_step")) for t in g["batch_times"]])
+    assert np.array_equal(K, want)
+    sched = batch.schedule(desc)
+    assert sched.total_steps == len(g["step_log"])
+    # knots reproduce every (t_last, t_next) pair bit for bit
+    R = sched.tile_rows
+    perm = sched.perm.cpu().numpy()
+    slot = sched.tile_slot_off.cpu().numpy()
+    knots = sched.knots.cpu().numpy()
+    got = {}
+    for idx, u in enumerate(perm):
+        if u < 0:
+            continue
+        tile, r = divmod(idx, R)
+        got[int(u)] = [knots[(slot[tile] + k) * R + r] for k in range(K[u] + 1)]
+    pairs = []
+    for u in range(len(K)):
+        pairs += [(got[u][k], got[u][k + 1]) for k in range(K[u])]
+    pairs = np.array(pairs, dtype=np.float32).reshape(-1, 2)
+    assert np.array_equal(pairs.view(np.uint32), g["step_log"].view(np.uint32))
+
+
+CASES = [
+    dict(input_dim=1, hidden_dim=32, output_dim=1, dt_ode_step=0.01, num_moments=2),
+    dict(input_dim=1, hidden_dim=32, output_dim=1, dt_ode_step=0.01, num_moments=2, shared_network=True),
+    dict(input_dim=1, hidden_dim=64, output_dim=1, dt_ode_step=0.01, num_moments=2),
+    dict(input_dim=1, hidden_dim=32, output_dim=1, dt_ode_step=None, num_moments=2),
+    dict(input_dim=1, hidden_dim=48, output_dim=1, dt_ode_step=0.02, num_moments=1, n_hidden_layers=2,
+         activation="tanh", input_scaling="tanh"),
+]
+
+
+def _random_batch(B, seed, n_steps=100, ragged=True):
+    rng = np.random.RandomState(seed)
+    bt, bv = [], []
+    for b in range(B):
+        n = rng.randint(2, 14) if ragged else 10
+        idx = np.sort(np.concatenate([[0, n_steps], rng.choice(np.arange(1, n_steps), n - 2, replace=False)]))
+        t = torch.linspace(0.0, 1.0, n_steps + 1)[torch.from_numpy(idx)]
+        v = torch.from_numpy((1.0 + 0.4 * rng.randn(n, 1)).astype(np.float32))
+        bt.append(t)
+        bv.append(v)
+    return bt, bv
+
+
+@pytest.mark.parametrize("impl", ["generic", "auto"])
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_oracle_parity_random(case, impl):
+    """Seeded ragged batch of 96 trajectories against the float64 interval-flattened oracle."""
+    from neural_jump_ode import NeuralJumpODE
+    mk = CASES[case]
+    torch.manual_seed(100 + case)
+    model = NeuralJumpODE(**mk)
+    P = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model.kernel_impl = impl
+    model = model.to(DEV)
+    bt, bv = _random_batch(96, seed=case)
+    lk = dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct")
+    preds, before, loss = _run(model, bt, bv, lk)
+    ref = orc.run_flat(P, _cfg(mk), bt, bv, lk, dtype=torch.float64)
+    assert rel_err(preds.packed.cpu(), ref["preds"]) <= TOL
+    assert rel_err(before.packed.cpu(), ref["preds_before"]) <= TOL
+    assert abs(loss.item() - float(ref["loss"])) <= TOL_LOSS * abs(float(ref["loss"]))
+    for k, p in model.named_parameters():
+        assert rel_err(p.grad.cpu(), ref["grads"][k]) <= TOL, k
+    desc = model.descriptor()
+    assert np.array_equal(preds.batch.step_counts(desc).cpu().numpy(), ref["K"])
+
+
+@pytest.mark.parametrize("variance_method", ["direct", "second_moment"])
+@pytest.mark.parametrize("ignore_first", [False, True])
+@pytest.mark.parametrize("M", [1, 2, 3])
+def test_loss_on_arbitrary_tensors(variance_method, ignore_first, M):
+    """nj_ode_loss on tensors that did not come from the model (utils/training.py:250), value and
+    gradient w.r.t. preds / preds_before, against the eager port."""
+    from neural_jump_ode import nj_ode_loss
+    g = torch.Generator().manual_seed(5 + M)
+    sizes = [1, 4, 7, 2, 9]
+    d = 2
+    bt = [torch.sort(torch.rand(n, generator=g))[0] for n in sizes]
+    bv = [torch.randn(n, d, generator=g) for n in sizes]
+    Y = [torch.randn(n, d, M, generator=g).requires_grad_(True) for n in sizes]
+    Yb = [torch.randn(n, d, M, generator=g).requires_grad_(True) for n in sizes]
+    w = [1.0, 10.0, 3.0][:max(M, 2)]
+    ref = orc.loss_port(bv, Y, Yb, ignore_first_continuity=ignore_first, moment_weights=w,
+                        variance_method=variance_method)
+    ref.backward()
+    Yc = [y.detach().to(DEV).requires_grad_(True) for y in Y]
+    Ybc = [y.detach().to(DEV).requires_grad_(True) for y in Yb]
+    wt = torch.tensor(w, device=DEV)     # the reference Trainer passes a device tensor
+    got = nj_ode_loss([t.to(DEV) for t in bt], [v.to(DEV) for v in bv], Yc, Ybc,
+                      ignore_first_continuity=ignore_first, moment_weights=wt, variance_method=variance_method)
+    got.backward()
+    assert got.dim() == 0
+    assert abs(got.item() - ref.item()) <= TOL_LOSS * abs(ref.item())
+    for a, b in zip(Yc + Ybc, Y + Yb):
+        assert rel_err(a.grad.cpu(), b.grad) <= TOL
+
+
+def test_packed_path_equals_list_path_and_no_grad():
+    from neural_jump_ode import NeuralJumpODE, nj_ode_loss, PackedBatch
+    torch.manual_seed(3)
+    model = NeuralJumpODE(1, 32, 1, dt_ode_step=0.01, num_moments=2).to(DEV)
+    bt, bv = _random_batch(40, seed=9)
+    btc, bvc = [t.to(DEV) for t in bt], [v.to(DEV) for v in bv]
+    p1, b1 = model(btc, bvc)
+    batch = PackedBatch.from_lists(bt, bv, device=DEV)       # host lists -> one H2D copy
+    p2, b2 = model.forward_packed(batch)
+    assert torch.equal(p1.packed, p2) and torch.equal(b1.packed, b2)
+    l1 = nj_ode_loss(btc, bvc, p1, b1, ignore_first_continuity=True, moment_weights=[1.0, 10.0])
+    l2 = nj_ode_loss(batch, None, p2, b2, ignore_first_continuity=True, moment_weights=[1.0, 10.0])
+    assert l1.item() == l2.item()
+    model.eval()
+    with torch.no_grad():
+        p3, b3 = model(btc, bvc)
+        l3 = nj_ode_loss(btc, bvc, p3, b3, ignore_first_continuity=True, moment_weights=[1.0, 10.0])
+    assert not p3.packed.requires_grad and torch.equal(p3.packed, p2)
+    assert l3.item() == l1.item()
+    y, yb = model.forward_single(btc[0], bvc[0])
+    assert torch.equal(y, p1[0]) and torch.equal(yb, b1[0])
+
+
+def test_submodules_and_euler_step_agree_with_kernels():
+    """plotting.py drives jump_nns / euler_step / output_nns directly; they must describe the same model."""
+    from neural_jump_ode import NeuralJumpODE
+    torch.manual_seed(4)
+    model = NeuralJumpODE(1, 32, 1, dt_ode_step=None, num_moments=2).to(DEV)
+    t = torch.tensor([0.0, 0.37], device=DEV)
+    x = torch.tensor([[0.8], [1.1]], device=DEV)
+    with torch.no_grad():
+        preds, before = model([t], [x])
+        h = [model.jump_nns[m](x[:1]) for m in range(2)]
+        y0 = torch.stack([model.output_nns[m](h[m]) for m in range(2)], dim=-1)
+        h1 = model.euler_step(h, x[:1], t[0], t[1])
+        y1 = torch.stack([model.output_nns[m](h1[m]) for m in range(2)], dim=-1)
+    assert rel_err(preds[0][0].cpu(), y0[0].cpu()) <= TOL
+    assert rel_err(before[0][1].cpu(), y1[0].cpu()) <= TOL
+
+
+def test_adam_kernel_matches_torch():
+    from neural_jump_ode import _native as nat
+    lib = nat.load()
+    torch.manual_seed(0)
+    n = 10007
+    p = torch.randn(n, device=DEV)
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-3, weight_decay=5e-4)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    stream = torch.cuda.current_stream().cuda_stream
+    for step in range(1, 6):
+        g = torch.randn(n, device=DEV)
+        ref.grad = g.clone()
+        opt.step()
+        nat.check(lib.njode_adam_step(nat.ptr(p), nat.ptr(g), nat.ptr(m), nat.ptr(v), n, 1e-3, 0.9, 0.999, 1e-8,
+                                      5e-4, step, 1.0, stream), "njode_adam_step")
+    assert rel_err(p.cpu(), ref.detach().cpu()) <= 1e-6
+
+
+def test_error_paths():
+    from neural_jump_ode import NeuralJumpODE, nj_ode_loss
+    m = NeuralJumpODE(1, 8, 1)
+    with pytest.raises(RuntimeError):
+        m([torch.tensor([0.0, 1.0])], [torch.tensor([[1.0], [2.0]])])     # CPU parameters: no fallback
+    m = NeuralJumpODE(1, 8, 1, dropout_rate=0.1).to(DEV)
+    with pytest.raises(NotImplementedError):
+        m([torch.tensor([0.0, 1.0], device=DEV)], [torch.tensor([[1.0], [2.0]], device=DEV)])
+    m.eval()
+    m([torch.tensor([0.0, 1.0], device=DEV)], [torch.tensor([[1.0], [2.0]], device=DEV)])
+    with pytest.raises(ValueError):
+        nj_ode_loss([], [], [], [], variance_method="nope")
+    with pytest.raises(ValueError):
+        NeuralJumpODE(1, 8, 1, input_scaling="bogus")

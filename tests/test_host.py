@@ -1,0 +1,110 @@
+"""CPU-only checks of the host side: import surface, state_dict layout, init RNG order, the C-ABI
+library loads and exports every symbol include/njode.h declares (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, load_golden, golden_names
+
+
+def test_import_surface():
+    import neural_jump_ode
+    from neural_jump_ode import NeuralJumpODE, nj_ode_loss          # reference __init__.py:3
+    from neural_jump_ode.models import JumpNN, ODEFunc, OutputNN    # reference models/__init__.py:3
+    assert neural_jump_ode.__version__ == "0.1.0"
+    assert callable(nj_ode_loss) and callable(NeuralJumpODE)
+    assert all(callable(c) for c in (JumpNN, ODEFunc, OutputNN))
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_state_dict_and_init_match_reference(name):
+    """Same keys, shapes AND values as the reference under torch.manual_seed(0): parameters are
+    created in the reference's order, so old checkpoints load and seeds reproduce."""
+    from neural_jump_ode import NeuralJumpODE
+    g = load_golden(name)
+    torch.manual_seed(0)
+    m = NeuralJumpODE(**g["model"])
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(g["params"].keys()) or set(sd) == set(g["params"])
+    for k, v in sd.items():
+        assert torch.equal(v, g["params"][k]), k
+    m.load_state_dict(g["params"])
+    flat = m.flat_parameters()
+    assert sum(p.numel() for p in flat) == sum(p.numel() for p in m.parameters())
+    assert len({id(p) for p in flat}) == len(list(m.parameters()))
+
+
+def test_constructor_compat():
+    from neural_jump_ode import NeuralJumpODE
+    m = NeuralJumpODE(1, 16, 1)                                      # positional, as in the reference tests
+    assert m.jump_nns is not None and m.jump_nn is None and m.num_moments == 1
+    m = NeuralJumpODE(input_dim=1, hidden_dim=16, output_dim=1, n_steps_between=3)   # stale README kwarg
+    assert m.dt_ode_step is None
+    m = NeuralJumpODE(1, 16, 1, num_moments=2, shared_network=True, activation="identity")
+    assert m.jump_nn is not None and m.jump_nns is None
+    assert isinstance(m.jump_nn.net[1], torch.nn.ReLU)              # unknown activation -> ReLU
+    assert m.output_nn.net[3].weight.shape == (2, 16)
+    for attr in ("num_moments", "shared_network", "variance_method", "dt_ode_step", "output_dim"):
+        assert hasattr(m, attr)
+    with pytest.raises(ValueError):
+        NeuralJumpODE(1, 16, 1, input_scaling="bogus")
+
+
+def test_submodules_callable_on_cpu():
+    """The small sub-modules are ordinary torch modules (plotting drives them); only the batched
+    hot path is CUDA-only."""
+    from neural_jump_ode import NeuralJumpODE
+    m = NeuralJumpODE(1, 8, 1, num_moments=2)
+    x = torch.tensor([[0.5]])
+    h = [m.jump_nns[i](x) for i in range(2)]
+    h2 = m.euler_step(h, x, torch.tensor(0.0), torch.tensor(0.1))
+    assert h2[0].shape == (1, 8) and m.output_nns[1](h2[1]).shape == (1, 1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m([torch.tensor([0.0, 1.0])], [torch.tensor([[1.0], [2.0]])])
+
+
+def test_abi_library_exports_every_declared_symbol():
+    from neural_jump_ode import _native as nat
+    hdr = open(os.path.join(ROOT, "include", "njode.h")).read()
+    declared = set(re.findall(r"\b(njode_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(nat.SIGNATURES), declared ^ set(nat.SIGNATURES)
+    lib = ctypes.CDLL(nat.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib2 = nat.load()
+    assert lib2.njode_abi_version() == nat.ABI_VERSION
+
+
+def test_abi_param_count_and_validation():
+    from neural_jump_ode import NeuralJumpODE, _native as nat
+    lib = nat.load()
+    for kw in (dict(num_moments=2), dict(num_moments=2, shared_network=True), dict(n_hidden_layers=3, hidden_dim=128)):
+        args = dict(input_dim=1, hidden_dim=32, output_dim=1)
+        args.update(kw)
+        m = NeuralJumpODE(**args)
+        d = m.descriptor()
+        assert lib.njode_param_count(d) == sum(p.numel() for p in m.parameters())
+        assert lib.njode_num_stacks(d) == (1 if m.shared_network else m.num_moments)
+    bad = NeuralJumpODE(1, 32, 1).descriptor()
+    bad.n_hidden_layers = 0
+    assert lib.njode_param_count(bad) == -1
+    assert b"n_hidden_layers" in lib.njode_last_error()
+
+
+def test_packed_batch_host_logic():
+    from neural_jump_ode import PackedBatch
+    bt = [torch.tensor([0.0, 0.5, 1.0]), torch.tensor([0.0, 0.3])]
+    bv = [torch.tensor([[1.0], [1.2], [0.9]]), torch.tensor([[0.5], [0.7]])]
+    b = PackedBatch.from_lists(bt, bv)
+    assert b.B == 2 and b.N == 5 and b.offsets.tolist() == [0, 3, 5] and b.sizes == [3, 2]
+    parts = b.split(torch.arange(5.0).view(5, 1))
+    assert [p.shape[0] for p in parts] == [3, 2]
+    assert b.came_from(bt, bv) and not b.came_from(list(bt), bv)
+    with pytest.raises(ValueError):
+        PackedBatch.from_lists(bt, bv[:1])
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        from neural_jump_ode import NeuralJumpODE
+        b.schedule(NeuralJumpODE(1, 8, 1, dt_ode_step=0.1).descriptor())
