@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- trajectory-ODE-steps/s (fwd+bwd, device-timed) of the Neural Jump ODE hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference --steps K --warmup W    (CPU port of the reference on a bounded sample)
+
+One "step" = forward sweep + nj_ode_loss + reverse sweep over one batch of the workload (Adam and
+host packing excluded).  Default workload = BASELINE.json configs[1]: experiment_ou.py
+--shared-network --cache-data, batch 4096 per GPU, n_steps 100, obs 0.1, hidden 32, 1 layer,
+activation 'identity' (-> ReLU), 2 moments, dt_ode_step 0.01 (run_ou.sh:36).  Data is synthetic
+(on-device OU paths of that shape), weights are random-init of that architecture.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "neural-jump-ode_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "ou_shared_b4096": dict(
+        process="ornstein_uhlenbeck", pkw=dict(theta=1.0, mu=0.5, sigma=0.3, x0=0.0), B=4096, n_steps=100, T=1.0,
+        obs_fraction=0.1, model=dict(input_dim=1, hidden_dim=32, output_dim=1, dt_ode_step=0.01, num_moments=2,
+                                     n_hidden_layers=1, activation="identity", shared_network=True),
+        loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct")),
+    # BASELINE.json configs[0] at batch 128 (the reference's CPU-runnable case)
+    "bs_sep_b128": dict(
+        process="black_scholes", pkw=dict(mu=0.1, sigma=0.5, x0=1.0), B=128, n_steps=100, T=1.0,
+        obs_fraction=0.1, model=dict(input_dim=1, hidden_dim=32, output_dim=1, dt_ode_step=0.01, num_moments=2),
+        loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct")),
+    # BASELINE.json configs[2]
+    "heston_sep_b262144": dict(
+        process="heston", pkw=dict(mu=0.5, kappa=2.0, theta=0.04, xi=0.5, rho=-0.5, x0=1.0, v0=0.04), B=262144,
+        n_steps=200, T=1.0, obs_fraction=0.1,
+        model=dict(input_dim=1, hidden_dim=32, output_dim=1, dt_ode_step=0.005, num_moments=2),
+        loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct")),
+}
+
+
+def mac_counts(mk):
+    H, dx, L = mk["hidden_dim"], mk["input_dim"], mk.get("n_hidden_layers", 1)
+    M = mk.get("num_moments", 1)
+    shared = mk.get("shared_network", False)
+    S = 1 if shared else M
+    O = mk["output_dim"] * (M if shared else 1)
+    return dict(S=S, ode=H * (H + dx + 2) + L * H * H, jump=dx * H + L * H * H, out=L * H * H + H * O)
+
+
+def algorithmic_flops(mk, total_steps, n_obs_total, n_traj):
+    """F = 6*S*[E*MAC_ode + n*MAC_jump + (2n-1)*MAC_out] (2 fwd + 4 bwd flop per MAC)."""
+    c = mac_counts(mk)
+    macs = c["S"] * (total_steps * c["ode"] + n_obs_total * c["jump"] + (2 * n_obs_total - n_traj) * c["out"])
+    return dict(fwd=2.0 * macs, bwd=4.0 * macs, total=6.0 * macs, per_step_ode=6.0 * c["S"] * c["ode"])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_baseline(wl, n_traj, repeats=1):
+    """Time the CPU port of the reference (oracle.run_port: same per-step eager op granularity as
+    jump_ode.py) on `n_traj` trajectories of the workload.  Returns (steps/s, steps, seconds)."""
+    from oracle import njode_oracle as orc
+    from neural_jump_ode.simulation import make_packed_batch
+    mk = wl["model"]
+    batch = make_packed_batch(wl["process"], n_traj, wl["obs_fraction"], n_steps=wl["n_steps"], T=wl["T"],
+                              device="cpu", seed=1234, **wl["pkw"])
+    bt = list(torch.split(batch.times, batch.sizes))
+    bv = list(torch.split(batch.values, batch.sizes))
+    cfg = orc.make_cfg(mk["input_dim"], mk["hidden_dim"], mk["output_dim"], mk.get("dt_ode_step"),
+                       mk.get("num_moments", 1), mk.get("n_hidden_layers", 1), mk.get("activation", "relu"),
+                       mk.get("shared_network", False), mk.get("input_scaling", "identity"))
+    P = orc.init_params(cfg, seed=0)
+    best, steps = None, 0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        r = orc.run_port(P, cfg, bt, bv, wl["loss"])
+        dt = time.perf_counter() - t0
+        steps = len(r["step_log"])
+        best = dt if best is None else min(best, dt)
+    return steps / best, steps, best
+
+
+def run_reference(args, wl, name):
+    """--impl reference: the reference's algorithm on the host cores.  /root/reference (pure Python) does
+    not exist on the GPU box and cannot be compiled into oracle/_ref, so the oracle port is timed."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_traj = min(args.cpu_sample, 96)           # bounded sample per step (~3 s of CPU work)
+    for _ in range(args.warmup):
+        cpu_port_baseline(wl, max(2, n_traj // 8))
+    t_tot, steps_tot = 0.0, 0
+    for _ in range(args.steps):
+        sps, steps, sec = cpu_port_baseline(wl, n_traj)
+        t_tot += sec
+        steps_tot += steps
+    value = steps_tot / t_tot
+    sample = f"{n_traj} trajectories of {name} per step ({steps_tot // args.steps} trajectory-ODE-steps), fwd+loss+bwd"
+    out = {"impl": "reference", "metric": "trajectory-ODE-steps/sec (fwd+bwd)", "value": value,
+           "unit": "trajectory-ODE-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "config": {"workload": name, "sample": sample},
+           "cpu_baseline": {"value": value, "unit": "trajectory-ODE-steps/s", "cores": torch.get_num_threads(),
+                            "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": "trajectory-ODE-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ou_shared_b4096", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="override trajectories per GPU")
+    ap.add_argument("--kernel-impl", default="auto", choices=["auto", "generic", "tiled"])
+    ap.add_argument("--cpu-sample", type=int, default=384, help="trajectories in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    name = args.workload
+    wl = dict(WORKLOADS[name])
+    if args.batch:
+        wl["B"] = args.batch
+
+    if args.impl == "reference":
+        run_reference(args, wl, name)
+        return
+
+    import torch.distributed as dist
+    from neural_jump_ode import NeuralJumpODE, nj_ode_loss, PackedBatch, _native as nat
+    from neural_jump_ode.simulation import make_packed_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = nat.load()
+
+    mk = wl["model"]
+    torch.manual_seed(0)                       # identical replicas on every rank
+    model = NeuralJumpODE(**mk)
+    model.kernel_impl = args.kernel_impl
+    model = model.to(dev)
+    params = model.flat_parameters()
+    B = wl["B"]                                # per GPU: weak scaling
+    B_global = B * world
+    batch = make_packed_batch(wl["process"], B, wl["obs_fraction"], n_steps=wl["n_steps"], T=wl["T"], device=dev,
+                              seed=1000 + rank, **wl["pkw"])
+    desc = model.descriptor()
+    sched = batch.schedule(desc)               # --cache-data: schedule built once, outside the timed region
+    total_steps_rank = sched.total_steps
+    lk = wl["loss"]
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    def step():
+        for p in params:
+            p.grad = None
+        preds, before = model.forward_packed(batch)
+        loss = nj_ode_loss(batch, None, preds, before, traj_scale=1.0 / B_global, **lk)
+        loss.backward()
+        if world > 1:                          # one all-reduce of the flat gradient (+ loss) over NVLink
+            flat = torch.cat([p.grad.reshape(-1) for p in params] + [loss.detach().reshape(1)])
+            dist.all_reduce(flat)
+        return loss
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+
+    # ---- timed region: K steps, device-timed with CUDA events, L2 flushed between steps ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    nat.launch_count = 0
+    sync_all()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record()
+        step()
+        ev[i][1].record()
+    sync_all()
+    wall = time.perf_counter() - wall0
+    launches = nat.launch_count
+    clocks = sampler.stop() if rank == 0 else None
+    ms = [a.elapsed_time(b) for a, b in ev]
+    t_dev = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+    steps_all = torch.tensor([float(total_steps_rank)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(steps_all)
+    t_total_ms = float(t_dev.item())
+    value = float(steps_all.item()) * args.steps / (t_total_ms * 1e-3)
+
+    # ---- dominant kernel (reverse sweep) timed alone with events on its stream -> roofline ----
+    bwd_ms = []
+    for i in range(min(args.steps, 10)):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        # torch.cuda.Event creates its cudaEvent lazily on first record: record once so the handle exists
+        e0.record(); e1.record()
+        torch.cuda.synchronize()
+        nat.check(lib.njode_set_kernel_timing(2, ctypes.c_void_p(e0.cuda_event), ctypes.c_void_p(e1.cuda_event)),
+                  "njode_set_kernel_timing")
+        step()
+        torch.cuda.synchronize()
+        bwd_ms.append(e0.elapsed_time(e1))
+    bwd_ms.sort()
+    bwd_med = bwd_ms[len(bwd_ms) // 2]
+    peak = ctypes.c_float(0.0)
+    nat.check(lib.njode_ffma_peak(ctypes.byref(peak)), "njode_ffma_peak")
+    fl = algorithmic_flops(mk, total_steps_rank, batch.N, batch.B)
+    achieved = fl["bwd"] / (bwd_med * 1e-3) * 1e-12
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    measured = json.load(open(peaks_file)) if os.path.exists(peaks_file) else {}
+    roofline = {"bound": "fp32-fma", "kernel": "reverse sweep (njode_backward main kernel)", "achieved": achieved,
+                "peak": float(peak.value), "unit": "TFLOP/s", "frac": achieved / float(peak.value), "traffic": None,
+                "peak_source": "FFMA micro-kernel run in this process (njode_ffma_peak); MEASURED_PEAKS.json has no "
+                               "FP32-FMA figure",
+                "kernel_ms": bwd_med, "algorithmic_flop_per_launch": fl["bwd"],
+                "frac_of_measured_bf16_tensor_peak": (achieved / measured["bf16_tflops"]) if measured.get("bf16_tflops") else None,
+                "whole_step_tflops": fl["total"] * args.steps / (t_total_ms * 1e-3) * 1e-12 / max(world, 1)}
+
+    # ---- end to end through the public API: pinned host inputs -> H2D -> schedule -> fwd/loss/bwd -> loss D2H ----
+    h_times = batch.times.cpu().pin_memory()
+    h_values = batch.values.cpu().pin_memory()
+    h_off = batch.offsets.cpu().pin_memory()
+    sizes = batch.sizes
+
+    def e2e_step():
+        b = PackedBatch(h_times.to(dev, non_blocking=True), h_values.to(dev, non_blocking=True),
+                        h_off.to(dev, non_blocking=True), sizes)
+        for p in params:
+            p.grad = None
+        preds, before = model.forward_packed(b)
+        loss = nj_ode_loss(b, None, preds, before, traj_scale=1.0 / B_global, **lk)
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in params] + [loss.detach().reshape(1)])
+            dist.all_reduce(flat)
+        return loss.item()                     # device -> host read of the step's result
+
+    for _ in range(3):
+        e2e_step()
+    sync_all()
+    e2e_ev = []
+    for _ in range(args.steps):
+        flush.zero_()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        e2e_step()
+        b_.record()
+        e2e_ev.append((a, b_))
+    sync_all()
+    t_e2e = torch.tensor([sum(a.elapsed_time(b_) for a, b_ in e2e_ev)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = float(steps_all.item()) * args.steps / (float(t_e2e.item()) * 1e-3)
+    h2d = h_times.numel() * 4 + h_values.numel() * 4 + h_off.numel() * 8
+    d2h = 4 + 8 * nat.HDR_WORDS
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            sps, steps, sec = cpu_port_baseline(wl, args.cpu_sample)
+            cpu = {"value": sps, "unit": "trajectory-ODE-steps/s", "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": f"{args.cpu_sample} trajectories of {name} ({steps} trajectory-ODE-steps, {sec:.1f} s), "
+                             f"fwd+loss+bwd, oracle.run_port (eager per-step port of jump_ode.py)",
+                   "host_cpus": os.cpu_count()}
+        out = {"metric": "trajectory-ODE-steps/sec (fwd+bwd, device-timed)", "value": value,
+               "unit": "trajectory-ODE-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": t_total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": name, "process": wl["process"], "batch_per_gpu": B, "global_batch": B_global,
+                          "n_steps": wl["n_steps"], "obs_fraction": wl["obs_fraction"], "model": mk,
+                          "trajectory_ode_steps_per_gpu": total_steps_rank, "observations_per_gpu": batch.N,
+                          "parallelism": f"dp{world}", "kernel_impl": args.kernel_impl,
+                          "tile_rows": sched.tile_rows, "l2": "flushed between steps (256 MiB write)",
+                          "flop_per_trajectory_step_ode": fl["per_step_ode"]},
+               "e2e": {"value": e2e_value, "unit": "trajectory-ODE-steps/s", "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": d2h, "includes": "H2D of packed inputs from pinned memory, schedule "
+                       "build, fwd, loss, bwd, loss.item()"},
+               "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+               "wall_s_timed_region": wall}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

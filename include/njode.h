@@ -167,6 +167,16 @@ int njode_adam_step(float* params, const float* grads, float* exp_avg, float* ex
                     float lr, float beta1, float beta2, float eps, float weight_decay,
                     int64_t step, float grad_scale, void* stream);
 
+
+/* ---- measurement hooks (bench.py) ---------------------------------------------------------------
+ * njode_set_kernel_timing: the next njode_forward (which=1) / njode_backward (which=2) call records the
+ * two caller-owned cudaEvent_t around its main sweep kernel only (on the call's stream).  One-shot;
+ * pass NULLs to clear.  njode_ffma_peak: runs an FFMA-only kernel on the current device and returns the
+ * measured dense FP32 FMA throughput in TFLOP/s (the roofline denominator of the FP32 path; it is not
+ * in MEASURED_PEAKS.json).  Synchronises the device. */
+int njode_set_kernel_timing(int32_t which, void* ev_start, void* ev_stop);
+int njode_ffma_peak(float* tflops_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,70 @@ void njode_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* njode_last_error(void) { return g_err; }
+
+// ---- measurement hooks -------------------------------------------------------------------------
+#include <atomic>
+static std::atomic<void*> g_ev[3][2];
+extern "C" int njode_set_kernel_timing(int32_t which, void* ev_start, void* ev_stop) {
+  if (which < 1 || which > 2) NJODE_FAIL(NJODE_EINVAL, "njode_set_kernel_timing: which must be 1 (forward) or 2 (backward)");
+  g_ev[which][0].store(ev_start);
+  g_ev[which][1].store(ev_stop);
+  return NJODE_OK;
+}
+void njode_timing_begin(int which, cudaStream_t st) {
+  void* e = g_ev[which][0].exchange(nullptr);
+  if (e) cudaEventRecord((cudaEvent_t)e, st);
+}
+void njode_timing_end(int which, cudaStream_t st) {
+  void* e = g_ev[which][1].exchange(nullptr);
+  if (e) cudaEventRecord((cudaEvent_t)e, st);
+}
+
+__global__ void __launch_bounds__(256) k_ffma_peak(float* out, int iters, float a, float b) {
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = threadIdx.x * 0.001f + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], a, b);
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int njode_ffma_peak(float* tflops_host) {
+  if (!tflops_host) NJODE_FAIL(NJODE_EINVAL, "njode_ffma_peak: null output");
+  int dev = 0, sms = 0;
+  NJODE_CUDA_OK(cudaGetDevice(&dev));
+  NJODE_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int blocks = sms * 8, iters = 8000;
+  float* out = nullptr;
+  NJODE_CUDA_OK(cudaMalloc(&out, (size_t)blocks * 256 * sizeof(float)));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(e0);
+    k_ffma_peak<<<blocks, 256>>>(out, iters, 1.0001f, 0.5f);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  NJODE_LAUNCH_OK("k_ffma_peak");
+  const double flops = 2.0 * blocks * 256.0 * iters * 8 * 16;
+  *tflops_host = (float)(flops / best * 1e-9);
+  return NJODE_OK;
+}
 extern "C" int32_t njode_abi_version(void) { return NJODE_ABI_VERSION; }
 
 extern "C" int64_t njode_params_per_stack(const NjodeDesc* d) {

@@ -132,6 +132,10 @@ void njode_set_error(const char* fmt, ...);
     njode_set_error("launch of %s failed: %s (%s:%d)", what, cudaGetErrorString(e__), __FILE__, __LINE__); \
     return NJODE_ECUDA; } } while (0)
 
+// one-shot CUDA events around the main sweep kernel (njode_set_kernel_timing)
+void njode_timing_begin(int which, cudaStream_t st);
+void njode_timing_end(int which, cudaStream_t st);
+
 static inline size_t njode_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ------------------------------------------------------------------------------------------------

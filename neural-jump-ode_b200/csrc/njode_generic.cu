@@ -317,8 +317,10 @@ int njode_generic_workers(const NjodeDesc* d, int64_t n_tiles) {
 template <int NJ>
 static int launch_generic(const SweepArgs& a, cudaStream_t st, bool backward) {
   if (a.n_tiles == 0) return NJODE_OK;
+  njode_timing_begin(backward ? 2 : 1, st);
   if (backward) k_generic_backward<NJ><<<a.n_workers, 32, 0, st>>>(a);
   else k_generic_forward<NJ><<<a.n_workers, 32, 0, st>>>(a);
+  njode_timing_end(backward ? 2 : 1, st);
   NJODE_LAUNCH_OK(backward ? "k_generic_backward" : "k_generic_forward");
   return NJODE_OK;
 }

@@ -61,7 +61,19 @@ SIGNATURES = {
     "njode_backward": (C.c_int, [_DESC, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _I64, _I64, _I32,
                                  _P, _P, _P, _P, _P, _SZ, _P]),
     "njode_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I64, _F, _P]),
+    "njode_set_kernel_timing": (C.c_int, [_I32, _P, _P]),
+    "njode_ffma_peak": (C.c_int, [C.POINTER(C.c_float)]),
 }
+
+# kernels launched by each ABI call (bench.py's gpu_launches claim): name -> count
+KERNELS_PER_CALL = {"njode_schedule_build": 5, "njode_schedule_knots": 1, "njode_forward": 2, "njode_loss": 2,
+                    "njode_backward": 3, "njode_adam_step": 1}
+launch_count = 0
+
+
+def count(name):
+    global launch_count
+    launch_count += KERNELS_PER_CALL[name]
 
 _lib = None
 
@@ -93,6 +105,8 @@ def load():
 
 
 def check(rc, what):
+    global launch_count
+    launch_count += KERNELS_PER_CALL.get(what, 0)
     if rc != 0:
         msg = load().njode_last_error().decode(errors="replace")
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")

@@ -163,18 +163,12 @@ class _SweepFunction(torch.autograd.Function):
                                          nat.ptr(g_preds), nat.ptr(g_before), nat.ptr(ctx.ckpt), nat.ptr(grad_flat),
                                          nat.ptr(ws), ws_bytes, stream), "njode_backward")
         ctx.ckpt = None     # checkpoints are the big buffer: release them as soon as they are consumed
-        # Separate networks with M > 2: a stack whose outputs received an all-zero gradient (nj_ode_loss
-        # ignores moments >= 2, jump_ode.py:328-378) reports no gradient, like the reference's `.grad is None`.
-        S = 1 if desc.shared_network else desc.num_moments
-        dead = set()
-        if S > 2:
-            nz = (g_preds[:, :, 2:].ne(0).flatten(0, 1).any(0) | g_before[:, :, 2:].ne(0).flatten(0, 1).any(0)).tolist()
-            dead = {s + 2 for s, live in enumerate(nz) if not live}
-        per_stack = len(ctx.shapes) // S
+        # Stacks of moments >= 2 get an all-zero gradient from nj_ode_loss (jump_ode.py:328-378); the
+        # reference reports zero tensors for them too (torch.stack backward), so nothing is special-cased.
         grads, o = [], 0
-        for i, shp in enumerate(ctx.shapes):
+        for shp in ctx.shapes:
             n = shp.numel()
-            grads.append(None if i // per_stack in dead else grad_flat[o:o + n].view(shp))
+            grads.append(grad_flat[o:o + n].view(shp))
             o += n
         return (None, None, None, None, *grads)
 

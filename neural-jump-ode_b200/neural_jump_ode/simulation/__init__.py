@@ -1,0 +1,6 @@
+"""Synthetic path generators producing the packed batch format directly on the device
+(recurrences of reference simulation/data_generation.py)."""
+
+from .device_paths import simulate_paths, sample_observations, make_packed_batch
+
+__all__ = ["simulate_paths", "sample_observations", "make_packed_batch"]
