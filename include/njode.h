@@ -175,6 +175,9 @@ int njode_adam_step(float* params, const float* grads, float* exp_avg, float* ex
  * measured dense FP32 FMA throughput in TFLOP/s (the roofline denominator of the FP32 path; it is not
  * in MEASURED_PEAKS.json).  Synchronises the device. */
 int njode_set_kernel_timing(int32_t which, void* ev_start, void* ev_stop);
+/* sticky device-side diagnostic word of the tiled kernels (0 = healthy; bit 0 / bit 1: a forward / reverse
+ * sweep CTA gave up waiting on an MMA-completion barrier).  Synchronises the device. */
+int njode_device_status(uint32_t* status_host);
 int njode_ffma_peak(float* tflops_host);
 
 #ifdef __cplusplus

@@ -82,6 +82,14 @@ extern "C" int njode_ffma_peak(float* tflops_host) {
 }
 extern "C" int32_t njode_abi_version(void) { return NJODE_ABI_VERSION; }
 
+extern "C" int njode_device_status(uint32_t* status_host) {
+  if (!status_host) NJODE_FAIL(NJODE_EINVAL, "njode_device_status: null output");
+  unsigned v = 0;
+  const int rc = njode_tiled_status(&v);
+  *status_host = v;
+  return rc;
+}
+
 extern "C" int64_t njode_params_per_stack(const NjodeDesc* d) {
   const char* why = nullptr;
   if (!njode_desc_ok(d, &why)) { njode_set_error("njode_params_per_stack: %s", why); return -1; }

@@ -177,3 +177,4 @@ int  njode_tiled_supported(const NjodeDesc* d);
 int  njode_tiled_workers(const NjodeDesc* d, int64_t n_tiles);
 int  njode_tiled_forward(const SweepArgs& a, cudaStream_t st);
 int  njode_tiled_backward(const SweepArgs& a, cudaStream_t st);
+int  njode_tiled_status(unsigned* out_host);

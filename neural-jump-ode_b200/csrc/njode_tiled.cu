@@ -1,6 +1,632 @@
-// njode_tiled.cu -- tuned FP32-FMA tile kernels (placeholder: not yet enabled)
+// njode_tiled.cu -- tcgen05 / TMEM sweep kernels for hidden_dim = 32, one hidden layer (BASELINE configs 1-3).
+//
+// A CTA owns a tile of 128 observation units of one network stack; thread r owns row r (= TMEM lane r).
+// Every Linear layer of the forward sweep, the re-computation and the two data-gradient products of the
+// reverse sweep are "chain" GEMMs  D[128 x 32] = A[128 x 32] * B[32 x 32]^T:
+//     A  is written by the row owners straight into TMEM (tcgen05.st) -- no activation tile ever goes
+//        through shared memory on the chain,
+//     B  is the pre-split weight tile in shared memory (K-major, 128B swizzle),
+//     D  accumulates in TMEM and is read back with tcgen05.ld for the fused epilogue
+//        (bias + x/t/dt columns + activation + Euler update + checkpoint store).
+// FP32 accuracy comes from the 3xTF32 split (Al*Bh + Ah*Bl + Ah*Bh, 12 MMAs of M128 N32 K8 per GEMM,
+// 16.4 cycles each = tensor floor in TS mode).  Weight gradients are sums over rows, i.e. GEMMs whose
+// contraction index is the row: they run as stacked MN-major MMAs  [D1|D0]^T (M=64) x [Z|A_in|aux] (N=72)
+// over shared-memory tiles (32 cycles per MMA = the 128 B/cycle shared-memory operand floor), with the
+// accumulators persistent in TMEM for the whole kernel; the aux columns (1, x, t, dt) give the bias and
+// observation/time-column gradients in the same MMA.  See DESIGN.md for the measurements behind this.
 #include "njode_common.cuh"
-int njode_tiled_supported(const NjodeDesc* d) { (void)d; return 0; }
-int njode_tiled_workers(const NjodeDesc* d, int64_t n_tiles) { (void)d; (void)n_tiles; return 1; }
-int njode_tiled_forward(const SweepArgs& a, cudaStream_t st) { (void)a; (void)st; NJODE_FAIL(NJODE_EINVAL, "tiled kernels not built"); }
-int njode_tiled_backward(const SweepArgs& a, cudaStream_t st) { (void)a; (void)st; NJODE_FAIL(NJODE_EINVAL, "tiled kernels not built"); }
+#include "njode_umma.cuh"
+
+namespace {
+
+constexpr int R = NJODE_TILED_TILE_ROWS;   // 128
+constexpr int H = 32;
+constexpr int TILE_F = R * 32;             // floats in a [128][32] tile (16 KB)
+constexpr int WT_F = 32 * 32;              // floats in a weight tile (4 KB)
+constexpr int MAX_DX = 2, MAX_O = 4;
+
+struct SmallParams {
+  float b_ode0[32], b_ode1[32], b_jump0[32], b_jump1[32], b_out0[32];
+  float ext_ode0[MAX_DX + 2][32];   // [e][j]: columns H.. of the ODE first layer (x.., t_cur, dt)
+  float w_jump0[MAX_DX][32];        // [e][j]
+  float w_out1[MAX_O][32];          // [o][j]
+  float b_out1[MAX_O];
+  float dbo1[MAX_O];                // backward: readout-bias gradient accumulator
+};
+
+// sticky diagnostic word: bit 0 = forward, bit 1 = backward saw an mbarrier wait time out (njode_device_status)
+__device__ unsigned g_tiled_status = 0;
+
+struct Ctl {
+  uint64_t bar_chain, bar_wgrad;
+  uint32_t tmem_base;
+  uint32_t timeout;
+};
+
+// weight tile W[n][k] (transpose: W^T) -> tf32 hi / lo, K-major 128B-swizzled B operand
+__device__ __forceinline__ void load_wtile(float* hi, float* lo, const float* __restrict__ W, int ld, bool transpose) {
+  for (int idx = threadIdx.x; idx < WT_F; idx += R) {
+    const int n = idx >> 5, k = idx & 31;
+    const float v = transpose ? W[k * ld + n] : W[n * ld + k];
+    const float h = umma::tf32_hi(v);
+    hi[umma::swz_k(n, k)] = h;
+    lo[umma::swz_k(n, k)] = umma::tf32_hi(v - h);
+  }
+}
+
+__device__ __forceinline__ void load_small(SmallParams& sp, const ParamTable& T, const float* __restrict__ p) {
+  const int t = threadIdx.x;
+  if (t < 32) {
+    const int ld0 = H + T.d_x + 2;
+    sp.b_ode0[t] = p[T.b_off[NET_ODE][0] + t];
+    sp.b_ode1[t] = p[T.b_off[NET_ODE][1] + t];
+    sp.b_jump0[t] = p[T.b_off[NET_JUMP][0] + t];
+    sp.b_jump1[t] = p[T.b_off[NET_JUMP][1] + t];
+    sp.b_out0[t] = p[T.b_off[NET_OUT][0] + t];
+    for (int e = 0; e < T.d_x + 2; ++e) sp.ext_ode0[e][t] = p[T.w_off[NET_ODE][0] + t * ld0 + H + e];
+    for (int e = 0; e < T.d_x; ++e) sp.w_jump0[e][t] = p[T.w_off[NET_JUMP][0] + t * T.d_x + e];
+    for (int o = 0; o < T.O; ++o) sp.w_out1[o][t] = p[T.w_off[NET_OUT][1] + o * H + t];
+    if (t < T.O) { sp.b_out1[t] = p[T.b_off[NET_OUT][1] + t]; sp.dbo1[t] = 0.0f; }
+  }
+}
+
+// 3xTF32 chain GEMM, A from TMEM: acc = A * B^T   (issued by one thread)
+__device__ __forceinline__ void issue_chain(uint32_t tmem_acc, uint32_t tmem_a_hi, uint32_t tmem_a_lo,
+                                            const float* b_hi, const float* b_lo) {
+  constexpr uint32_t idesc = umma::idesc_tf32(128, 32, 0, 0);
+  const uint64_t dbh = umma::desc_k(umma::smem_u32(b_hi)), dbl = umma::desc_k(umma::smem_u32(b_lo));
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) umma::mma_ts(tmem_acc, tmem_a_lo + 8 * ks, dbh + 2 * ks, idesc, ks > 0);
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) umma::mma_ts(tmem_acc, tmem_a_hi + 8 * ks, dbl + 2 * ks, idesc, 1);
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) umma::mma_ts(tmem_acc, tmem_a_hi + 8 * ks, dbh + 2 * ks, idesc, 1);
+}
+
+// 3xTF32 row-contraction GEMM: acc[64 x N] += [A0|A1]^T (MN-major tiles, rows = contraction) * [B0|B1|..]
+template <int N>
+__device__ __forceinline__ void issue_wgrad(uint32_t tmem_acc, const float* a_hi, const float* a_lo,
+                                            const float* b_hi, const float* b_lo) {
+  constexpr uint32_t idesc = umma::idesc_tf32(64, N, 1, 1);
+  const uint64_t dah = umma::desc_mn(umma::smem_u32(a_hi), TILE_F * 4), dal = umma::desc_mn(umma::smem_u32(a_lo), TILE_F * 4);
+  const uint64_t dbh = umma::desc_mn(umma::smem_u32(b_hi), TILE_F * 4), dbl = umma::desc_mn(umma::smem_u32(b_lo), TILE_F * 4);
+#pragma unroll
+  for (int ks = 0; ks < 16; ++ks) umma::mma_ss(tmem_acc, dal + 64 * ks, dbh + 64 * ks, idesc, 1);
+#pragma unroll
+  for (int ks = 0; ks < 16; ++ks) umma::mma_ss(tmem_acc, dah + 64 * ks, dbl + 64 * ks, idesc, 1);
+#pragma unroll
+  for (int ks = 0; ks < 16; ++ks) umma::mma_ss(tmem_acc, dah + 64 * ks, dbh + 64 * ks, idesc, 1);
+}
+
+__device__ __forceinline__ int64_t pred_index(const ParamTable& T, int64_t obs, int s, int o) {
+  return T.S == 1 ? obs * T.d_y * T.M + o : (obs * T.d_y + o) * T.M + s;
+}
+
+__device__ __forceinline__ void load_row32(const float* __restrict__ src, float (&v)[32]) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const float4 q = s4[i]; v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w; }
+}
+__device__ __forceinline__ void store_row32(float* __restrict__ dst, const float (&v)[32]) {
+  float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) __stcs(&d4[i], make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward sweep
+// ------------------------------------------------------------------------------------------------
+enum { FW_ODE0 = 0, FW_ODE1, FW_JUMP1, FW_OUT0, FW_COUNT };
+constexpr uint32_t F_AHI = 0, F_ALO = 32, F_ACC = 64, F_TMEM_COLS = 128;
+constexpr size_t FWD_SMEM = 1024 + FW_COUNT * 2 * WT_F * 4 + sizeof(SmallParams) + sizeof(Ctl) + 20 * 1024;  // pad: <= 4 CTAs/SM
+
+template <int ACT>
+__global__ void __launch_bounds__(R) k_tiled_forward(SweepArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  float* wt = reinterpret_cast<float*>(base);                                  // [FW_COUNT][2][WT_F]
+  SmallParams& sp = *reinterpret_cast<SmallParams*>(base + FW_COUNT * 2 * WT_F * 4);
+  Ctl& ctl = *reinterpret_cast<Ctl*>(base + FW_COUNT * 2 * WT_F * 4 + sizeof(SmallParams));
+
+  const ParamTable& T = a.T;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int s = blockIdx.x % T.S;
+  const int worker = blockIdx.x / T.S, n_workers = gridDim.x / T.S;
+  const float* p = a.params + (int64_t)s * T.stack_floats;
+  const int dx = T.d_x, O = T.O, sc_kind = a.desc.input_scaling;
+  float* ckpt = a.ckpt ? a.ckpt + (int64_t)s * a.total_slots * R * H : nullptr;
+
+  load_wtile(wt + (FW_ODE0 * 2) * WT_F, wt + (FW_ODE0 * 2 + 1) * WT_F, p + T.w_off[NET_ODE][0], H + dx + 2, false);
+  load_wtile(wt + (FW_ODE1 * 2) * WT_F, wt + (FW_ODE1 * 2 + 1) * WT_F, p + T.w_off[NET_ODE][1], H, false);
+  load_wtile(wt + (FW_JUMP1 * 2) * WT_F, wt + (FW_JUMP1 * 2 + 1) * WT_F, p + T.w_off[NET_JUMP][1], H, false);
+  load_wtile(wt + (FW_OUT0 * 2) * WT_F, wt + (FW_OUT0 * 2 + 1) * WT_F, p + T.w_off[NET_OUT][0], H, false);
+  load_small(sp, T, p);
+  if (tid == 0) {
+    umma::mbar_init(&ctl.bar_chain, 1);
+    umma::fence_mbar_init();
+    ctl.timeout = 0;
+  }
+  if (warp == 0) umma::tmem_alloc(&ctl.tmem_base, F_TMEM_COLS);
+  umma::fence_async_smem();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = ctl.tmem_base;
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  uint32_t phase = 0;
+  bool ok = true;
+
+  // acc = in * W^T for this thread's row (all 128 threads call this together)
+  auto gemm = [&](const float (&in)[32], int wid, float (&acc)[32]) {
+    uint32_t hi[32], lo[32];
+    umma::split32(in, hi, lo);
+    umma::row_to_tmem(lane_base, F_AHI, F_ALO, hi, lo);
+    umma::wait_st();
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      umma::fence_after_sync();
+      issue_chain(tmem + F_ACC, tmem + F_AHI, tmem + F_ALO, wt + (wid * 2) * WT_F, wt + (wid * 2 + 1) * WT_F);
+      umma::commit(&ctl.bar_chain);
+    }
+    ok = umma::mbar_wait(&ctl.bar_chain, phase) && ok;
+    phase ^= 1;
+    umma::fence_after_sync();
+    umma::tmem_ld32(lane_base + F_ACC, acc);
+  };
+
+  for (int64_t tile = worker; tile < a.n_tiles; tile += n_workers) {
+    const int64_t slot0 = a.tile_slot_off[tile];
+    const int kmax = a.tile_kmax[tile];
+    const int u = a.perm[tile * R + tid];
+    const int ke = u >= 0 ? a.kenc[u] : 0;
+    const int K = ke >> 1;
+    float x[MAX_DX], xs[MAX_DX];
+#pragma unroll
+    for (int e = 0; e < MAX_DX; ++e) {
+      x[e] = (e < dx && u >= 0) ? a.values[(int64_t)u * dx + e] : 0.0f;
+      xs[e] = scale_fwd_rt(sc_kind, x[e]);
+    }
+    float h[32], z[32], acc[32];
+    // h = jump(x)                                                   jump_ode.py:169 / :176
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float v = sp.b_jump0[j];
+#pragma unroll
+      for (int e = 0; e < MAX_DX; ++e) if (e < dx) v = fmaf(sp.w_jump0[e][j], x[e], v);
+      z[j] = act_fwd<ACT>(v);
+    }
+    gemm(z, FW_JUMP1, acc);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) h[j] = act_fwd<ACT>(acc[j] + sp.b_jump1[j]);
+    if (ckpt) store_row32(ckpt + ((slot0 + 0) * R + tid) * H, h);
+
+    // readout: y = out(h)                                           jump_ode.py:170 / :177, :205-212
+    auto readout = [&](float* __restrict__ dst, int64_t obs, bool write) {
+      gemm(h, FW_OUT0, acc);
+      float y[MAX_O];
+#pragma unroll
+      for (int o = 0; o < MAX_O; ++o) y[o] = sp.b_out1[o < O ? o : 0];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float zz = act_fwd<ACT>(acc[j] + sp.b_out0[j]);
+#pragma unroll
+        for (int o = 0; o < MAX_O; ++o) if (o < O) y[o] = fmaf(zz, sp.w_out1[o][j], y[o]);
+      }
+      if (write) {
+#pragma unroll
+        for (int o = 0; o < MAX_O; ++o) if (o < O) dst[pred_index(T, obs, s, o)] = y[o];
+      }
+    };
+    readout(a.preds, u, u >= 0);
+
+    // Euler steps with x held constant                              jump_ode.py:188-203, :122-140
+    for (int k = 0; k < kmax; ++k) {
+      const float tc = a.knots[(slot0 + k) * R + tid], tn = a.knots[(slot0 + k + 1) * R + tid];
+      const float delta = __fsub_rn(tn, tc);
+      if (sc_kind != NJODE_SCALE_IDENTITY) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) z[j] = scale_fwd_rt(sc_kind, h[j]);
+        gemm(z, FW_ODE0, acc);
+      } else {
+        gemm(h, FW_ODE0, acc);
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float v = acc[j] + sp.b_ode0[j];
+#pragma unroll
+        for (int e = 0; e < MAX_DX; ++e) if (e < dx) v = fmaf(sp.ext_ode0[e][j], xs[e], v);
+        v = fmaf(sp.ext_ode0[dx][j], tc, v);
+        v = fmaf(sp.ext_ode0[dx + 1][j], delta, v);
+        z[j] = act_fwd<ACT>(v);
+      }
+      gemm(z, FW_ODE1, acc);
+      if (k < K) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) h[j] = fmaf(delta, acc[j] + sp.b_ode1[j], h[j]);
+      }
+      if (ckpt) store_row32(ckpt + ((slot0 + k + 1) * R + tid) * H, h);
+    }
+    readout(a.preds_before, (int64_t)u + 1, u >= 0 && (ke & 1));
+  }
+
+  if (!ok && tid == 0) atomicOr(&g_tiled_status, 1u);
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_free(tmem, F_TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// reverse sweep
+// ------------------------------------------------------------------------------------------------
+enum { WB_ODE0 = 0, WB_ODE1T, WB_ODE0T, WB_OUT0, WB_OUT0T, WB_JUMP1T, WB_COUNT };
+// shared-memory MN tiles; A = [D1M|D0M], B = [ZM|AM|XM] are consecutive so LBO = one tile
+enum { T_D1M_HI = 0, T_D0M_HI, T_D1M_LO, T_D0M_LO, T_ZM_HI, T_AM_HI, T_XM_HI, T_ZM_LO, T_AM_LO, T_XM_LO, T_COUNT };
+constexpr uint32_t B_AHI = 0, B_ALO = 32, B_DHI = 64, B_DLO = 96, B_ACCR = 128, B_ACCD = 160,
+                   B_WG_ODE = 192, B_WG_OUT = 288, B_WG_J1 = 352, B_WG_J0 = 416, B_TMEM_COLS = 512;
+constexpr size_t BWD_SMEM = 1024 + (size_t)T_COUNT * TILE_F * 4 + WB_COUNT * 2 * WT_F * 4 + sizeof(SmallParams) + sizeof(Ctl);
+
+template <int ACT>
+__global__ void __launch_bounds__(R, 1) k_tiled_backward(SweepArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  float* tiles = reinterpret_cast<float*>(base);                                         // [T_COUNT][TILE_F]
+  float* wt = tiles + (size_t)T_COUNT * TILE_F;                                          // [WB_COUNT][2][WT_F]
+  SmallParams& sp = *reinterpret_cast<SmallParams*>(reinterpret_cast<uint8_t*>(wt) + WB_COUNT * 2 * WT_F * 4);
+  Ctl& ctl = *reinterpret_cast<Ctl*>(reinterpret_cast<uint8_t*>(&sp) + sizeof(SmallParams));
+
+  const ParamTable& T = a.T;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int s = blockIdx.x % T.S;
+  const int worker = blockIdx.x / T.S, n_workers = gridDim.x / T.S;
+  const float* p = a.params + (int64_t)s * T.stack_floats;
+  float* part = a.partials + (int64_t)blockIdx.x * T.stack_floats;
+  const int dx = T.d_x, O = T.O, sc_kind = a.desc.input_scaling;
+  const float* ckpt = a.ckpt + (int64_t)s * a.total_slots * R * H;
+
+  auto W = [&](int id, int lo) { return wt + (id * 2 + lo) * WT_F; };
+  auto Tl = [&](int id) { return tiles + (size_t)id * TILE_F; };
+
+  load_wtile(W(WB_ODE0, 0), W(WB_ODE0, 1), p + T.w_off[NET_ODE][0], H + dx + 2, false);
+  load_wtile(W(WB_ODE0T, 0), W(WB_ODE0T, 1), p + T.w_off[NET_ODE][0], H + dx + 2, true);
+  load_wtile(W(WB_ODE1T, 0), W(WB_ODE1T, 1), p + T.w_off[NET_ODE][1], H, true);
+  load_wtile(W(WB_OUT0, 0), W(WB_OUT0, 1), p + T.w_off[NET_OUT][0], H, false);
+  load_wtile(W(WB_OUT0T, 0), W(WB_OUT0T, 1), p + T.w_off[NET_OUT][0], H, true);
+  load_wtile(W(WB_JUMP1T, 0), W(WB_JUMP1T, 1), p + T.w_off[NET_JUMP][1], H, true);
+  load_small(sp, T, p);
+  // MN tiles may hold anything at start; unused rows / columns only feed accumulator cells nobody reads,
+  // but NaN * 0 must not leak into used cells: XM columns beyond the 8 used ones are never addressed (N = 72).
+  for (int i = tid; i < T_COUNT * TILE_F; i += R) tiles[i] = 0.0f;
+  if (tid == 0) {
+    umma::mbar_init(&ctl.bar_chain, 1);
+    umma::mbar_init(&ctl.bar_wgrad, 1);
+    umma::fence_mbar_init();
+    ctl.timeout = 0;
+  }
+  if (warp == 0) umma::tmem_alloc(&ctl.tmem_base, B_TMEM_COLS);
+  umma::fence_async_smem();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = ctl.tmem_base;
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  {  // zero the persistent weight-gradient accumulators
+    uint32_t zero[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) zero[i] = 0u;
+    for (uint32_t c = B_WG_ODE; c < B_TMEM_COLS; c += 32) umma::tmem_st32_raw(lane_base + c, zero);
+    umma::wait_st();
+  }
+  uint32_t ph_c = 0, ph_w = 0;
+  bool ok = true;
+
+  auto wait_chain = [&]() { ok = umma::mbar_wait(&ctl.bar_chain, ph_c) && ok; ph_c ^= 1; umma::fence_after_sync(); };
+  auto wait_wgrad = [&]() { ok = umma::mbar_wait(&ctl.bar_wgrad, ph_w) && ok; ph_w ^= 1; umma::fence_after_sync(); };
+  // make this thread's TMEM / smem writes visible to the MMA issuer, then barrier
+  auto publish = [&]() { umma::wait_st(); umma::fence_async_smem(); umma::fence_before_sync(); __syncthreads(); };
+  // row -> TMEM A operand (hi, lo) and/or MN tile (hi, lo)
+  auto put = [&](const float (&v)[32], bool to_tmem, uint32_t c_hi, uint32_t c_lo, int tile_hi, int tile_lo) {
+    uint32_t hi[32], lo[32];
+    umma::split32(v, hi, lo);
+    if (to_tmem) umma::row_to_tmem(lane_base, c_hi, c_lo, hi, lo);
+    if (tile_hi >= 0) { umma::row_to_mn_tile(Tl(tile_hi), tid, hi); umma::row_to_mn_tile(Tl(tile_lo), tid, lo); }
+  };
+  auto put_aux = [&](const float (&xv)[8]) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float hh = umma::tf32_hi(xv[i]); hi[i] = __float_as_uint(hh); lo[i] = __float_as_uint(umma::tf32_hi(xv[i] - hh)); }
+    umma::row8_to_mn_tile(Tl(T_XM_HI), tid, hi);
+    umma::row8_to_mn_tile(Tl(T_XM_LO), tid, lo);
+  };
+
+  for (int64_t tile = worker; tile < a.n_tiles; tile += n_workers) {
+    const int64_t slot0 = a.tile_slot_off[tile];
+    const int kmax = a.tile_kmax[tile];
+    const int u = a.perm[tile * R + tid];
+    const int ke = u >= 0 ? a.kenc[u] : 0;
+    float x[MAX_DX], xs[MAX_DX];
+#pragma unroll
+    for (int e = 0; e < MAX_DX; ++e) {
+      x[e] = (e < dx && u >= 0) ? a.values[(int64_t)u * dx + e] : 0.0f;
+      xs[e] = scale_fwd_rt(sc_kind, x[e]);
+    }
+    float g[32], hrow[32], z[32], acc[32], d[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) g[j] = 0.0f;
+
+    // ---- readout backward at a hidden state `hrow`; adds d loss / d hrow to g ----
+    auto out_backward = [&](const float* __restrict__ gsrc, int64_t obs, bool live) {
+      float dY[MAX_O];
+#pragma unroll
+      for (int o = 0; o < MAX_O; ++o) dY[o] = (live && o < O) ? gsrc[pred_index(T, obs, s, o)] : 0.0f;
+      put(hrow, true, B_AHI, B_ALO, T_AM_HI, T_AM_LO);
+      float xv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xv[i] = 0.0f;
+      xv[0] = 1.0f;
+#pragma unroll
+      for (int o = 0; o < MAX_O; ++o) xv[1 + o] = dY[o];
+      put_aux(xv);
+      publish();
+      if (tid == 0) {
+        umma::fence_after_sync();
+        issue_chain(tmem + B_ACCR, tmem + B_AHI, tmem + B_ALO, W(WB_OUT0, 0), W(WB_OUT0, 1));
+        umma::commit(&ctl.bar_chain);
+      }
+      // readout-bias gradient: sum of dY over rows
+#pragma unroll
+      for (int o = 0; o < MAX_O; ++o) {
+        float v = dY[o];
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(NJODE_FULL, v, sft);
+        if (lane == 0 && o < O) atomicAdd(&sp.dbo1[o], v);
+      }
+      wait_chain();
+      umma::tmem_ld32(lane_base + B_ACCR, acc);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        z[j] = act_fwd<ACT>(acc[j] + sp.b_out0[j]);
+        float dz = 0.0f;
+#pragma unroll
+        for (int o = 0; o < MAX_O; ++o) if (o < O) dz = fmaf(dY[o], sp.w_out1[o][j], dz);
+        d[j] = dz * act_grad_from_out<ACT>(z[j]);
+      }
+      put(d, true, B_DHI, B_DLO, T_D1M_HI, T_D1M_LO);
+      put(z, false, 0, 0, T_D0M_HI, T_D0M_LO);
+      publish();
+      if (tid == 0) {
+        umma::fence_after_sync();
+        issue_chain(tmem + B_ACCD, tmem + B_DHI, tmem + B_DLO, W(WB_OUT0T, 0), W(WB_OUT0T, 1));
+        umma::commit(&ctl.bar_chain);
+        issue_wgrad<40>(tmem + B_WG_OUT, Tl(T_D1M_HI), Tl(T_D1M_LO), Tl(T_AM_HI), Tl(T_AM_LO));
+        umma::commit(&ctl.bar_wgrad);
+      }
+      wait_chain();
+      umma::tmem_ld32(lane_base + B_ACCD, acc);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) g[j] += acc[j];
+      wait_wgrad();
+    };
+
+    // ---- preds_before[u+1] = out(h_end) ----
+    load_row32(ckpt + ((slot0 + kmax) * R + tid) * H, hrow);
+    out_backward(a.grad_preds_before, (int64_t)u + 1, u >= 0 && (ke & 1));
+
+    // ---- Euler steps, last to first ----
+    for (int k = kmax - 1; k >= 0; --k) {
+      const float tc = a.knots[(slot0 + k) * R + tid], tn = a.knots[(slot0 + k + 1) * R + tid];
+      const float delta = __fsub_rn(tn, tc);            // 0 for rows that took fewer than k+1 steps
+      load_row32(ckpt + ((slot0 + k) * R + tid) * H, hrow);
+      if (sc_kind != NJODE_SCALE_IDENTITY) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) hrow[j] = scale_fwd_rt(sc_kind, hrow[j]);
+      }
+      put(hrow, true, B_AHI, B_ALO, T_AM_HI, T_AM_LO);
+      float xv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xv[i] = 0.0f;
+      xv[0] = 1.0f;
+#pragma unroll
+      for (int e = 0; e < MAX_DX; ++e) if (e < dx) xv[1 + e] = xs[e];
+      xv[1 + dx] = tc;
+      xv[2 + dx] = delta;
+      put_aux(xv);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) d[j] = delta * g[j];                       // d loss / d f(h)
+      put(d, true, B_DHI, B_DLO, T_D1M_HI, T_D1M_LO);
+      publish();
+      if (tid == 0) {
+        umma::fence_after_sync();
+        issue_chain(tmem + B_ACCR, tmem + B_AHI, tmem + B_ALO, W(WB_ODE0, 0), W(WB_ODE0, 1));      // recompute
+        issue_chain(tmem + B_ACCD, tmem + B_DHI, tmem + B_DLO, W(WB_ODE1T, 0), W(WB_ODE1T, 1));    // d z0
+        umma::commit(&ctl.bar_chain);
+      }
+      wait_chain();
+      umma::tmem_ld32(lane_base + B_ACCR, acc);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float v = acc[j] + sp.b_ode0[j];
+#pragma unroll
+        for (int e = 0; e < MAX_DX; ++e) if (e < dx) v = fmaf(sp.ext_ode0[e][j], xs[e], v);
+        v = fmaf(sp.ext_ode0[dx][j], tc, v);
+        v = fmaf(sp.ext_ode0[dx + 1][j], delta, v);
+        z[j] = act_fwd<ACT>(v);
+      }
+      put(z, false, 0, 0, T_ZM_HI, T_ZM_LO);
+      umma::tmem_ld32(lane_base + B_ACCD, acc);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) d[j] = acc[j] * act_grad_from_out<ACT>(z[j]);   // d loss / d a0
+      put(d, true, B_DHI, B_DLO, T_D0M_HI, T_D0M_LO);
+      publish();
+      if (tid == 0) {
+        umma::fence_after_sync();
+        issue_chain(tmem + B_ACCD, tmem + B_DHI, tmem + B_DLO, W(WB_ODE0T, 0), W(WB_ODE0T, 1));    // d s(h)
+        umma::commit(&ctl.bar_chain);
+        issue_wgrad<72>(tmem + B_WG_ODE, Tl(T_D1M_HI), Tl(T_D1M_LO), Tl(T_ZM_HI), Tl(T_ZM_LO));
+        umma::commit(&ctl.bar_wgrad);
+      }
+      wait_chain();
+      umma::tmem_ld32(lane_base + B_ACCD, acc);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) g[j] = fmaf(acc[j], scale_grad_rt(sc_kind, hrow[j]), g[j]);
+      wait_wgrad();
+    }
+
+    // ---- preds[u] = out(h0), then the jump net ----
+    load_row32(ckpt + ((slot0 + 0) * R + tid) * H, hrow);
+    out_backward(a.grad_preds, u, u >= 0);
+    {
+      // z = first jump layer (recomputed), d = d loss / d (pre-activation of h0)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float v = sp.b_jump0[j];
+#pragma unroll
+        for (int e = 0; e < MAX_DX; ++e) if (e < dx) v = fmaf(sp.w_jump0[e][j], x[e], v);
+        z[j] = act_fwd<ACT>(v);
+        d[j] = g[j] * act_grad_from_out<ACT>(hrow[j]);
+      }
+      put(d, true, B_DHI, B_DLO, T_D1M_HI, T_D1M_LO);
+      put(z, false, 0, 0, T_AM_HI, T_AM_LO);
+      float xv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xv[i] = 0.0f;
+      xv[0] = 1.0f;
+#pragma unroll
+      for (int e = 0; e < MAX_DX; ++e) if (e < dx) xv[1 + e] = x[e];
+      put_aux(xv);
+      publish();
+      if (tid == 0) {
+        umma::fence_after_sync();
+        issue_chain(tmem + B_ACCD, tmem + B_DHI, tmem + B_DLO, W(WB_JUMP1T, 0), W(WB_JUMP1T, 1));
+        umma::commit(&ctl.bar_chain);
+        issue_wgrad<40>(tmem + B_WG_J1, Tl(T_D1M_HI), Tl(T_D1M_LO), Tl(T_AM_HI), Tl(T_AM_LO));
+        umma::commit(&ctl.bar_wgrad);
+      }
+      wait_chain();
+      umma::tmem_ld32(lane_base + B_ACCD, acc);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) d[j] = acc[j] * act_grad_from_out<ACT>(z[j]);
+      wait_wgrad();
+      put(d, false, 0, 0, T_D1M_HI, T_D1M_LO);
+      publish();
+      if (tid == 0) {
+        umma::fence_after_sync();
+        issue_wgrad<8>(tmem + B_WG_J0, Tl(T_D1M_HI), Tl(T_D1M_LO), Tl(T_XM_HI), Tl(T_XM_LO));
+        umma::commit(&ctl.bar_wgrad);
+      }
+      wait_wgrad();
+    }
+  }
+
+  // ---- flush the TMEM-resident weight-gradient accumulators into this CTA's partial buffer ----
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  {
+    const bool has_row = lane < 16;                 // M = 64 accumulator: row i lives in lane (i%16) + 32*(i/16)
+    const int i = warp * 16 + lane;                 // 0..63 when has_row
+    const int j = i & 31;
+    const int ld0 = H + dx + 2;
+    float v[32], v8[8];
+    // ODE net
+    umma::tmem_ld32(lane_base + B_WG_ODE, v);
+    if (has_row && i < 32) { for (int k = 0; k < 32; ++k) part[T.w_off[NET_ODE][1] + j * H + k] = v[k]; }
+    umma::tmem_ld32(lane_base + B_WG_ODE + 32, v);
+    if (has_row && i >= 32) { for (int k = 0; k < 32; ++k) part[T.w_off[NET_ODE][0] + j * ld0 + k] = v[k]; }
+    umma::tmem_ld8(lane_base + B_WG_ODE + 64, v8);
+    if (has_row && i < 32) part[T.b_off[NET_ODE][1] + j] = v8[0];
+    if (has_row && i >= 32) {
+      part[T.b_off[NET_ODE][0] + j] = v8[0];
+      for (int e = 0; e < dx + 2; ++e) part[T.w_off[NET_ODE][0] + j * ld0 + H + e] = v8[1 + e];
+    }
+    // output net
+    umma::tmem_ld32(lane_base + B_WG_OUT, v);
+    if (has_row && i < 32) { for (int k = 0; k < 32; ++k) part[T.w_off[NET_OUT][0] + j * H + k] = v[k]; }
+    umma::tmem_ld8(lane_base + B_WG_OUT + 32, v8);
+    if (has_row && i < 32) part[T.b_off[NET_OUT][0] + j] = v8[0];
+    if (has_row && i >= 32) { for (int o = 0; o < O; ++o) part[T.w_off[NET_OUT][1] + o * H + j] = v8[1 + o]; }
+    if (tid < O) part[T.b_off[NET_OUT][1] + tid] = sp.dbo1[tid];
+    // jump net
+    umma::tmem_ld32(lane_base + B_WG_J1, v);
+    if (has_row && i < 32) { for (int k = 0; k < 32; ++k) part[T.w_off[NET_JUMP][1] + j * H + k] = v[k]; }
+    umma::tmem_ld8(lane_base + B_WG_J1 + 32, v8);
+    if (has_row && i < 32) part[T.b_off[NET_JUMP][1] + j] = v8[0];
+    umma::tmem_ld8(lane_base + B_WG_J0, v8);
+    if (has_row && i < 32) {
+      part[T.b_off[NET_JUMP][0] + j] = v8[0];
+      for (int e = 0; e < dx; ++e) part[T.w_off[NET_JUMP][0] + j * dx + e] = v8[1 + e];
+    }
+  }
+  if (!ok && tid == 0) atomicOr(&g_tiled_status, 2u);
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_free(tmem, B_TMEM_COLS);
+}
+
+template <int ACT>
+int launch_tiled(const SweepArgs& a, cudaStream_t st, bool backward) {
+  if (a.n_tiles == 0) return NJODE_OK;
+  if (backward) {
+    NJODE_CUDA_OK(cudaFuncSetAttribute(k_tiled_backward<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
+    njode_timing_begin(2, st);
+    k_tiled_backward<ACT><<<a.n_workers, R, BWD_SMEM, st>>>(a);
+    njode_timing_end(2, st);
+    NJODE_LAUNCH_OK("k_tiled_backward");
+  } else {
+    NJODE_CUDA_OK(cudaFuncSetAttribute(k_tiled_forward<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM));
+    njode_timing_begin(1, st);
+    k_tiled_forward<ACT><<<a.n_workers, R, FWD_SMEM, st>>>(a);
+    njode_timing_end(1, st);
+    NJODE_LAUNCH_OK("k_tiled_forward");
+  }
+  return NJODE_OK;
+}
+
+int dispatch_tiled(const SweepArgs& a, cudaStream_t st, bool backward) {
+  switch (a.desc.activation) {
+    case NJODE_ACT_RELU: return launch_tiled<NJODE_ACT_RELU>(a, st, backward);
+    case NJODE_ACT_TANH: return launch_tiled<NJODE_ACT_TANH>(a, st, backward);
+    case NJODE_ACT_SIGMOID: return launch_tiled<NJODE_ACT_SIGMOID>(a, st, backward);
+    case NJODE_ACT_ELU: return launch_tiled<NJODE_ACT_ELU>(a, st, backward);
+    case NJODE_ACT_LEAKY_RELU: return launch_tiled<NJODE_ACT_LEAKY_RELU>(a, st, backward);
+    default: return launch_tiled<NJODE_ACT_SELU>(a, st, backward);
+  }
+}
+
+}  // namespace
+
+int njode_tiled_supported(const NjodeDesc* d) {
+  const int O = d->shared_network ? d->d_y * d->num_moments : d->d_y;
+  return d->hidden == H && d->n_hidden_layers == 1 && d->d_x <= MAX_DX && O <= MAX_O;
+}
+
+static int sm_count() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+// CTAs of the reverse sweep (one per SM: it owns all 512 TMEM columns); a multiple of S
+int njode_tiled_workers(const NjodeDesc* d, int64_t n_tiles) {
+  const int S = d->shared_network ? 1 : d->num_moments;
+  int64_t per_stack = sm_count() / S;
+  if (per_stack < 1) per_stack = 1;
+  if (per_stack > n_tiles) per_stack = n_tiles > 0 ? n_tiles : 1;
+  return (int)(per_stack * S);
+}
+
+int njode_tiled_forward(const SweepArgs& a_in, cudaStream_t st) {
+  SweepArgs a = a_in;
+  // forward CTAs use 128 TMEM columns and ~55 KB smem: up to 4 per SM
+  const int S = a.T.S;
+  int64_t per_stack = (int64_t)sm_count() * 4 / S;
+  if (per_stack > a.n_tiles) per_stack = a.n_tiles > 0 ? a.n_tiles : 1;
+  a.n_workers = (int)(per_stack * S);
+  return dispatch_tiled(a, st, false);
+}
+int njode_tiled_backward(const SweepArgs& a, cudaStream_t st) { return dispatch_tiled(a, st, true); }
+
+int njode_tiled_status(unsigned* out_host) {
+  NJODE_CUDA_OK(cudaMemcpyFromSymbol(out_host, g_tiled_status, sizeof(unsigned)));
+  return NJODE_OK;
+}

@@ -1,0 +1,163 @@
+// njode_umma.cuh -- thin wrappers over the Blackwell tcgen05 (UMMA) / TMEM / mbarrier PTX used by the
+// tiled sweep kernels.  Every encoding here was validated on a B200 by tools/umma_probe*.cu:
+//   * smem matrix descriptor: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 | layout <<61
+//       K-major  fp32/tf32 tiles: layout 2 (SWIZZLE_128B), 128-byte rows, 16-byte chunk ^= row%8, SBO = 1024
+//       MN-major fp32/tf32 tiles: layout 1 (SWIZZLE_128B_BASE32B, the only MN-major layout for tf32),
+//                                 128-byte rows, 32-byte chunk ^= row%4, SBO = 512, LBO = next 32-wide block
+//   * instruction descriptor (kind::tf32): c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), a_major<<15, b_major<<16,
+//       N>>3 <<17, M>>4 <<24
+//   * A operand from TMEM (lane = row, column = k) for the chain GEMMs; accumulators in TMEM;
+//       an M=64 accumulator keeps row i in lane (i%16) + 32*(i/16)
+//   * 3xTF32 split: x = hi + lo, hi = rna_tf32(x), lo = rna_tf32(x - hi);  A*B ~= Al*Bh + Ah*Bl + Ah*Bh
+//       (measured 1.5e-7 .. 4.8e-7 relative error against fp64, tools/umma_probe.cu tests 2 and 4)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+__device__ __forceinline__ uint64_t desc_k(uint32_t saddr) { return desc(saddr, 16, 1024, 2); }
+__device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t lbo_bytes) { return desc(saddr, lbo_bytes, 512, 1); }
+
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// float index of element (r, c) inside a [rows][32] tile
+__host__ __device__ __forceinline__ int swz_k(int r, int c) { return r * 32 + (((c >> 2) ^ (r & 7)) << 2) + (c & 3); }
+__host__ __device__ __forceinline__ int swz_mn(int r, int c) { return r * 32 + (((c >> 3) ^ (r & 3)) << 3) + (c & 7); }
+
+__device__ __forceinline__ float tf32_hi(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// D[tmem_d] (+)= A[tmem_a] * B[smem desc]   (A from TMEM, K-major; one k-step of 8)
+__device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+               :: "r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D[tmem_d] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+               :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;"); }
+// bounded wait: returns false on timeout (the caller records an error instead of hanging the GPU)
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    if (done) return true;
+  }
+  return false;
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {   // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(dst_smem)), "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_free(uint32_t taddr, uint32_t ncols) {        // the same warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols));
+}
+
+// 32 consecutive columns of this thread's TMEM lane  <->  32 registers
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t u[32];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                 "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
+                 "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
+                 "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+               : "r"(taddr));
+  wait_ld();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t u[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]) : "r"(taddr));
+  wait_ld();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void tmem_st32_raw(uint32_t taddr, const uint32_t (&u)[32]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+               "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+               :: "r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]),
+                 "r"(u[8]), "r"(u[9]), "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15]),
+                 "r"(u[16]), "r"(u[17]), "r"(u[18]), "r"(u[19]), "r"(u[20]), "r"(u[21]), "r"(u[22]), "r"(u[23]),
+                 "r"(u[24]), "r"(u[25]), "r"(u[26]), "r"(u[27]), "r"(u[28]), "r"(u[29]), "r"(u[30]), "r"(u[31]) : "memory");
+}
+
+// split a row of 32 floats into tf32 hi / lo parts
+__device__ __forceinline__ void split32(const float (&v)[32], uint32_t (&hi)[32], uint32_t (&lo)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float h = tf32_hi(v[i]);
+    hi[i] = __float_as_uint(h);
+    lo[i] = __float_as_uint(tf32_hi(v[i] - h));
+  }
+}
+
+// this thread's row -> TMEM columns [col_hi, +32) and [col_lo, +32) of its lane (A operand of a chain GEMM)
+__device__ __forceinline__ void row_to_tmem(uint32_t lane_base, uint32_t col_hi, uint32_t col_lo,
+                                            const uint32_t (&hi)[32], const uint32_t (&lo)[32]) {
+  tmem_st32_raw(lane_base + col_hi, hi);
+  tmem_st32_raw(lane_base + col_lo, lo);
+}
+
+// this thread's row r -> MN-major tile (128-byte row, 32-byte chunks ^ r%4).  Lanes r and r+4 share r%4, so
+// they write the two 16-byte halves of each chunk in opposite order: conflict-free quarter-warps.
+__device__ __forceinline__ void row_to_mn_tile(float* tile, int r, const uint32_t (&v)[32]) {
+  const bool sw = (r >> 2) & 1;
+  uint4* row = reinterpret_cast<uint4*>(tile + r * 32);
+#pragma unroll
+  for (int c8 = 0; c8 < 4; ++c8) {
+    const uint4 a = make_uint4(v[c8 * 8 + 0], v[c8 * 8 + 1], v[c8 * 8 + 2], v[c8 * 8 + 3]);
+    const uint4 b = make_uint4(v[c8 * 8 + 4], v[c8 * 8 + 5], v[c8 * 8 + 6], v[c8 * 8 + 7]);
+    const int chunk = (c8 ^ (r & 3)) * 2;            // in 16-byte units
+    const uint4 first = sw ? b : a, second = sw ? a : b;
+    row[chunk + (sw ? 1 : 0)] = first;
+    row[chunk + (sw ? 0 : 1)] = second;
+  }
+}
+// only the first 8 columns (one 32-byte chunk) of an MN-major tile row
+__device__ __forceinline__ void row8_to_mn_tile(float* tile, int r, const uint32_t (&v)[8]) {
+  uint4* row = reinterpret_cast<uint4*>(tile + r * 32);
+  const int chunk = (0 ^ (r & 3)) * 2;
+  row[chunk] = make_uint4(v[0], v[1], v[2], v[3]);
+  row[chunk + 1] = make_uint4(v[4], v[5], v[6], v[7]);
+}
+
+}  // namespace umma

@@ -63,6 +63,7 @@ SIGNATURES = {
     "njode_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I64, _F, _P]),
     "njode_set_kernel_timing": (C.c_int, [_I32, _P, _P]),
     "njode_ffma_peak": (C.c_int, [C.POINTER(C.c_float)]),
+    "njode_device_status": (C.c_int, [C.POINTER(C.c_uint32)]),
 }
 
 # kernels launched by each ABI call (bench.py's gpu_launches claim): name -> count

@@ -249,3 +249,21 @@ def test_error_paths():
         nj_ode_loss([], [], [], [], variance_method="nope")
     with pytest.raises(ValueError):
         NeuralJumpODE(1, 8, 1, input_scaling="bogus")
+
+
+def test_tiled_kernels_selected_and_healthy():
+    """hidden 32 / one hidden layer runs on the tcgen05 kernels (tile_rows 128), and no CTA ever timed out
+    waiting for an MMA-completion barrier."""
+    import ctypes
+    from neural_jump_ode import NeuralJumpODE, nj_ode_loss, _native as nat
+    lib = nat.load()
+    m = NeuralJumpODE(1, 32, 1, dt_ode_step=0.01, num_moments=2).to(DEV)
+    assert lib.njode_tile_rows(m.descriptor()) == 128
+    m64 = NeuralJumpODE(1, 64, 1, dt_ode_step=0.01, num_moments=2)
+    assert lib.njode_tile_rows(m64.descriptor()) == 32
+    bt, bv = _random_batch(300, seed=21)
+    preds, before, loss = _run(m, bt, bv, dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0]))
+    assert torch.isfinite(loss)
+    st = ctypes.c_uint32(99)
+    nat.check(lib.njode_device_status(ctypes.byref(st)), "njode_device_status")
+    assert st.value == 0
