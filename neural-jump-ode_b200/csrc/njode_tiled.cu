@@ -11,9 +11,11 @@
 // FP32 accuracy comes from the 3xTF32 split (Al*Bh + Ah*Bl + Ah*Bh, 12 MMAs of M128 N32 K8 per GEMM,
 // 16.4 cycles each = tensor floor in TS mode).  Weight gradients are sums over rows, i.e. GEMMs whose
 // contraction index is the row: they run as stacked MN-major MMAs  [D1|D0]^T (M=64) x [Z|A_in|aux] (N=72)
-// over shared-memory tiles (32 cycles per MMA = the 128 B/cycle shared-memory operand floor), with the
-// accumulators persistent in TMEM for the whole kernel; the aux columns (1, x, t, dt) give the bias and
-// observation/time-column gradients in the same MMA.  See DESIGN.md for the measurements behind this.
+// over shared-memory tiles (32 cycles per MMA = the 128 B/cycle shared-memory operand floor); the aux
+// columns (1, x, t, dt) give the bias and observation/time-column gradients in the same MMA.  The tensor
+// core's accumulate is not round-to-nearest: ~3000 MMAs into one TMEM accumulator drifted by 6e-5
+// (measured), so every step accumulates its 48 MMAs into a FRESH TMEM accumulator that the CUDA cores then
+// merge into running sums (also TMEM-resident) with IEEE fp32 adds.  See DESIGN.md for the measurements.
 #include "njode_common.cuh"
 #include "njode_umma.cuh"
 
@@ -83,7 +85,7 @@ __device__ __forceinline__ void issue_chain(uint32_t tmem_acc, uint32_t tmem_a_h
   for (int ks = 0; ks < 4; ++ks) umma::mma_ts(tmem_acc, tmem_a_hi + 8 * ks, dbh + 2 * ks, idesc, 1);
 }
 
-// 3xTF32 row-contraction GEMM: acc[64 x N] += [A0|A1]^T (MN-major tiles, rows = contraction) * [B0|B1|..]
+// 3xTF32 row-contraction GEMM: acc[64 x N] = [A0|A1]^T (MN-major tiles, rows = contraction) * [B0|B1|..]
 template <int N>
 __device__ __forceinline__ void issue_wgrad(uint32_t tmem_acc, const float* a_hi, const float* a_lo,
                                             const float* b_hi, const float* b_lo) {
@@ -91,7 +93,7 @@ __device__ __forceinline__ void issue_wgrad(uint32_t tmem_acc, const float* a_hi
   const uint64_t dah = umma::desc_mn(umma::smem_u32(a_hi), TILE_F * 4), dal = umma::desc_mn(umma::smem_u32(a_lo), TILE_F * 4);
   const uint64_t dbh = umma::desc_mn(umma::smem_u32(b_hi), TILE_F * 4), dbl = umma::desc_mn(umma::smem_u32(b_lo), TILE_F * 4);
 #pragma unroll
-  for (int ks = 0; ks < 16; ++ks) umma::mma_ss(tmem_acc, dal + 64 * ks, dbh + 64 * ks, idesc, 1);
+  for (int ks = 0; ks < 16; ++ks) umma::mma_ss(tmem_acc, dal + 64 * ks, dbh + 64 * ks, idesc, ks > 0);   // fresh accumulator
 #pragma unroll
   for (int ks = 0; ks < 16; ++ks) umma::mma_ss(tmem_acc, dah + 64 * ks, dbl + 64 * ks, idesc, 1);
 #pragma unroll
@@ -262,8 +264,11 @@ __global__ void __launch_bounds__(R) k_tiled_forward(SweepArgs a) {
 enum { WB_ODE0 = 0, WB_ODE1T, WB_ODE0T, WB_OUT0, WB_OUT0T, WB_JUMP1T, WB_COUNT };
 // shared-memory MN tiles; A = [D1M|D0M], B = [ZM|AM|XM] are consecutive so LBO = one tile
 enum { T_D1M_HI = 0, T_D0M_HI, T_D1M_LO, T_D0M_LO, T_ZM_HI, T_AM_HI, T_XM_HI, T_ZM_LO, T_AM_LO, T_XM_LO, T_COUNT };
-constexpr uint32_t B_AHI = 0, B_ALO = 32, B_DHI = 64, B_DLO = 96, B_ACCR = 128, B_ACCD = 160,
-                   B_WG_ODE = 192, B_WG_OUT = 288, B_WG_J1 = 352, B_WG_J0 = 416, B_TMEM_COLS = 512;
+// TMEM columns: chain operands / accumulators, one fresh row-contraction accumulator (72 columns), and the
+// running weight-gradient sums (40 useful columns per accumulator row, see merge_* below)
+constexpr uint32_t B_AHI = 0, B_ALO = 32, B_DHI = 64, B_DLO = 96, B_ACCR = 128, B_ACCD = 160, B_SACC = 192,
+                   B_RUN_ODE = 288, B_RUN_OUT = 328, B_RUN_J1 = 368, B_RUN_J0 = 408, B_RUN_END = 416,
+                   B_TMEM_COLS = 512;
 constexpr size_t BWD_SMEM = 1024 + (size_t)T_COUNT * TILE_F * 4 + WB_COUNT * 2 * WT_F * 4 + sizeof(SmallParams) + sizeof(Ctl);
 
 template <int ACT>
@@ -314,7 +319,7 @@ __global__ void __launch_bounds__(R, 1) k_tiled_backward(SweepArgs a) {
     uint32_t zero[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) zero[i] = 0u;
-    for (uint32_t c = B_WG_ODE; c < B_TMEM_COLS; c += 32) umma::tmem_st32_raw(lane_base + c, zero);
+    for (uint32_t c = 256; c < 448; c += 32) umma::tmem_st32_raw(lane_base + c, zero);   // covers B_RUN_*
     umma::wait_st();
   }
   uint32_t ph_c = 0, ph_w = 0;
@@ -337,6 +342,25 @@ __global__ void __launch_bounds__(R, 1) k_tiled_backward(SweepArgs a) {
     for (int i = 0; i < 8; ++i) { const float hh = umma::tf32_hi(xv[i]); hi[i] = __float_as_uint(hh); lo[i] = __float_as_uint(umma::tf32_hi(xv[i] - hh)); }
     umma::row8_to_mn_tile(Tl(T_XM_HI), tid, hi);
     umma::row8_to_mn_tile(Tl(T_XM_LO), tid, lo);
+  };
+
+  // running[run .. run+32) += fresh[src .. src+32) ; running[run+32 .. run+40) += fresh[src8 .. src8+8)   (IEEE adds)
+  auto merge = [&](uint32_t run, uint32_t src, uint32_t src8, bool wide) {
+    float f[32], q[32];
+    if (wide) {
+      umma::tmem_ld32(lane_base + src, f);
+      umma::tmem_ld32(lane_base + run, q);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) q[i] += f[i];
+      umma::tmem_st32(lane_base + run, q);
+    }
+    float f8[8], q8[8];
+    umma::tmem_ld8(lane_base + src8, f8);
+    umma::tmem_ld8(lane_base + run + (wide ? 32 : 0), q8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q8[i] += f8[i];
+    umma::tmem_st8(lane_base + run + (wide ? 32 : 0), q8);
+    umma::wait_st();
   };
 
   for (int64_t tile = worker; tile < a.n_tiles; tile += n_workers) {
@@ -398,7 +422,7 @@ __global__ void __launch_bounds__(R, 1) k_tiled_backward(SweepArgs a) {
         umma::fence_after_sync();
         issue_chain(tmem + B_ACCD, tmem + B_DHI, tmem + B_DLO, W(WB_OUT0T, 0), W(WB_OUT0T, 1));
         umma::commit(&ctl.bar_chain);
-        issue_wgrad<40>(tmem + B_WG_OUT, Tl(T_D1M_HI), Tl(T_D1M_LO), Tl(T_AM_HI), Tl(T_AM_LO));
+        issue_wgrad<40>(tmem + B_SACC, Tl(T_D1M_HI), Tl(T_D1M_LO), Tl(T_AM_HI), Tl(T_AM_LO));
         umma::commit(&ctl.bar_wgrad);
       }
       wait_chain();
@@ -406,6 +430,7 @@ __global__ void __launch_bounds__(R, 1) k_tiled_backward(SweepArgs a) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) g[j] += acc[j];
       wait_wgrad();
+      merge(B_RUN_OUT, B_SACC, B_SACC + 32, true);
     };
 
     // ---- preds_before[u+1] = out(h_end) ----
@@ -462,7 +487,7 @@ __global__ void __launch_bounds__(R, 1) k_tiled_backward(SweepArgs a) {
         umma::fence_after_sync();
         issue_chain(tmem + B_ACCD, tmem + B_DHI, tmem + B_DLO, W(WB_ODE0T, 0), W(WB_ODE0T, 1));    // d s(h)
         umma::commit(&ctl.bar_chain);
-        issue_wgrad<72>(tmem + B_WG_ODE, Tl(T_D1M_HI), Tl(T_D1M_LO), Tl(T_ZM_HI), Tl(T_ZM_LO));
+        issue_wgrad<72>(tmem + B_SACC, Tl(T_D1M_HI), Tl(T_D1M_LO), Tl(T_ZM_HI), Tl(T_ZM_LO));
         umma::commit(&ctl.bar_wgrad);
       }
       wait_chain();
@@ -470,6 +495,9 @@ __global__ void __launch_bounds__(R, 1) k_tiled_backward(SweepArgs a) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) g[j] = fmaf(acc[j], scale_grad_rt(sc_kind, hrow[j]), g[j]);
       wait_wgrad();
+      // accumulator rows 0-31 (warps 0,1) are the d f rows: W1 block = columns 0-31; rows 32-63 (warps 2,3) are
+      // the d a0 rows: W0 block = columns 32-63; column 64.. = bias, x, t, dt gradients for either
+      merge(B_RUN_ODE, B_SACC + (warp < 2 ? 0 : 32), B_SACC + 64, true);
     }
 
     // ---- preds[u] = out(h0), then the jump net ----
@@ -499,7 +527,7 @@ __global__ void __launch_bounds__(R, 1) k_tiled_backward(SweepArgs a) {
         umma::fence_after_sync();
         issue_chain(tmem + B_ACCD, tmem + B_DHI, tmem + B_DLO, W(WB_JUMP1T, 0), W(WB_JUMP1T, 1));
         umma::commit(&ctl.bar_chain);
-        issue_wgrad<40>(tmem + B_WG_J1, Tl(T_D1M_HI), Tl(T_D1M_LO), Tl(T_AM_HI), Tl(T_AM_LO));
+        issue_wgrad<40>(tmem + B_SACC, Tl(T_D1M_HI), Tl(T_D1M_LO), Tl(T_AM_HI), Tl(T_AM_LO));
         umma::commit(&ctl.bar_wgrad);
       }
       wait_chain();
@@ -507,14 +535,16 @@ __global__ void __launch_bounds__(R, 1) k_tiled_backward(SweepArgs a) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) d[j] = acc[j] * act_grad_from_out<ACT>(z[j]);
       wait_wgrad();
+      merge(B_RUN_J1, B_SACC, B_SACC + 32, true);
       put(d, false, 0, 0, T_D1M_HI, T_D1M_LO);
       publish();
       if (tid == 0) {
         umma::fence_after_sync();
-        issue_wgrad<8>(tmem + B_WG_J0, Tl(T_D1M_HI), Tl(T_D1M_LO), Tl(T_XM_HI), Tl(T_XM_LO));
+        issue_wgrad<8>(tmem + B_SACC, Tl(T_D1M_HI), Tl(T_D1M_LO), Tl(T_XM_HI), Tl(T_XM_LO));
         umma::commit(&ctl.bar_wgrad);
       }
       wait_wgrad();
+      merge(B_RUN_J0, 0, B_SACC, false);
     }
   }
 
@@ -528,30 +558,35 @@ __global__ void __launch_bounds__(R, 1) k_tiled_backward(SweepArgs a) {
     const int j = i & 31;
     const int ld0 = H + dx + 2;
     float v[32], v8[8];
-    // ODE net
-    umma::tmem_ld32(lane_base + B_WG_ODE, v);
-    if (has_row && i < 32) { for (int k = 0; k < 32; ++k) part[T.w_off[NET_ODE][1] + j * H + k] = v[k]; }
-    umma::tmem_ld32(lane_base + B_WG_ODE + 32, v);
-    if (has_row && i >= 32) { for (int k = 0; k < 32; ++k) part[T.w_off[NET_ODE][0] + j * ld0 + k] = v[k]; }
-    umma::tmem_ld8(lane_base + B_WG_ODE + 64, v8);
-    if (has_row && i < 32) part[T.b_off[NET_ODE][1] + j] = v8[0];
+    // ODE net: running rows 0-31 = second layer (W1, b1), rows 32-63 = first layer (W0 incl. x/t/dt columns, b0)
+    umma::tmem_ld32(lane_base + B_RUN_ODE, v);
+    umma::tmem_ld8(lane_base + B_RUN_ODE + 32, v8);
+    if (has_row && i < 32) {
+      for (int k = 0; k < 32; ++k) part[T.w_off[NET_ODE][1] + j * H + k] = v[k];
+      part[T.b_off[NET_ODE][1] + j] = v8[0];
+    }
     if (has_row && i >= 32) {
+      for (int k = 0; k < 32; ++k) part[T.w_off[NET_ODE][0] + j * ld0 + k] = v[k];
       part[T.b_off[NET_ODE][0] + j] = v8[0];
       for (int e = 0; e < dx + 2; ++e) part[T.w_off[NET_ODE][0] + j * ld0 + H + e] = v8[1 + e];
     }
-    // output net
-    umma::tmem_ld32(lane_base + B_WG_OUT, v);
-    if (has_row && i < 32) { for (int k = 0; k < 32; ++k) part[T.w_off[NET_OUT][0] + j * H + k] = v[k]; }
-    umma::tmem_ld8(lane_base + B_WG_OUT + 32, v8);
-    if (has_row && i < 32) part[T.b_off[NET_OUT][0] + j] = v8[0];
+    // output net: rows 0-31 = hidden layer (W, b); rows 32-63 (z rows) x dY columns = readout weights
+    umma::tmem_ld32(lane_base + B_RUN_OUT, v);
+    umma::tmem_ld8(lane_base + B_RUN_OUT + 32, v8);
+    if (has_row && i < 32) {
+      for (int k = 0; k < 32; ++k) part[T.w_off[NET_OUT][0] + j * H + k] = v[k];
+      part[T.b_off[NET_OUT][0] + j] = v8[0];
+    }
     if (has_row && i >= 32) { for (int o = 0; o < O; ++o) part[T.w_off[NET_OUT][1] + o * H + j] = v8[1 + o]; }
     if (tid < O) part[T.b_off[NET_OUT][1] + tid] = sp.dbo1[tid];
     // jump net
-    umma::tmem_ld32(lane_base + B_WG_J1, v);
-    if (has_row && i < 32) { for (int k = 0; k < 32; ++k) part[T.w_off[NET_JUMP][1] + j * H + k] = v[k]; }
-    umma::tmem_ld8(lane_base + B_WG_J1 + 32, v8);
-    if (has_row && i < 32) part[T.b_off[NET_JUMP][1] + j] = v8[0];
-    umma::tmem_ld8(lane_base + B_WG_J0, v8);
+    umma::tmem_ld32(lane_base + B_RUN_J1, v);
+    umma::tmem_ld8(lane_base + B_RUN_J1 + 32, v8);
+    if (has_row && i < 32) {
+      for (int k = 0; k < 32; ++k) part[T.w_off[NET_JUMP][1] + j * H + k] = v[k];
+      part[T.b_off[NET_JUMP][1] + j] = v8[0];
+    }
+    umma::tmem_ld8(lane_base + B_RUN_J0, v8);
     if (has_row && i < 32) {
       part[T.b_off[NET_JUMP][0] + j] = v8[0];
       for (int e = 0; e < dx; ++e) part[T.w_off[NET_JUMP][0] + j * dx + e] = v8[1 + e];

@@ -120,6 +120,19 @@ __device__ __forceinline__ void tmem_st32_raw(uint32_t taddr, const uint32_t (&u
                  "r"(u[24]), "r"(u[25]), "r"(u[26]), "r"(u[27]), "r"(u[28]), "r"(u[29]), "r"(u[30]), "r"(u[31]) : "memory");
 }
 
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  uint32_t u[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) u[i] = __float_as_uint(v[i]);
+  tmem_st32_raw(taddr, u);
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                 "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                 "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
+}
+
 // split a row of 32 floats into tf32 hi / lo parts
 __device__ __forceinline__ void split32(const float (&v)[32], uint32_t (&hi)[32], uint32_t (&lo)[32]) {
 #pragma unroll
