@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(R, 1) k_tiled_backward(SweepArgs a) {
   auto put_aux = [&](const float (&xv)[8]) {
     uint32_t hi[8], lo[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { const float hh = umma::tf32_hi(xv[i]); hi[i] = __float_as_uint(hh); lo[i] = __float_as_uint(umma::tf32_hi(xv[i] - hh)); }
+    for (int i = 0; i < 8; ++i) umma::split1(xv[i], hi[i], lo[i]);
     umma::row8_to_mn_tile(Tl(T_XM_HI), tid, hi);
     umma::row8_to_mn_tile(Tl(T_XM_LO), tid, lo);
   };
@@ -492,8 +492,13 @@ __global__ void __launch_bounds__(R, 1) k_tiled_backward(SweepArgs a) {
       }
       wait_chain();
       umma::tmem_ld32(lane_base + B_ACCD, acc);
+      if (sc_kind == NJODE_SCALE_IDENTITY) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) g[j] = fmaf(acc[j], scale_grad_rt(sc_kind, hrow[j]), g[j]);
+        for (int j = 0; j < 32; ++j) g[j] += acc[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) g[j] = fmaf(acc[j], scale_grad_rt(sc_kind, hrow[j]), g[j]);
+      }
       wait_wgrad();
       // accumulator rows 0-31 (warps 0,1) are the d f rows: W1 block = columns 0-31; rows 32-63 (warps 2,3) are
       // the d a0 rows: W0 block = columns 32-63; column 64.. = bias, x, t, dt gradients for either

@@ -133,14 +133,17 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
                  "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
 }
 
-// split a row of 32 floats into tf32 hi / lo parts
+// split a row of 32 floats into tf32 hi / lo parts.  hi = round-to-nearest(ties away) to 10 explicit
+// mantissa bits = (bits + 0x1000) & ~0x1fff (2 integer ops; cvt.rna.tf32.f32 costs 4 SASS ops because it
+// also special-cases inf/NaN); lo = x - hi is exact in fp32 and is handed to the tensor core unrounded
+// (the MMA reads the top 19 bits): dropped part <= 2^-21 |x|.  3 instructions per element instead of 9.
+__device__ __forceinline__ void split1(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
 __device__ __forceinline__ void split32(const float (&v)[32], uint32_t (&hi)[32], uint32_t (&lo)[32]) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const float h = tf32_hi(v[i]);
-    hi[i] = __float_as_uint(h);
-    lo[i] = __float_as_uint(tf32_hi(v[i] - h));
-  }
+  for (int i = 0; i < 32; ++i) split1(v[i], hi[i], lo[i]);
 }
 
 // this thread's row -> TMEM columns [col_hi, +32) and [col_lo, +32) of its lane (A operand of a chain GEMM)
@@ -150,19 +153,16 @@ __device__ __forceinline__ void row_to_tmem(uint32_t lane_base, uint32_t col_hi,
   tmem_st32_raw(lane_base + col_lo, lo);
 }
 
-// this thread's row r -> MN-major tile (128-byte row, 32-byte chunks ^ r%4).  Lanes r and r+4 share r%4, so
-// they write the two 16-byte halves of each chunk in opposite order: conflict-free quarter-warps.
+// this thread's row r -> MN-major tile (128-byte row, 32-byte chunks ^ r%4).  Lanes r and r+4 share r%4
+// and hit the same banks (2-way conflict); the kernels are issue-latency bound, not LSU bound, so the
+// conflict-free variant (which needs 32 SELs per row) is slower.
 __device__ __forceinline__ void row_to_mn_tile(float* tile, int r, const uint32_t (&v)[32]) {
-  const bool sw = (r >> 2) & 1;
   uint4* row = reinterpret_cast<uint4*>(tile + r * 32);
 #pragma unroll
   for (int c8 = 0; c8 < 4; ++c8) {
-    const uint4 a = make_uint4(v[c8 * 8 + 0], v[c8 * 8 + 1], v[c8 * 8 + 2], v[c8 * 8 + 3]);
-    const uint4 b = make_uint4(v[c8 * 8 + 4], v[c8 * 8 + 5], v[c8 * 8 + 6], v[c8 * 8 + 7]);
     const int chunk = (c8 ^ (r & 3)) * 2;            // in 16-byte units
-    const uint4 first = sw ? b : a, second = sw ? a : b;
-    row[chunk + (sw ? 1 : 0)] = first;
-    row[chunk + (sw ? 0 : 1)] = second;
+    row[chunk] = make_uint4(v[c8 * 8 + 0], v[c8 * 8 + 1], v[c8 * 8 + 2], v[c8 * 8 + 3]);
+    row[chunk + 1] = make_uint4(v[c8 * 8 + 4], v[c8 * 8 + 5], v[c8 * 8 + 6], v[c8 * 8 + 7]);
   }
 }
 // only the first 8 columns (one 32-byte chunk) of an MN-major tile row
