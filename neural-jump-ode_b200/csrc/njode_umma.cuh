@@ -133,6 +133,51 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
                  "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
 }
 
+// 16 / 8 consecutive columns of this thread's TMEM lane <-> registers (two warps share a lane quadrant and
+// each owns one 16-column half of a 32-column operand / accumulator)
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float (&v)[16]) {
+  uint32_t u[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                 "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]) : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t u[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                 "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]) : "r"(taddr));
+  wait_ld();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void tmem_st16_raw(uint32_t taddr, const uint32_t (&u)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+               :: "r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]),
+                 "r"(u[8]), "r"(u[9]), "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  uint32_t u[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) u[i] = __float_as_uint(v[i]);
+  tmem_st16_raw(taddr, u);
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+// one lane of a fully converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t e;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(e));
+  return e != 0;
+}
+// named barrier among `count` threads (count a multiple of 32)
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory");
+}
+
 // split a row of 32 floats into tf32 hi / lo parts.  hi = round-to-nearest(ties away) to 10 explicit
 // mantissa bits = (bits + 0x1000) & ~0x1fff (2 integer ops; cvt.rna.tf32.f32 costs 4 SASS ops because it
 // also special-cases inf/NaN); lo = x - hi is exact in fp32 and is handed to the tensor core unrounded
