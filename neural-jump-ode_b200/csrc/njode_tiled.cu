@@ -1,6 +1,10 @@
 // njode_tiled.cu -- tcgen05 / TMEM sweep kernels for hidden_dim = 32, one hidden layer (BASELINE configs 1-3).
 //
-// A CTA owns a tile of 128 observation units of one network stack; thread r owns row r (= TMEM lane r).
+// A CTA owns a tile of 128 observation units of one network stack.  Row r of the tile is TMEM lane r; FOUR
+// threads share a row, each owning 8 of its 32 columns (512 threads: warp w serves TMEM lane quadrant w % 4
+// and column slice w / 4).  The sweeps are latency chains (every Euler step is 2 dependent GEMM phases), so
+// the per-phase CUDA-core work per thread is what sets the step time: 8 elements instead of 32 per thread.
+//
 // Every Linear layer of the forward sweep, the re-computation and the two data-gradient products of the
 // reverse sweep are "chain" GEMMs  D[128 x 32] = A[128 x 32] * B[32 x 32]^T:
 //     A  is written by the row owners straight into TMEM (tcgen05.st) -- no activation tile ever goes
@@ -21,23 +25,36 @@
 
 namespace {
 
-constexpr int R = NJODE_TILED_TILE_ROWS;   // 128
+constexpr int R = NJODE_TILED_TILE_ROWS;   // 128 rows per tile
 constexpr int H = 32;
+constexpr int CW = 8;                      // columns per thread
+constexpr int NT = R * (H / CW);           // 512 threads
 constexpr int TILE_F = R * 32;             // floats in a [128][32] tile (16 KB)
 constexpr int WT_F = 32 * 32;              // floats in a weight tile (4 KB)
 constexpr int MAX_DX = 2, MAX_O = 4;
 
-struct SmallParams {
+struct __align__(16) SmallParams {
   float b_ode0[32], b_ode1[32], b_jump0[32], b_jump1[32], b_out0[32];
   float ext_ode0[MAX_DX + 2][32];   // [e][j]: columns H.. of the ODE first layer (x.., t_cur, dt)
   float w_jump0[MAX_DX][32];        // [e][j]
   float w_out1[MAX_O][32];          // [o][j]
   float b_out1[MAX_O];
-  float dbo1[MAX_O];                // backward: readout-bias gradient accumulator
+  float red[4][R][MAX_O];           // forward: readout partial sums of the 4 column slices; backward: bias-gradient reduction
 };
 
 // sticky diagnostic word: bit 0 = forward, bit 1 = backward saw an mbarrier wait time out (njode_device_status)
 __device__ unsigned g_tiled_status = 0;
+
+// optional phase trace (make TRACE=1): thread 0 of CTA 0 records (clock64 << 8 | id) at phase boundaries
+#ifdef NJODE_TRACE
+#define NJODE_TRACE_CAP 8192
+__device__ long long g_trace[NJODE_TRACE_CAP];
+__device__ int g_trace_n = 0;
+#define TR(id) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const int n__ = g_trace_n; if (n__ < NJODE_TRACE_CAP) { \
+    g_trace[n__] = (clock64() << 8) | (long long)(id); g_trace_n = n__ + 1; } } } while (0)
+#else
+#define TR(id) do { } while (0)
+#endif
 
 struct Ctl {
   uint64_t bar_chain, bar_wgrad;
@@ -47,7 +64,7 @@ struct Ctl {
 
 // weight tile W[n][k] (transpose: W^T) -> tf32 hi / lo, K-major 128B-swizzled B operand
 __device__ __forceinline__ void load_wtile(float* hi, float* lo, const float* __restrict__ W, int ld, bool transpose) {
-  for (int idx = threadIdx.x; idx < WT_F; idx += R) {
+  for (int idx = threadIdx.x; idx < WT_F; idx += NT) {
     const int n = idx >> 5, k = idx & 31;
     const float v = transpose ? W[k * ld + n] : W[n * ld + k];
     const float h = umma::tf32_hi(v);
@@ -68,8 +85,18 @@ __device__ __forceinline__ void load_small(SmallParams& sp, const ParamTable& T,
     for (int e = 0; e < T.d_x + 2; ++e) sp.ext_ode0[e][t] = p[T.w_off[NET_ODE][0] + t * ld0 + H + e];
     for (int e = 0; e < T.d_x; ++e) sp.w_jump0[e][t] = p[T.w_off[NET_JUMP][0] + t * T.d_x + e];
     for (int o = 0; o < T.O; ++o) sp.w_out1[o][t] = p[T.w_off[NET_OUT][1] + o * H + t];
-    if (t < T.O) { sp.b_out1[t] = p[T.b_off[NET_OUT][1] + t]; sp.dbo1[t] = 0.0f; }
+    if (t < T.O) sp.b_out1[t] = p[T.b_off[NET_OUT][1] + t];
   }
+}
+
+// 8 consecutive floats (32-byte aligned) from shared / global memory
+__device__ __forceinline__ void ld8(const float* __restrict__ src, float (&v)[8]) {
+  const float4 q0 = reinterpret_cast<const float4*>(src)[0], q1 = reinterpret_cast<const float4*>(src)[1];
+  v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+}
+__device__ __forceinline__ void st8_stream(float* __restrict__ dst, const float (&v)[8]) {
+  __stcs(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+  __stcs(reinterpret_cast<float4*>(dst) + 1, make_float4(v[4], v[5], v[6], v[7]));
 }
 
 // 3xTF32 chain GEMM, A from TMEM: acc = A * B^T   (issued by one thread)
@@ -104,15 +131,10 @@ __device__ __forceinline__ int64_t pred_index(const ParamTable& T, int64_t obs, 
   return T.S == 1 ? obs * T.d_y * T.M + o : (obs * T.d_y + o) * T.M + s;
 }
 
-__device__ __forceinline__ void load_row32(const float* __restrict__ src, float (&v)[32]) {
-  const float4* s4 = reinterpret_cast<const float4*>(src);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { const float4 q = s4[i]; v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w; }
-}
-__device__ __forceinline__ void store_row32(float* __restrict__ dst, const float (&v)[32]) {
-  float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) __stcs(&d4[i], make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+// tiles are sorted by step count (descending); worker w takes them in snake order so that every worker
+// gets one long and one short tile per pair of rounds
+__device__ __forceinline__ int64_t snake_tile(int64_t round, int worker, int n_workers) {
+  return round * n_workers + ((round & 1) ? n_workers - 1 - worker : worker);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -120,10 +142,10 @@ __device__ __forceinline__ void store_row32(float* __restrict__ dst, const float
 // ------------------------------------------------------------------------------------------------
 enum { FW_ODE0 = 0, FW_ODE1, FW_JUMP1, FW_OUT0, FW_COUNT };
 constexpr uint32_t F_AHI = 0, F_ALO = 32, F_ACC = 64, F_TMEM_COLS = 128;
-constexpr size_t FWD_SMEM = 1024 + FW_COUNT * 2 * WT_F * 4 + sizeof(SmallParams) + sizeof(Ctl) + 20 * 1024;  // pad: <= 4 CTAs/SM
+constexpr size_t FWD_SMEM = 1024 + FW_COUNT * 2 * WT_F * 4 + sizeof(SmallParams) + sizeof(Ctl);
 
 template <int ACT>
-__global__ void __launch_bounds__(R) k_tiled_forward(SweepArgs a) {
+__global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   float* wt = reinterpret_cast<float*>(base);                                  // [FW_COUNT][2][WT_F]
@@ -131,7 +153,8 @@ __global__ void __launch_bounds__(R) k_tiled_forward(SweepArgs a) {
   Ctl& ctl = *reinterpret_cast<Ctl*>(base + FW_COUNT * 2 * WT_F * 4 + sizeof(SmallParams));
 
   const ParamTable& T = a.T;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, c = warp >> 2, row = q * 32 + lane, col0 = c * CW;
   const int s = blockIdx.x % T.S;
   const int worker = blockIdx.x / T.S, n_workers = gridDim.x / T.S;
   const float* p = a.params + (int64_t)s * T.stack_floats;
@@ -154,33 +177,42 @@ __global__ void __launch_bounds__(R) k_tiled_forward(SweepArgs a) {
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem = ctl.tmem_base;
-  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
   uint32_t phase = 0;
   bool ok = true;
 
-  // acc = in * W^T for this thread's row (all 128 threads call this together)
-  auto gemm = [&](const float (&in)[32], int wid, float (&acc)[32]) {
-    uint32_t hi[32], lo[32];
-    umma::split32(in, hi, lo);
-    umma::row_to_tmem(lane_base, F_AHI, F_ALO, hi, lo);
+  // acc = (in * W^T)[row][col0 .. col0+8)   (all 512 threads call this together)
+  auto gemm = [&](const float (&in)[8], int wid, float (&acc)[8]) {
+    uint32_t hi[8], lo[8];
+    TR(32 + 1);
+    umma::split8(in, hi, lo);
+    umma::tmem_st8_raw(lane_base + F_AHI, hi);
+    umma::tmem_st8_raw(lane_base + F_ALO, lo);
     umma::wait_st();
+    TR(32 + 2);
     umma::fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    TR(32 + 3);
+    if (warp == 0 && umma::elect_one()) {
       umma::fence_after_sync();
       issue_chain(tmem + F_ACC, tmem + F_AHI, tmem + F_ALO, wt + (wid * 2) * WT_F, wt + (wid * 2 + 1) * WT_F);
       umma::commit(&ctl.bar_chain);
     }
+    TR(32 + 4);
     ok = umma::mbar_wait(&ctl.bar_chain, phase) && ok;
     phase ^= 1;
     umma::fence_after_sync();
-    umma::tmem_ld32(lane_base + F_ACC, acc);
+    TR(32 + 5);
+    umma::tmem_ld8(lane_base + F_ACC, acc);
+    TR(32 + 6);
   };
 
-  for (int64_t tile = worker; tile < a.n_tiles; tile += n_workers) {
+  for (int64_t round = 0; round * n_workers < a.n_tiles; ++round) {
+    const int64_t tile = snake_tile(round, worker, n_workers);
+    if (tile >= a.n_tiles) continue;
     const int64_t slot0 = a.tile_slot_off[tile];
     const int kmax = a.tile_kmax[tile];
-    const int u = a.perm[tile * R + tid];
+    const int u = a.perm[tile * R + row];
     const int ke = u >= 0 ? a.kenc[u] : 0;
     const int K = ke >> 1;
     float x[MAX_DX], xs[MAX_DX];
@@ -189,65 +221,84 @@ __global__ void __launch_bounds__(R) k_tiled_forward(SweepArgs a) {
       x[e] = (e < dx && u >= 0) ? a.values[(int64_t)u * dx + e] : 0.0f;
       xs[e] = scale_fwd_rt(sc_kind, x[e]);
     }
-    float h[32], z[32], acc[32];
+    float h[8], z[8], acc[8], cb[8], cw[8];
     // h = jump(x)                                                   jump_ode.py:169 / :176
+    ld8(sp.b_jump0 + col0, z);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float v = sp.b_jump0[j];
+    for (int e = 0; e < MAX_DX; ++e) if (e < dx) {
+      ld8(sp.w_jump0[e] + col0, cw);
 #pragma unroll
-      for (int e = 0; e < MAX_DX; ++e) if (e < dx) v = fmaf(sp.w_jump0[e][j], x[e], v);
-      z[j] = act_fwd<ACT>(v);
+      for (int j = 0; j < 8; ++j) z[j] = fmaf(cw[j], x[e], z[j]);
     }
-    gemm(z, FW_JUMP1, acc);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) h[j] = act_fwd<ACT>(acc[j] + sp.b_jump1[j]);
-    if (ckpt) store_row32(ckpt + ((slot0 + 0) * R + tid) * H, h);
+    for (int j = 0; j < 8; ++j) z[j] = act_fwd<ACT>(z[j]);
+    gemm(z, FW_JUMP1, acc);
+    ld8(sp.b_jump1 + col0, cb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h[j] = act_fwd<ACT>(acc[j] + cb[j]);
+    if (ckpt) st8_stream(ckpt + ((slot0 + 0) * R + row) * H + col0, h);
 
     // readout: y = out(h)                                           jump_ode.py:170 / :177, :205-212
     auto readout = [&](float* __restrict__ dst, int64_t obs, bool write) {
       gemm(h, FW_OUT0, acc);
-      float y[MAX_O];
+      ld8(sp.b_out0 + col0, cb);
+      float zz[8], y[MAX_O];
 #pragma unroll
-      for (int o = 0; o < MAX_O; ++o) y[o] = sp.b_out1[o < O ? o : 0];
+      for (int j = 0; j < 8; ++j) zz[j] = act_fwd<ACT>(acc[j] + cb[j]);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float zz = act_fwd<ACT>(acc[j] + sp.b_out0[j]);
+      for (int o = 0; o < MAX_O; ++o) {
+        y[o] = 0.0f;
+        if (o < O) {
+          ld8(sp.w_out1[o] + col0, cw);
 #pragma unroll
-        for (int o = 0; o < MAX_O; ++o) if (o < O) y[o] = fmaf(zz, sp.w_out1[o][j], y[o]);
+          for (int j = 0; j < 8; ++j) y[o] = fmaf(zz[j], cw[j], y[o]);
+        }
       }
-      if (write) {
+      *reinterpret_cast<float4*>(sp.red[c][row]) = make_float4(y[0], y[1], y[2], y[3]);
+      __syncthreads();
+      if (c == 0 && write) {
 #pragma unroll
-        for (int o = 0; o < MAX_O; ++o) if (o < O) dst[pred_index(T, obs, s, o)] = y[o];
+        for (int o = 0; o < MAX_O; ++o) if (o < O)
+          dst[pred_index(T, obs, s, o)] = sp.b_out1[o] + ((sp.red[0][row][o] + sp.red[1][row][o]) + (sp.red[2][row][o] + sp.red[3][row][o]));
       }
     };
     readout(a.preds, u, u >= 0);
 
     // Euler steps with x held constant                              jump_ode.py:188-203, :122-140
+    float tn = a.knots[(slot0 + 0) * R + row];
     for (int k = 0; k < kmax; ++k) {
-      const float tc = a.knots[(slot0 + k) * R + tid], tn = a.knots[(slot0 + k + 1) * R + tid];
+      const float tc = tn;
+      tn = a.knots[(slot0 + k + 1) * R + row];
       const float delta = __fsub_rn(tn, tc);
       if (sc_kind != NJODE_SCALE_IDENTITY) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) z[j] = scale_fwd_rt(sc_kind, h[j]);
+        for (int j = 0; j < 8; ++j) z[j] = scale_fwd_rt(sc_kind, h[j]);
         gemm(z, FW_ODE0, acc);
       } else {
         gemm(h, FW_ODE0, acc);
       }
+      ld8(sp.b_ode0 + col0, cb);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float v = acc[j] + sp.b_ode0[j];
+      for (int j = 0; j < 8; ++j) z[j] = acc[j] + cb[j];
 #pragma unroll
-        for (int e = 0; e < MAX_DX; ++e) if (e < dx) v = fmaf(sp.ext_ode0[e][j], xs[e], v);
-        v = fmaf(sp.ext_ode0[dx][j], tc, v);
-        v = fmaf(sp.ext_ode0[dx + 1][j], delta, v);
-        z[j] = act_fwd<ACT>(v);
+      for (int e = 0; e < MAX_DX; ++e) if (e < dx) {
+        ld8(sp.ext_ode0[e] + col0, cw);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[j] = fmaf(cw[j], xs[e], z[j]);
       }
+      ld8(sp.ext_ode0[dx] + col0, cw);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) z[j] = fmaf(cw[j], tc, z[j]);
+      ld8(sp.ext_ode0[dx + 1] + col0, cw);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) z[j] = act_fwd<ACT>(fmaf(cw[j], delta, z[j]));
       gemm(z, FW_ODE1, acc);
       if (k < K) {
+        ld8(sp.b_ode1 + col0, cb);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) h[j] = fmaf(delta, acc[j] + sp.b_ode1[j], h[j]);
+        for (int j = 0; j < 8; ++j) h[j] = fmaf(delta, acc[j] + cb[j], h[j]);
       }
-      if (ckpt) store_row32(ckpt + ((slot0 + k + 1) * R + tid) * H, h);
+      if (ckpt) st8_stream(ckpt + ((slot0 + k + 1) * R + row) * H + col0, h);
     }
     readout(a.preds_before, (int64_t)u + 1, u >= 0 && (ke & 1));
   }
@@ -265,14 +316,14 @@ enum { WB_ODE0 = 0, WB_ODE1T, WB_ODE0T, WB_OUT0, WB_OUT0T, WB_JUMP1T, WB_COUNT }
 // shared-memory MN tiles; A = [D1M|D0M], B = [ZM|AM|XM] are consecutive so LBO = one tile
 enum { T_D1M_HI = 0, T_D0M_HI, T_D1M_LO, T_D0M_LO, T_ZM_HI, T_AM_HI, T_XM_HI, T_ZM_LO, T_AM_LO, T_XM_LO, T_COUNT };
 // TMEM columns: chain operands / accumulators, one fresh row-contraction accumulator (72 columns), and the
-// running weight-gradient sums (40 useful columns per accumulator row, see merge_* below)
+// running weight-gradient sums (40 useful columns per accumulator row, see merge below)
 constexpr uint32_t B_AHI = 0, B_ALO = 32, B_DHI = 64, B_DLO = 96, B_ACCR = 128, B_ACCD = 160, B_SACC = 192,
                    B_RUN_ODE = 288, B_RUN_OUT = 328, B_RUN_J1 = 368, B_RUN_J0 = 408, B_RUN_END = 416,
                    B_TMEM_COLS = 512;
 constexpr size_t BWD_SMEM = 1024 + (size_t)T_COUNT * TILE_F * 4 + WB_COUNT * 2 * WT_F * 4 + sizeof(SmallParams) + sizeof(Ctl);
 
 template <int ACT>
-__global__ void __launch_bounds__(R, 1) k_tiled_backward(SweepArgs a) {
+__global__ void __launch_bounds__(NT, 1) k_tiled_backward(SweepArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   float* tiles = reinterpret_cast<float*>(base);                                         // [T_COUNT][TILE_F]
@@ -282,6 +333,7 @@ __global__ void __launch_bounds__(R, 1) k_tiled_backward(SweepArgs a) {
 
   const ParamTable& T = a.T;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, c = warp >> 2, row = q * 32 + lane, col0 = c * CW;
   const int s = blockIdx.x % T.S;
   const int worker = blockIdx.x / T.S, n_workers = gridDim.x / T.S;
   const float* p = a.params + (int64_t)s * T.stack_floats;
@@ -301,7 +353,7 @@ __global__ void __launch_bounds__(R, 1) k_tiled_backward(SweepArgs a) {
   load_small(sp, T, p);
   // MN tiles may hold anything at start; unused rows / columns only feed accumulator cells nobody reads,
   // but NaN * 0 must not leak into used cells: XM columns beyond the 8 used ones are never addressed (N = 72).
-  for (int i = tid; i < T_COUNT * TILE_F; i += R) tiles[i] = 0.0f;
+  for (int i = tid; i < T_COUNT * TILE_F / 4; i += NT) reinterpret_cast<float4*>(tiles)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (tid == 0) {
     umma::mbar_init(&ctl.bar_chain, 1);
     umma::mbar_init(&ctl.bar_wgrad, 1);
@@ -314,59 +366,69 @@ __global__ void __launch_bounds__(R, 1) k_tiled_backward(SweepArgs a) {
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem = ctl.tmem_base;
-  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-  {  // zero the persistent weight-gradient accumulators
+  const uint32_t quad_base = tmem + ((uint32_t)(q * 32) << 16);     // this warp's lane quadrant, column 0
+  const uint32_t lane_base = quad_base + (uint32_t)col0;            // ... at this thread's column slice
+  if (c == 0) {  // zero the persistent weight-gradient accumulators
     uint32_t zero[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) zero[i] = 0u;
-    for (uint32_t c = 256; c < 448; c += 32) umma::tmem_st32_raw(lane_base + c, zero);   // covers B_RUN_*
+    for (uint32_t col = 256; col < 448; col += 32) umma::tmem_st32_raw(quad_base + col, zero);   // covers B_RUN_*
     umma::wait_st();
   }
   uint32_t ph_c = 0, ph_w = 0;
   bool ok = true;
+  float dbo[MAX_O];                 // readout-bias gradient: this row's dY summed over all tiles (c == 0 threads)
+#pragma unroll
+  for (int o = 0; o < MAX_O; ++o) dbo[o] = 0.0f;
 
   auto wait_chain = [&]() { ok = umma::mbar_wait(&ctl.bar_chain, ph_c) && ok; ph_c ^= 1; umma::fence_after_sync(); };
   auto wait_wgrad = [&]() { ok = umma::mbar_wait(&ctl.bar_wgrad, ph_w) && ok; ph_w ^= 1; umma::fence_after_sync(); };
   // make this thread's TMEM / smem writes visible to the MMA issuer, then barrier
   auto publish = [&]() { umma::wait_st(); umma::fence_async_smem(); umma::fence_before_sync(); __syncthreads(); };
-  // row -> TMEM A operand (hi, lo) and/or MN tile (hi, lo)
-  auto put = [&](const float (&v)[32], bool to_tmem, uint32_t c_hi, uint32_t c_lo, int tile_hi, int tile_lo) {
-    uint32_t hi[32], lo[32];
-    umma::split32(v, hi, lo);
-    if (to_tmem) umma::row_to_tmem(lane_base, c_hi, c_lo, hi, lo);
-    if (tile_hi >= 0) { umma::row_to_mn_tile(Tl(tile_hi), tid, hi); umma::row_to_mn_tile(Tl(tile_lo), tid, lo); }
-  };
-  auto put_aux = [&](const float (&xv)[8]) {
+  // this thread's 8 columns -> TMEM A operand (hi, lo) and/or MN tile (hi, lo)
+  auto put = [&](const float (&v)[8], bool to_tmem, uint32_t c_hi, uint32_t c_lo, int tile_hi, int tile_lo) {
     uint32_t hi[8], lo[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) umma::split1(xv[i], hi[i], lo[i]);
-    umma::row8_to_mn_tile(Tl(T_XM_HI), tid, hi);
-    umma::row8_to_mn_tile(Tl(T_XM_LO), tid, lo);
+    umma::split8(v, hi, lo);
+    if (to_tmem) { umma::tmem_st8_raw(lane_base + c_hi, hi); umma::tmem_st8_raw(lane_base + c_lo, lo); }
+    if (tile_hi >= 0) { umma::chunk_to_mn_tile(Tl(tile_hi), row, c, hi); umma::chunk_to_mn_tile(Tl(tile_lo), row, c, lo); }
+  };
+  auto put_aux = [&](const float (&xv)[8]) {       // per-row scalars: written by the c == 0 thread of the row
+    if (c == 0) {
+      uint32_t hi[8], lo[8];
+      umma::split8(xv, hi, lo);
+      umma::chunk_to_mn_tile(Tl(T_XM_HI), row, 0, hi);
+      umma::chunk_to_mn_tile(Tl(T_XM_LO), row, 0, lo);
+    }
   };
 
-  // running[run .. run+32) += fresh[src .. src+32) ; running[run+32 .. run+40) += fresh[src8 .. src8+8)   (IEEE adds)
+  // running[run + col0 ..+8) += fresh[src + col0 ..+8) ; running[run+32+2c ..+2) += fresh[src8+2c ..+2)   (IEEE adds)
   auto merge = [&](uint32_t run, uint32_t src, uint32_t src8, bool wide) {
-    float f[32], q[32];
+    float f2[2], q2[2];
+    umma::tmem_ld2_nowait(quad_base + src8 + 2 * c, f2);
+    umma::tmem_ld2_nowait(quad_base + run + (wide ? 32 : 0) + 2 * c, q2);
     if (wide) {
-      umma::tmem_ld32(lane_base + src, f);
-      umma::tmem_ld32(lane_base + run, q);
+      float f[8], r8[8];
+      umma::tmem_ld8_nowait(lane_base + src, f);
+      umma::tmem_ld8_nowait(lane_base + run, r8);
+      umma::wait_ld();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) q[i] += f[i];
-      umma::tmem_st32(lane_base + run, q);
+      for (int i = 0; i < 8; ++i) r8[i] += f[i];
+      umma::tmem_st8(lane_base + run, r8);
+    } else {
+      umma::wait_ld();
     }
-    float f8[8], q8[8];
-    umma::tmem_ld8(lane_base + src8, f8);
-    umma::tmem_ld8(lane_base + run + (wide ? 32 : 0), q8);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) q8[i] += f8[i];
-    umma::tmem_st8(lane_base + run + (wide ? 32 : 0), q8);
+    q2[0] += f2[0];
+    q2[1] += f2[1];
+    umma::tmem_st2(quad_base + run + (wide ? 32 : 0) + 2 * c, q2);
     umma::wait_st();
   };
 
-  for (int64_t tile = worker; tile < a.n_tiles; tile += n_workers) {
+  for (int64_t round = 0; round * n_workers < a.n_tiles; ++round) {
+    const int64_t tile = snake_tile(round, worker, n_workers);
+    if (tile >= a.n_tiles) continue;
     const int64_t slot0 = a.tile_slot_off[tile];
     const int kmax = a.tile_kmax[tile];
-    const int u = a.perm[tile * R + tid];
+    const int u = a.perm[tile * R + row];
     const int ke = u >= 0 ? a.kenc[u] : 0;
     float x[MAX_DX], xs[MAX_DX];
 #pragma unroll
@@ -374,9 +436,9 @@ __global__ void __launch_bounds__(R, 1) k_tiled_backward(SweepArgs a) {
       x[e] = (e < dx && u >= 0) ? a.values[(int64_t)u * dx + e] : 0.0f;
       xs[e] = scale_fwd_rt(sc_kind, x[e]);
     }
-    float g[32], hrow[32], z[32], acc[32], d[32];
+    float g[8], hrow[8], z[8], acc[8], d[8], cb[8], cw[8];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) g[j] = 0.0f;
+    for (int j = 0; j < 8; ++j) g[j] = 0.0f;
 
     // ---- readout backward at a hidden state `hrow`; adds d loss / d hrow to g ----
     auto out_backward = [&](const float* __restrict__ gsrc, int64_t obs, bool live) {
@@ -389,36 +451,36 @@ __global__ void __launch_bounds__(R, 1) k_tiled_backward(SweepArgs a) {
       for (int i = 0; i < 8; ++i) xv[i] = 0.0f;
       xv[0] = 1.0f;
 #pragma unroll
-      for (int o = 0; o < MAX_O; ++o) xv[1 + o] = dY[o];
+      for (int o = 0; o < MAX_O; ++o) { xv[1 + o] = dY[o]; dbo[o] += dY[o]; }
       put_aux(xv);
       publish();
-      if (tid == 0) {
+      if (warp == 0 && umma::elect_one()) {
         umma::fence_after_sync();
         issue_chain(tmem + B_ACCR, tmem + B_AHI, tmem + B_ALO, W(WB_OUT0, 0), W(WB_OUT0, 1));
         umma::commit(&ctl.bar_chain);
       }
-      // readout-bias gradient: sum of dY over rows
+      // d (readout hidden pre-activation) needs sum_o dY[o] * w_out1[o][j]: prepare while the MMA runs
+      float dz[8];
 #pragma unroll
-      for (int o = 0; o < MAX_O; ++o) {
-        float v = dY[o];
+      for (int j = 0; j < 8; ++j) dz[j] = 0.0f;
 #pragma unroll
-        for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(NJODE_FULL, v, sft);
-        if (lane == 0 && o < O) atomicAdd(&sp.dbo1[o], v);
+      for (int o = 0; o < MAX_O; ++o) if (o < O) {
+        ld8(sp.w_out1[o] + col0, cw);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dz[j] = fmaf(dY[o], cw[j], dz[j]);
       }
+      ld8(sp.b_out0 + col0, cb);
       wait_chain();
-      umma::tmem_ld32(lane_base + B_ACCR, acc);
+      umma::tmem_ld8(lane_base + B_ACCR, acc);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        z[j] = act_fwd<ACT>(acc[j] + sp.b_out0[j]);
-        float dz = 0.0f;
-#pragma unroll
-        for (int o = 0; o < MAX_O; ++o) if (o < O) dz = fmaf(dY[o], sp.w_out1[o][j], dz);
-        d[j] = dz * act_grad_from_out<ACT>(z[j]);
+      for (int j = 0; j < 8; ++j) {
+        z[j] = act_fwd<ACT>(acc[j] + cb[j]);
+        d[j] = dz[j] * act_grad_from_out<ACT>(z[j]);
       }
       put(d, true, B_DHI, B_DLO, T_D1M_HI, T_D1M_LO);
       put(z, false, 0, 0, T_D0M_HI, T_D0M_LO);
       publish();
-      if (tid == 0) {
+      if (warp == 0 && umma::elect_one()) {
         umma::fence_after_sync();
         issue_chain(tmem + B_ACCD, tmem + B_DHI, tmem + B_DLO, W(WB_OUT0T, 0), W(WB_OUT0T, 1));
         umma::commit(&ctl.bar_chain);
@@ -426,25 +488,37 @@ __global__ void __launch_bounds__(R, 1) k_tiled_backward(SweepArgs a) {
         umma::commit(&ctl.bar_wgrad);
       }
       wait_chain();
-      umma::tmem_ld32(lane_base + B_ACCD, acc);
+      umma::tmem_ld8(lane_base + B_ACCD, acc);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) g[j] += acc[j];
+      for (int j = 0; j < 8; ++j) g[j] += acc[j];
       wait_wgrad();
       merge(B_RUN_OUT, B_SACC, B_SACC + 32, true);
     };
 
     // ---- preds_before[u+1] = out(h_end) ----
-    load_row32(ckpt + ((slot0 + kmax) * R + tid) * H, hrow);
+    ld8(ckpt + ((slot0 + kmax) * R + row) * H + col0, hrow);
     out_backward(a.grad_preds_before, (int64_t)u + 1, u >= 0 && (ke & 1));
 
     // ---- Euler steps, last to first ----
+    float hnext[8];                                   // prefetched checkpoint of the next (earlier) step
+    float tn = a.knots[(slot0 + kmax) * R + row];
+    float tc_next = kmax > 0 ? a.knots[(slot0 + kmax - 1) * R + row] : tn;
+    ld8(ckpt + ((slot0 + (kmax > 0 ? kmax - 1 : 0)) * R + row) * H + col0, hnext);
     for (int k = kmax - 1; k >= 0; --k) {
-      const float tc = a.knots[(slot0 + k) * R + tid], tn = a.knots[(slot0 + k + 1) * R + tid];
-      const float delta = __fsub_rn(tn, tc);            // 0 for rows that took fewer than k+1 steps
-      load_row32(ckpt + ((slot0 + k) * R + tid) * H, hrow);
+      TR(1);
+      const float tc = tc_next;
+      const float delta = __fsub_rn(tn, tc);          // 0 for rows that took fewer than k+1 steps
+      tn = tc;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) hrow[j] = hnext[j];
+      {  // prefetch step k-1 (or the h0 checkpoint again for the readout at the observation)
+        const int kn = k > 0 ? k - 1 : 0;
+        ld8(ckpt + ((slot0 + kn) * R + row) * H + col0, hnext);
+        tc_next = a.knots[(slot0 + kn) * R + row];
+      }
       if (sc_kind != NJODE_SCALE_IDENTITY) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) hrow[j] = scale_fwd_rt(sc_kind, hrow[j]);
+        for (int j = 0; j < 8; ++j) hrow[j] = scale_fwd_rt(sc_kind, hrow[j]);
       }
       put(hrow, true, B_AHI, B_ALO, T_AM_HI, T_AM_LO);
       float xv[8];
@@ -457,65 +531,92 @@ __global__ void __launch_bounds__(R, 1) k_tiled_backward(SweepArgs a) {
       xv[2 + dx] = delta;
       put_aux(xv);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) d[j] = delta * g[j];                       // d loss / d f(h)
+      for (int j = 0; j < 8; ++j) d[j] = delta * g[j];                       // d loss / d f(h)
       put(d, true, B_DHI, B_DLO, T_D1M_HI, T_D1M_LO);
+      TR(2);
       publish();
-      if (tid == 0) {
+      TR(3);
+      if (warp == 0 && umma::elect_one()) {
         umma::fence_after_sync();
         issue_chain(tmem + B_ACCR, tmem + B_AHI, tmem + B_ALO, W(WB_ODE0, 0), W(WB_ODE0, 1));      // recompute
         issue_chain(tmem + B_ACCD, tmem + B_DHI, tmem + B_DLO, W(WB_ODE1T, 0), W(WB_ODE1T, 1));    // d z0
         umma::commit(&ctl.bar_chain);
       }
-      wait_chain();
-      umma::tmem_ld32(lane_base + B_ACCR, acc);
+      TR(4);
+      // the part of the hidden pre-activation that does not come from the GEMM: bias + x, t, dt columns
+      ld8(sp.b_ode0 + col0, cb);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float v = acc[j] + sp.b_ode0[j];
+      for (int e = 0; e < MAX_DX; ++e) if (e < dx) {
+        ld8(sp.ext_ode0[e] + col0, cw);
 #pragma unroll
-        for (int e = 0; e < MAX_DX; ++e) if (e < dx) v = fmaf(sp.ext_ode0[e][j], xs[e], v);
-        v = fmaf(sp.ext_ode0[dx][j], tc, v);
-        v = fmaf(sp.ext_ode0[dx + 1][j], delta, v);
-        z[j] = act_fwd<ACT>(v);
+        for (int j = 0; j < 8; ++j) cb[j] = fmaf(cw[j], xs[e], cb[j]);
       }
-      put(z, false, 0, 0, T_ZM_HI, T_ZM_LO);
-      umma::tmem_ld32(lane_base + B_ACCD, acc);
+      ld8(sp.ext_ode0[dx] + col0, cw);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) d[j] = acc[j] * act_grad_from_out<ACT>(z[j]);   // d loss / d a0
+      for (int j = 0; j < 8; ++j) cb[j] = fmaf(cw[j], tc, cb[j]);
+      ld8(sp.ext_ode0[dx + 1] + col0, cw);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cb[j] = fmaf(cw[j], delta, cb[j]);
+      wait_chain();
+      TR(5);
+      umma::tmem_ld8_nowait(lane_base + B_ACCR, acc);
+      umma::tmem_ld8_nowait(lane_base + B_ACCD, d);
+      umma::wait_ld();
+      TR(6);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        z[j] = act_fwd<ACT>(acc[j] + cb[j]);
+        d[j] = d[j] * act_grad_from_out<ACT>(z[j]);                          // d loss / d a0
+      }
       put(d, true, B_DHI, B_DLO, T_D0M_HI, T_D0M_LO);
+      put(z, false, 0, 0, T_ZM_HI, T_ZM_LO);
+      TR(7);
       publish();
-      if (tid == 0) {
+      TR(8);
+      if (warp == 0 && umma::elect_one()) {
         umma::fence_after_sync();
         issue_chain(tmem + B_ACCD, tmem + B_DHI, tmem + B_DLO, W(WB_ODE0T, 0), W(WB_ODE0T, 1));    // d s(h)
         umma::commit(&ctl.bar_chain);
         issue_wgrad<72>(tmem + B_SACC, Tl(T_D1M_HI), Tl(T_D1M_LO), Tl(T_ZM_HI), Tl(T_ZM_LO));
         umma::commit(&ctl.bar_wgrad);
       }
+      TR(9);
       wait_chain();
-      umma::tmem_ld32(lane_base + B_ACCD, acc);
+      TR(10);
+      umma::tmem_ld8(lane_base + B_ACCD, acc);
       if (sc_kind == NJODE_SCALE_IDENTITY) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) g[j] += acc[j];
+        for (int j = 0; j < 8; ++j) g[j] += acc[j];
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) g[j] = fmaf(acc[j], scale_grad_rt(sc_kind, hrow[j]), g[j]);
+        for (int j = 0; j < 8; ++j) g[j] = fmaf(acc[j], scale_grad_rt(sc_kind, hrow[j]), g[j]);
       }
+      TR(11);
       wait_wgrad();
-      // accumulator rows 0-31 (warps 0,1) are the d f rows: W1 block = columns 0-31; rows 32-63 (warps 2,3) are
-      // the d a0 rows: W0 block = columns 32-63; column 64.. = bias, x, t, dt gradients for either
-      merge(B_RUN_ODE, B_SACC + (warp < 2 ? 0 : 32), B_SACC + 64, true);
+      TR(12);
+      // accumulator rows 0-31 (quadrants 0,1) are the d f rows: W1 block = columns 0-31; rows 32-63 (quadrants 2,3)
+      // are the d a0 rows: W0 block = columns 32-63; column 64.. = bias, x, t, dt gradients for either
+      merge(B_RUN_ODE, B_SACC + (q < 2 ? 0 : 32), B_SACC + 64, true);
+      TR(13);
     }
 
     // ---- preds[u] = out(h0), then the jump net ----
-    load_row32(ckpt + ((slot0 + 0) * R + tid) * H, hrow);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hrow[j] = hnext[j];
+    if (kmax == 0) ld8(ckpt + ((slot0 + 0) * R + row) * H + col0, hrow);
     out_backward(a.grad_preds, u, u >= 0);
     {
       // z = first jump layer (recomputed), d = d loss / d (pre-activation of h0)
+      ld8(sp.b_jump0 + col0, z);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float v = sp.b_jump0[j];
+      for (int e = 0; e < MAX_DX; ++e) if (e < dx) {
+        ld8(sp.w_jump0[e] + col0, cw);
 #pragma unroll
-        for (int e = 0; e < MAX_DX; ++e) if (e < dx) v = fmaf(sp.w_jump0[e][j], x[e], v);
-        z[j] = act_fwd<ACT>(v);
+        for (int j = 0; j < 8; ++j) z[j] = fmaf(cw[j], x[e], z[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        z[j] = act_fwd<ACT>(z[j]);
         d[j] = g[j] * act_grad_from_out<ACT>(hrow[j]);
       }
       put(d, true, B_DHI, B_DLO, T_D1M_HI, T_D1M_LO);
@@ -528,7 +629,7 @@ __global__ void __launch_bounds__(R, 1) k_tiled_backward(SweepArgs a) {
       for (int e = 0; e < MAX_DX; ++e) if (e < dx) xv[1 + e] = x[e];
       put_aux(xv);
       publish();
-      if (tid == 0) {
+      if (warp == 0 && umma::elect_one()) {
         umma::fence_after_sync();
         issue_chain(tmem + B_ACCD, tmem + B_DHI, tmem + B_DLO, W(WB_JUMP1T, 0), W(WB_JUMP1T, 1));
         umma::commit(&ctl.bar_chain);
@@ -536,14 +637,14 @@ __global__ void __launch_bounds__(R, 1) k_tiled_backward(SweepArgs a) {
         umma::commit(&ctl.bar_wgrad);
       }
       wait_chain();
-      umma::tmem_ld32(lane_base + B_ACCD, acc);
+      umma::tmem_ld8(lane_base + B_ACCD, acc);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) d[j] = acc[j] * act_grad_from_out<ACT>(z[j]);
+      for (int j = 0; j < 8; ++j) d[j] = acc[j] * act_grad_from_out<ACT>(z[j]);
       wait_wgrad();
       merge(B_RUN_J1, B_SACC, B_SACC + 32, true);
       put(d, false, 0, 0, T_D1M_HI, T_D1M_LO);
       publish();
-      if (tid == 0) {
+      if (warp == 0 && umma::elect_one()) {
         umma::fence_after_sync();
         issue_wgrad<8>(tmem + B_SACC, Tl(T_D1M_HI), Tl(T_D1M_LO), Tl(T_XM_HI), Tl(T_XM_LO));
         umma::commit(&ctl.bar_wgrad);
@@ -559,42 +660,51 @@ __global__ void __launch_bounds__(R, 1) k_tiled_backward(SweepArgs a) {
   umma::fence_after_sync();
   {
     const bool has_row = lane < 16;                 // M = 64 accumulator: row i lives in lane (i%16) + 32*(i/16)
-    const int i = warp * 16 + lane;                 // 0..63 when has_row
+    const int i = q * 16 + lane;                    // 0..63 when has_row
     const int j = i & 31;
     const int ld0 = H + dx + 2;
-    float v[32], v8[8];
+    float v[8], v8[8];
     // ODE net: running rows 0-31 = second layer (W1, b1), rows 32-63 = first layer (W0 incl. x/t/dt columns, b0)
-    umma::tmem_ld32(lane_base + B_RUN_ODE, v);
-    umma::tmem_ld8(lane_base + B_RUN_ODE + 32, v8);
+    umma::tmem_ld8_nowait(lane_base + B_RUN_ODE, v);
+    umma::tmem_ld8(quad_base + B_RUN_ODE + 32, v8);
     if (has_row && i < 32) {
-      for (int k = 0; k < 32; ++k) part[T.w_off[NET_ODE][1] + j * H + k] = v[k];
-      part[T.b_off[NET_ODE][1] + j] = v8[0];
+      for (int k = 0; k < 8; ++k) part[T.w_off[NET_ODE][1] + j * H + col0 + k] = v[k];
+      if (c == 0) part[T.b_off[NET_ODE][1] + j] = v8[0];
     }
     if (has_row && i >= 32) {
-      for (int k = 0; k < 32; ++k) part[T.w_off[NET_ODE][0] + j * ld0 + k] = v[k];
-      part[T.b_off[NET_ODE][0] + j] = v8[0];
-      for (int e = 0; e < dx + 2; ++e) part[T.w_off[NET_ODE][0] + j * ld0 + H + e] = v8[1 + e];
+      for (int k = 0; k < 8; ++k) part[T.w_off[NET_ODE][0] + j * ld0 + col0 + k] = v[k];
+      if (c == 0) {
+        part[T.b_off[NET_ODE][0] + j] = v8[0];
+        for (int e = 0; e < dx + 2; ++e) part[T.w_off[NET_ODE][0] + j * ld0 + H + e] = v8[1 + e];
+      }
     }
     // output net: rows 0-31 = hidden layer (W, b); rows 32-63 (z rows) x dY columns = readout weights
-    umma::tmem_ld32(lane_base + B_RUN_OUT, v);
-    umma::tmem_ld8(lane_base + B_RUN_OUT + 32, v8);
+    umma::tmem_ld8_nowait(lane_base + B_RUN_OUT, v);
+    umma::tmem_ld8(quad_base + B_RUN_OUT + 32, v8);
     if (has_row && i < 32) {
-      for (int k = 0; k < 32; ++k) part[T.w_off[NET_OUT][0] + j * H + k] = v[k];
-      part[T.b_off[NET_OUT][0] + j] = v8[0];
+      for (int k = 0; k < 8; ++k) part[T.w_off[NET_OUT][0] + j * H + col0 + k] = v[k];
+      if (c == 0) part[T.b_off[NET_OUT][0] + j] = v8[0];
     }
-    if (has_row && i >= 32) { for (int o = 0; o < O; ++o) part[T.w_off[NET_OUT][1] + o * H + j] = v8[1 + o]; }
-    if (tid < O) part[T.b_off[NET_OUT][1] + tid] = sp.dbo1[tid];
+    if (has_row && i >= 32 && c == 0) { for (int o = 0; o < O; ++o) part[T.w_off[NET_OUT][1] + o * H + j] = v8[1 + o]; }
     // jump net
-    umma::tmem_ld32(lane_base + B_RUN_J1, v);
-    umma::tmem_ld8(lane_base + B_RUN_J1 + 32, v8);
+    umma::tmem_ld8_nowait(lane_base + B_RUN_J1, v);
+    umma::tmem_ld8(quad_base + B_RUN_J1 + 32, v8);
     if (has_row && i < 32) {
-      for (int k = 0; k < 32; ++k) part[T.w_off[NET_JUMP][1] + j * H + k] = v[k];
-      part[T.b_off[NET_JUMP][1] + j] = v8[0];
+      for (int k = 0; k < 8; ++k) part[T.w_off[NET_JUMP][1] + j * H + col0 + k] = v[k];
+      if (c == 0) part[T.b_off[NET_JUMP][1] + j] = v8[0];
     }
-    umma::tmem_ld8(lane_base + B_RUN_J0, v8);
-    if (has_row && i < 32) {
+    umma::tmem_ld8(quad_base + B_RUN_J0, v8);
+    if (has_row && i < 32 && c == 0) {
       part[T.b_off[NET_JUMP][0] + j] = v8[0];
       for (int e = 0; e < dx; ++e) part[T.w_off[NET_JUMP][0] + j * dx + e] = v8[1 + e];
+    }
+    // readout bias: per-row sums -> fixed-order block reduction (deterministic)
+    if (c == 0) *reinterpret_cast<float4*>(sp.red[0][row]) = make_float4(dbo[0], dbo[1], dbo[2], dbo[3]);
+    __syncthreads();
+    if (tid < O) {
+      float sum = 0.0f;
+      for (int r = 0; r < R; ++r) sum += sp.red[0][r][tid];
+      part[T.b_off[NET_OUT][1] + tid] = sum;
     }
   }
   if (!ok && tid == 0) atomicOr(&g_tiled_status, 2u);
@@ -609,13 +719,13 @@ int launch_tiled(const SweepArgs& a, cudaStream_t st, bool backward) {
   if (backward) {
     NJODE_CUDA_OK(cudaFuncSetAttribute(k_tiled_backward<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
     njode_timing_begin(2, st);
-    k_tiled_backward<ACT><<<a.n_workers, R, BWD_SMEM, st>>>(a);
+    k_tiled_backward<ACT><<<a.n_workers, NT, BWD_SMEM, st>>>(a);
     njode_timing_end(2, st);
     NJODE_LAUNCH_OK("k_tiled_backward");
   } else {
     NJODE_CUDA_OK(cudaFuncSetAttribute(k_tiled_forward<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM));
     njode_timing_begin(1, st);
-    k_tiled_forward<ACT><<<a.n_workers, R, FWD_SMEM, st>>>(a);
+    k_tiled_forward<ACT><<<a.n_workers, NT, FWD_SMEM, st>>>(a);
     njode_timing_end(1, st);
     NJODE_LAUNCH_OK("k_tiled_forward");
   }
@@ -657,14 +767,31 @@ int njode_tiled_workers(const NjodeDesc* d, int64_t n_tiles) {
 
 int njode_tiled_forward(const SweepArgs& a_in, cudaStream_t st) {
   SweepArgs a = a_in;
-  // forward CTAs use 128 TMEM columns and ~55 KB smem: up to 4 per SM
+  // forward CTAs use 128 TMEM columns, ~45 KB smem and 512 threads: 2 per SM
   const int S = a.T.S;
-  int64_t per_stack = (int64_t)sm_count() * 4 / S;
+  int64_t per_stack = (int64_t)sm_count() * 2 / S;
   if (per_stack > a.n_tiles) per_stack = a.n_tiles > 0 ? a.n_tiles : 1;
   a.n_workers = (int)(per_stack * S);
   return dispatch_tiled(a, st, false);
 }
 int njode_tiled_backward(const SweepArgs& a, cudaStream_t st) { return dispatch_tiled(a, st, true); }
+
+// make TRACE=1 only: copy the phase trace of CTA 0 to the host and reset it; returns the number of records
+extern "C" int njode_tiled_trace_fetch(long long* out_host, int cap) {
+#ifdef NJODE_TRACE
+  int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(int));
+  if (n > cap) n = cap;
+  if (n > 0) cudaMemcpyFromSymbol(out_host, g_trace, (size_t)n * sizeof(long long));
+  const int zero = 0;
+  cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(int));
+  return n;
+#else
+  (void)out_host; (void)cap;
+  return -1;
+#endif
+}
 
 int njode_tiled_status(unsigned* out_host) {
   NJODE_CUDA_OK(cudaMemcpyFromSymbol(out_host, g_tiled_status, sizeof(unsigned)));

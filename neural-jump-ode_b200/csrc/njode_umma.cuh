@@ -191,6 +191,41 @@ __device__ __forceinline__ void split32(const float (&v)[32], uint32_t (&hi)[32]
   for (int i = 0; i < 32; ++i) split1(v[i], hi[i], lo[i]);
 }
 
+// 8 / 2 columns per thread: four warps share a TMEM lane quadrant (warp % 4) and each owns an 8-column
+// slice of a 32-column operand / accumulator (tools/umma_probe4.cu validated the shared-quadrant access)
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float (&v)[8]) {
+  uint32_t u[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]) : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void tmem_st8_raw(uint32_t taddr, const uint32_t (&u)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld2_nowait(uint32_t taddr, float (&v)[2]) {
+  uint32_t u0, u1;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(u0), "=r"(u1) : "r"(taddr));
+  v[0] = __uint_as_float(u0);
+  v[1] = __uint_as_float(u1);
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, const float (&v)[2]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};"
+               :: "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])) : "memory");
+}
+__device__ __forceinline__ void split8(const float (&v)[8], uint32_t (&hi)[8], uint32_t (&lo)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split1(v[i], hi[i], lo[i]);
+}
+// columns [8c, 8c+8) of row r -> MN-major tile (one 32-byte chunk, position c ^ r%4)
+__device__ __forceinline__ void chunk_to_mn_tile(float* tile, int r, int c, const uint32_t (&v)[8]) {
+  uint4* row = reinterpret_cast<uint4*>(tile + r * 32);
+  const int chunk = (c ^ (r & 3)) * 2;
+  row[chunk] = make_uint4(v[0], v[1], v[2], v[3]);
+  row[chunk + 1] = make_uint4(v[4], v[5], v[6], v[7]);
+}
+
 // this thread's row -> TMEM columns [col_hi, +32) and [col_lo, +32) of its lane (A operand of a chain GEMM)
 __device__ __forceinline__ void row_to_tmem(uint32_t lane_base, uint32_t col_hi, uint32_t col_lo,
                                             const uint32_t (&hi)[32], const uint32_t (&lo)[32]) {
