@@ -127,8 +127,10 @@ extern "C" int32_t njode_tile_rows(const NjodeDesc* d) {
 
 extern "C" int64_t njode_ckpt_row_floats(const NjodeDesc* d) {
   const char* why = nullptr;
-  if (!njode_desc_ok(d, &why)) { njode_set_error("njode_ckpt_row_floats: %s", why); return -1; }
-  return d->hidden;
+  const int impl = pick_impl(d, &why);
+  if (!impl) { njode_set_error("njode_ckpt_row_floats: %s", why); return -1; }
+  // the tiled kernels also keep the hidden-layer activation of every step (see njode_tiled.cu)
+  return impl == NJODE_IMPL_TILED ? 2 * d->hidden : d->hidden;
 }
 
 // ------------------------------------------------------------------------------------------------

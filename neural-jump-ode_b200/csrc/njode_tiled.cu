@@ -45,26 +45,45 @@ struct __align__(16) SmallParams {
 // sticky diagnostic word: bit 0 = forward, bit 1 = backward saw an mbarrier wait time out (njode_device_status)
 __device__ unsigned g_tiled_status = 0;
 
-// optional phase trace (make TRACE=1): thread 0 of CTA 0 records (clock64 << 8 | id) at phase boundaries
+// optional phase trace (`make trace`): one thread per role of CTA 0 records (clock64 << 8 | id) at phase
+// boundaries.  Forward: thread 0 writes straight to global memory.  Reverse sweep: worker thread 0 and the MMA
+// issuer write into a shared-memory ring (a global store in front of the release-arrive of a hand-over would
+// itself cost an L2 round trip and distort the trace) that is dumped when the role finishes.
 #ifdef NJODE_TRACE
-#define NJODE_TRACE_CAP 8192
+#define NJODE_TRACE_CAP 12288
+#define NJODE_TRACE_SMEM_REC 512
 __device__ long long g_trace[NJODE_TRACE_CAP];
-__device__ int g_trace_n = 0;
-#define TR(id) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const int n__ = g_trace_n; if (n__ < NJODE_TRACE_CAP) { \
-    g_trace[n__] = (clock64() << 8) | (long long)(id); g_trace_n = n__ + 1; } } } while (0)
+__device__ int g_trace_n[3] = {0, 0, 0};
+#define TR_DECL(part) const int tr_base__ = (part) * (NJODE_TRACE_CAP / 3); int tr_n__ = 0; \
+    const bool tr_on__ = (threadIdx.x == ((part) == 2 ? NT : 0)) && blockIdx.x == 0; long long* tr_smem__ = nullptr; (void)tr_smem__
+#define TR_SMEM(ptr) tr_smem__ = (ptr)
+#define TR(id) do { if (tr_on__) { const long long v__ = (clock64() << 8) | (long long)(id); \
+    if (tr_smem__) { tr_smem__[tr_n__ & (NJODE_TRACE_SMEM_REC - 1)] = v__; ++tr_n__; } \
+    else if (tr_n__ < NJODE_TRACE_CAP / 3) { g_trace[tr_base__ + tr_n__] = v__; ++tr_n__; } } } while (0)
+#define TR_END(part) do { if (tr_on__) { int n__ = tr_n__; \
+    if (tr_smem__) { n__ = n__ < NJODE_TRACE_SMEM_REC ? n__ : NJODE_TRACE_SMEM_REC; \
+      for (int i__ = 0; i__ < n__; ++i__) g_trace[tr_base__ + i__] = tr_smem__[(tr_n__ - n__ + i__) & (NJODE_TRACE_SMEM_REC - 1)]; } \
+    g_trace_n[part] = n__; } } while (0)
+#define NJODE_TRACE_SMEM_BYTES (2 * NJODE_TRACE_SMEM_REC * 8)
+#define TRW_FLIP ph_tw ^= 1u     /* issuer: parity of the weight-gradient barrier (trace build measures its completion) */
 #else
+#define TRW_FLIP do { } while (0)
+#define TR_DECL(part) do { } while (0)
+#define TR_SMEM(ptr) do { } while (0)
 #define TR(id) do { } while (0)
+#define TR_END(part) do { } while (0)
+#define NJODE_TRACE_SMEM_BYTES 0
 #endif
 
 struct Ctl {
-  uint64_t bar_chain, bar_wgrad;
+  uint64_t bar_chain, bar_wgrad, bar_ops;
   uint32_t tmem_base;
   uint32_t timeout;
 };
 
 // weight tile W[n][k] (transpose: W^T) -> tf32 hi / lo, K-major 128B-swizzled B operand
-__device__ __forceinline__ void load_wtile(float* hi, float* lo, const float* __restrict__ W, int ld, bool transpose) {
-  for (int idx = threadIdx.x; idx < WT_F; idx += NT) {
+__device__ __forceinline__ void load_wtile(float* hi, float* lo, const float* __restrict__ W, int ld, bool transpose, int nthreads) {
+  for (int idx = threadIdx.x; idx < WT_F; idx += nthreads) {
     const int n = idx >> 5, k = idx & 31;
     const float v = transpose ? W[k * ld + n] : W[n * ld + k];
     const float h = umma::tf32_hi(v);
@@ -99,11 +118,17 @@ __device__ __forceinline__ void st8_stream(float* __restrict__ dst, const float 
   __stcs(reinterpret_cast<float4*>(dst) + 1, make_float4(v[4], v[5], v[6], v[7]));
 }
 
-// 3xTF32 chain GEMM, A from TMEM: acc = A * B^T   (issued by one thread)
-__device__ __forceinline__ void issue_chain(uint32_t tmem_acc, uint32_t tmem_a_hi, uint32_t tmem_a_lo,
-                                            const float* b_hi, const float* b_lo) {
+// Operands are addressed through descriptor bases: every weight tile / MN tile sits at a compile-time offset
+// from the first one, so a descriptor is base + constant (the 14-bit address field cannot overflow: shared
+// memory is < 256 KB) and the issuer keeps only two 64-bit bases in registers.
+constexpr uint64_t WT_DESC_STEP = WT_F * 4 / 16;     // one weight tile (4 KB) in descriptor address units
+constexpr uint64_t MN_DESC_STEP = TILE_F * 4 / 16;   // one MN tile (16 KB)
+__device__ __forceinline__ uint64_t wdesc(uint64_t wbase, int id, int lo) { return wbase + (uint64_t)(id * 2 + lo) * WT_DESC_STEP; }
+__device__ __forceinline__ uint64_t tdesc(uint64_t tbase, int id) { return tbase + (uint64_t)id * MN_DESC_STEP; }
+
+// 3xTF32 chain GEMM, A from TMEM: acc = A * B^T   (issued by one thread); dbh / dbl = K-major descriptors of B hi / lo
+__device__ __forceinline__ void issue_chain(uint32_t tmem_acc, uint32_t tmem_a_hi, uint32_t tmem_a_lo, uint64_t dbh, uint64_t dbl) {
   constexpr uint32_t idesc = umma::idesc_tf32(128, 32, 0, 0);
-  const uint64_t dbh = umma::desc_k(umma::smem_u32(b_hi)), dbl = umma::desc_k(umma::smem_u32(b_lo));
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) umma::mma_ts(tmem_acc, tmem_a_lo + 8 * ks, dbh + 2 * ks, idesc, ks > 0);
 #pragma unroll
@@ -114,17 +139,38 @@ __device__ __forceinline__ void issue_chain(uint32_t tmem_acc, uint32_t tmem_a_h
 
 // 3xTF32 row-contraction GEMM: acc[64 x N] = [A0|A1]^T (MN-major tiles, rows = contraction) * [B0|B1|..]
 template <int N>
-__device__ __forceinline__ void issue_wgrad(uint32_t tmem_acc, const float* a_hi, const float* a_lo,
-                                            const float* b_hi, const float* b_lo) {
+__device__ __forceinline__ void issue_wgrad(uint32_t tmem_acc, uint64_t dah, uint64_t dal, uint64_t dbh, uint64_t dbl) {
   constexpr uint32_t idesc = umma::idesc_tf32(64, N, 1, 1);
-  const uint64_t dah = umma::desc_mn(umma::smem_u32(a_hi), TILE_F * 4), dal = umma::desc_mn(umma::smem_u32(a_lo), TILE_F * 4);
-  const uint64_t dbh = umma::desc_mn(umma::smem_u32(b_hi), TILE_F * 4), dbl = umma::desc_mn(umma::smem_u32(b_lo), TILE_F * 4);
 #pragma unroll
   for (int ks = 0; ks < 16; ++ks) umma::mma_ss(tmem_acc, dal + 64 * ks, dbh + 64 * ks, idesc, ks > 0);   // fresh accumulator
 #pragma unroll
   for (int ks = 0; ks < 16; ++ks) umma::mma_ss(tmem_acc, dah + 64 * ks, dbl + 64 * ks, idesc, 1);
 #pragma unroll
   for (int ks = 0; ks < 16; ++ks) umma::mma_ss(tmem_acc, dah + 64 * ks, dbh + 64 * ks, idesc, 1);
+}
+
+// input scaling of 8 values with ONE warp-uniform switch (a per-element runtime switch bloats the loops)
+__device__ __forceinline__ void scale8(int sc, float (&v)[8]) {
+  if (sc == NJODE_SCALE_TANH) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = tanhf(v[j]);
+  } else if (sc == NJODE_SCALE_SIGMOID) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 1.0f / (1.0f + expf(-v[j]));
+  }
+}
+// g += acc * s'(.) expressed through the scaled value sv
+__device__ __forceinline__ void scale_grad_acc8(int sc, const float (&acc)[8], const float (&sv)[8], float (&g)[8]) {
+  if (sc == NJODE_SCALE_TANH) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = fmaf(acc[j], 1.0f - sv[j] * sv[j], g[j]);
+  } else if (sc == NJODE_SCALE_SIGMOID) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = fmaf(acc[j], sv[j] * (1.0f - sv[j]), g[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] += acc[j];
+  }
 }
 
 __device__ __forceinline__ int64_t pred_index(const ParamTable& T, int64_t obs, int s, int o) {
@@ -154,17 +200,21 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
 
   const ParamTable& T = a.T;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  TR_DECL(0);
   const int q = warp & 3, c = warp >> 2, row = q * 32 + lane, col0 = c * CW;
   const int s = blockIdx.x % T.S;
   const int worker = blockIdx.x / T.S, n_workers = gridDim.x / T.S;
   const float* p = a.params + (int64_t)s * T.stack_floats;
   const int dx = T.d_x, O = T.O, sc_kind = a.desc.input_scaling;
-  float* ckpt = a.ckpt ? a.ckpt + (int64_t)s * a.total_slots * R * H : nullptr;
+  // checkpoints: [stack][slot][plane][row][32]; plane 0 = hidden state before the step of this slot (after the
+  // last step for the tile's final slot), plane 1 = hidden-layer activation z of that step (saves the reverse
+  // sweep the re-computation GEMM and its epilogue)
+  float* ckpt = a.ckpt ? a.ckpt + (int64_t)s * a.total_slots * (2 * R * H) : nullptr;
 
-  load_wtile(wt + (FW_ODE0 * 2) * WT_F, wt + (FW_ODE0 * 2 + 1) * WT_F, p + T.w_off[NET_ODE][0], H + dx + 2, false);
-  load_wtile(wt + (FW_ODE1 * 2) * WT_F, wt + (FW_ODE1 * 2 + 1) * WT_F, p + T.w_off[NET_ODE][1], H, false);
-  load_wtile(wt + (FW_JUMP1 * 2) * WT_F, wt + (FW_JUMP1 * 2 + 1) * WT_F, p + T.w_off[NET_JUMP][1], H, false);
-  load_wtile(wt + (FW_OUT0 * 2) * WT_F, wt + (FW_OUT0 * 2 + 1) * WT_F, p + T.w_off[NET_OUT][0], H, false);
+  load_wtile(wt + (FW_ODE0 * 2) * WT_F, wt + (FW_ODE0 * 2 + 1) * WT_F, p + T.w_off[NET_ODE][0], H + dx + 2, false, NT);
+  load_wtile(wt + (FW_ODE1 * 2) * WT_F, wt + (FW_ODE1 * 2 + 1) * WT_F, p + T.w_off[NET_ODE][1], H, false, NT);
+  load_wtile(wt + (FW_JUMP1 * 2) * WT_F, wt + (FW_JUMP1 * 2 + 1) * WT_F, p + T.w_off[NET_JUMP][1], H, false, NT);
+  load_wtile(wt + (FW_OUT0 * 2) * WT_F, wt + (FW_OUT0 * 2 + 1) * WT_F, p + T.w_off[NET_OUT][0], H, false, NT);
   load_small(sp, T, p);
   if (tid == 0) {
     umma::mbar_init(&ctl.bar_chain, 1);
@@ -178,6 +228,7 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
   umma::fence_after_sync();
   const uint32_t tmem = ctl.tmem_base;
   const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
+  const uint64_t wbase = umma::desc_k(umma::smem_u32(wt));
   uint32_t phase = 0;
   bool ok = true;
 
@@ -195,11 +246,11 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
     TR(32 + 3);
     if (warp == 0 && umma::elect_one()) {
       umma::fence_after_sync();
-      issue_chain(tmem + F_ACC, tmem + F_AHI, tmem + F_ALO, wt + (wid * 2) * WT_F, wt + (wid * 2 + 1) * WT_F);
+      issue_chain(tmem + F_ACC, tmem + F_AHI, tmem + F_ALO, wdesc(wbase, wid, 0), wdesc(wbase, wid, 1));
       umma::commit(&ctl.bar_chain);
     }
     TR(32 + 4);
-    ok = umma::mbar_wait(&ctl.bar_chain, phase) && ok;
+    ok = ok && umma::mbar_wait(&ctl.bar_chain, phase);
     phase ^= 1;
     umma::fence_after_sync();
     TR(32 + 5);
@@ -236,7 +287,7 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
     ld8(sp.b_jump1 + col0, cb);
 #pragma unroll
     for (int j = 0; j < 8; ++j) h[j] = act_fwd<ACT>(acc[j] + cb[j]);
-    if (ckpt) st8_stream(ckpt + ((slot0 + 0) * R + row) * H + col0, h);
+    if (ckpt) st8_stream(ckpt + ((slot0 + 0) * 2 * R + row) * H + col0, h);
 
     // readout: y = out(h)                                           jump_ode.py:170 / :177, :205-212
     auto readout = [&](float* __restrict__ dst, int64_t obs, bool write) {
@@ -270,13 +321,10 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
       const float tc = tn;
       tn = a.knots[(slot0 + k + 1) * R + row];
       const float delta = __fsub_rn(tn, tc);
-      if (sc_kind != NJODE_SCALE_IDENTITY) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) z[j] = scale_fwd_rt(sc_kind, h[j]);
-        gemm(z, FW_ODE0, acc);
-      } else {
-        gemm(h, FW_ODE0, acc);
-      }
+      for (int j = 0; j < 8; ++j) z[j] = h[j];
+      scale8(sc_kind, z);
+      gemm(z, FW_ODE0, acc);
       ld8(sp.b_ode0 + col0, cb);
 #pragma unroll
       for (int j = 0; j < 8; ++j) z[j] = acc[j] + cb[j];
@@ -292,17 +340,19 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
       ld8(sp.ext_ode0[dx + 1] + col0, cw);
 #pragma unroll
       for (int j = 0; j < 8; ++j) z[j] = act_fwd<ACT>(fmaf(cw[j], delta, z[j]));
+      if (ckpt) st8_stream(ckpt + (((slot0 + k) * 2 + 1) * R + row) * H + col0, z);
       gemm(z, FW_ODE1, acc);
       if (k < K) {
         ld8(sp.b_ode1 + col0, cb);
 #pragma unroll
         for (int j = 0; j < 8; ++j) h[j] = fmaf(delta, acc[j] + cb[j], h[j]);
       }
-      if (ckpt) st8_stream(ckpt + ((slot0 + k + 1) * R + row) * H + col0, h);
+      if (ckpt) st8_stream(ckpt + ((slot0 + k + 1) * 2 * R + row) * H + col0, h);
     }
     readout(a.preds_before, (int64_t)u + 1, u >= 0 && (ke & 1));
   }
 
+  TR_END(0);
   if (!ok && tid == 0) atomicOr(&g_tiled_status, 1u);
   umma::fence_before_sync();
   __syncthreads();
@@ -312,7 +362,7 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
 // ------------------------------------------------------------------------------------------------
 // reverse sweep
 // ------------------------------------------------------------------------------------------------
-enum { WB_ODE0 = 0, WB_ODE1T, WB_ODE0T, WB_OUT0, WB_OUT0T, WB_JUMP1T, WB_COUNT };
+enum { WB_ODE1T = 0, WB_ODE0T, WB_OUT0, WB_OUT0T, WB_JUMP1T, WB_COUNT };
 // shared-memory MN tiles; A = [D1M|D0M], B = [ZM|AM|XM] are consecutive so LBO = one tile
 enum { T_D1M_HI = 0, T_D0M_HI, T_D1M_LO, T_D0M_LO, T_ZM_HI, T_AM_HI, T_XM_HI, T_ZM_LO, T_AM_LO, T_XM_LO, T_COUNT };
 // TMEM columns: chain operands / accumulators, one fresh row-contraction accumulator (72 columns), and the
@@ -320,87 +370,198 @@ enum { T_D1M_HI = 0, T_D0M_HI, T_D1M_LO, T_D0M_LO, T_ZM_HI, T_AM_HI, T_XM_HI, T_
 constexpr uint32_t B_AHI = 0, B_ALO = 32, B_DHI = 64, B_DLO = 96, B_ACCR = 128, B_ACCD = 160, B_SACC = 192,
                    B_RUN_ODE = 288, B_RUN_OUT = 328, B_RUN_J1 = 368, B_RUN_J0 = 408, B_RUN_END = 416,
                    B_TMEM_COLS = 512;
-constexpr size_t BWD_SMEM = 1024 + (size_t)T_COUNT * TILE_F * 4 + WB_COUNT * 2 * WT_F * 4 + sizeof(SmallParams) + sizeof(Ctl);
+constexpr size_t BWD_SMEM = 1024 + (size_t)T_COUNT * TILE_F * 4 + WB_COUNT * 2 * WT_F * 4 + sizeof(SmallParams) + sizeof(Ctl) + 16 + NJODE_TRACE_SMEM_BYTES;
 
-template <int ACT>
-__global__ void __launch_bounds__(NT, 1) k_tiled_backward(SweepArgs a) {
-  extern __shared__ uint8_t smem_raw[];
+constexpr int NT_B = NT + 128;  // 16 worker warps + one warpgroup whose first warp issues the MMAs
+
+struct BwdSmem {
+  float* tiles;        // [T_COUNT][TILE_F]
+  float* wt;           // [WB_COUNT][2][WT_F]
+  SmallParams* sp;
+  Ctl* ctl;
+};
+__device__ __forceinline__ BwdSmem bwd_carve(uint8_t* smem_raw) {
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  float* tiles = reinterpret_cast<float*>(base);                                         // [T_COUNT][TILE_F]
-  float* wt = tiles + (size_t)T_COUNT * TILE_F;                                          // [WB_COUNT][2][WT_F]
-  SmallParams& sp = *reinterpret_cast<SmallParams*>(reinterpret_cast<uint8_t*>(wt) + WB_COUNT * 2 * WT_F * 4);
-  Ctl& ctl = *reinterpret_cast<Ctl*>(reinterpret_cast<uint8_t*>(&sp) + sizeof(SmallParams));
+  BwdSmem m;
+  m.tiles = reinterpret_cast<float*>(base);
+  m.wt = m.tiles + (size_t)T_COUNT * TILE_F;
+  m.sp = reinterpret_cast<SmallParams*>(reinterpret_cast<uint8_t*>(m.wt) + WB_COUNT * 2 * WT_F * 4);
+  m.ctl = reinterpret_cast<Ctl*>(reinterpret_cast<uint8_t*>(m.sp) + sizeof(SmallParams));
+  return m;
+}
 
+// ------------------------------------------------------------------------------------------------
+// MMA issuer (one warp): mirrors the workers' sequence of hand-overs -- 2 per readout, 2 per Euler step,
+// 2 for the jump net.  Everything it needs is re-derived here, after the register re-allocation.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bwd_issuer(const SweepArgs& a, uint8_t* smem_raw) {
+  const BwdSmem m = bwd_carve(smem_raw);
+  Ctl& ctl = *m.ctl;
+  const int S = a.T.S;
+  const int worker = blockIdx.x / S, n_workers = gridDim.x / S;
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&ctl.tmem_base);
+  const uint64_t wbase0 = umma::desc_k(umma::smem_u32(m.wt)), tbase0 = umma::desc_mn(umma::smem_u32(m.tiles), TILE_F * 4);
+  TR_DECL(2);
+  TR_SMEM(reinterpret_cast<long long*>((reinterpret_cast<uintptr_t>(m.ctl + 1) + 15) & ~(uintptr_t)15) + NJODE_TRACE_SMEM_REC);
+  bool ok = true;
+  uint32_t ph_o = 0;
+#ifdef NJODE_TRACE
+  uint32_t ph_tw = 0;
+#endif
+  // (after the first time-out every later wait falls through, so a protocol bug costs seconds, not the GPU)
+  auto wait_ops = [&]() { ok = ok && umma::mbar_wait(&ctl.bar_ops, ph_o); ph_o ^= 1; umma::fence_after_sync(); };
+  // descriptors are base + constant; laundering the bases through an empty asm at every hand-over keeps the
+  // compiler from hoisting ~200 loop-invariant 64-bit descriptors into (spilled) registers
+  uint64_t wbase, tbase;
+  auto fresh = [&]() { wbase = wbase0; tbase = tbase0; asm volatile("" : "+l"(wbase), "+l"(tbase)); };
+  auto issue_readout = [&]() {
+    wait_ops();
+    fresh();
+    if (umma::elect_one()) {
+      issue_chain(tmem + B_ACCR, tmem + B_AHI, tmem + B_ALO, wdesc(wbase, WB_OUT0, 0), wdesc(wbase, WB_OUT0, 1));
+      umma::commit(&ctl.bar_chain);
+    }
+    __syncwarp();
+    wait_ops();
+    fresh();
+    if (umma::elect_one()) {
+      issue_chain(tmem + B_ACCD, tmem + B_DHI, tmem + B_DLO, wdesc(wbase, WB_OUT0T, 0), wdesc(wbase, WB_OUT0T, 1));
+      umma::commit(&ctl.bar_chain);
+      issue_wgrad<40>(tmem + B_SACC, tdesc(tbase, T_D1M_HI), tdesc(tbase, T_D1M_LO), tdesc(tbase, T_AM_HI), tdesc(tbase, T_AM_LO));
+      umma::commit(&ctl.bar_wgrad);
+    }
+    __syncwarp();
+    TRW_FLIP;
+  };
+  for (int64_t round = 0; round * n_workers < a.n_tiles; ++round) {
+    const int64_t tile = snake_tile(round, worker, n_workers);
+    if (tile >= a.n_tiles) continue;
+    const int kmax = a.tile_kmax[tile];
+    issue_readout();
+    for (int k = kmax - 1; k >= 0; --k) {
+      TR(64);
+      wait_ops();
+      TR(65);
+      fresh();
+      if (umma::elect_one()) {
+        issue_chain(tmem + B_ACCD, tmem + B_DHI, tmem + B_DLO, wdesc(wbase, WB_ODE1T, 0), wdesc(wbase, WB_ODE1T, 1));    // d z0
+        umma::commit(&ctl.bar_chain);
+      }
+      __syncwarp();
+      TR(66);
+      wait_ops();
+      TR(67);
+      fresh();
+      if (umma::elect_one()) {
+        issue_chain(tmem + B_ACCD, tmem + B_DHI, tmem + B_DLO, wdesc(wbase, WB_ODE0T, 0), wdesc(wbase, WB_ODE0T, 1));    // d s(h)
+        umma::commit(&ctl.bar_chain);
+        issue_wgrad<72>(tmem + B_SACC, tdesc(tbase, T_D1M_HI), tdesc(tbase, T_D1M_LO), tdesc(tbase, T_ZM_HI), tdesc(tbase, T_ZM_LO));
+        umma::commit(&ctl.bar_wgrad);
+      }
+      __syncwarp();
+      TRW_FLIP;
+      TR(68);
+#ifdef NJODE_TRACE
+      umma::mbar_wait(&ctl.bar_wgrad, ph_tw ^ 1u);              // (waits do not consume the phase: the workers still see it)
+      TR(69);
+#endif
+    }
+    issue_readout();
+    wait_ops();
+    fresh();
+    if (umma::elect_one()) {
+      issue_chain(tmem + B_ACCD, tmem + B_DHI, tmem + B_DLO, wdesc(wbase, WB_JUMP1T, 0), wdesc(wbase, WB_JUMP1T, 1));
+      umma::commit(&ctl.bar_chain);
+      issue_wgrad<40>(tmem + B_SACC, tdesc(tbase, T_D1M_HI), tdesc(tbase, T_D1M_LO), tdesc(tbase, T_AM_HI), tdesc(tbase, T_AM_LO));
+      umma::commit(&ctl.bar_wgrad);
+    }
+    __syncwarp();
+    TRW_FLIP;
+    wait_ops();
+    fresh();
+    if (umma::elect_one()) {
+      issue_wgrad<8>(tmem + B_SACC, tdesc(tbase, T_D1M_HI), tdesc(tbase, T_D1M_LO), tdesc(tbase, T_XM_HI), tdesc(tbase, T_XM_LO));
+      umma::commit(&ctl.bar_wgrad);
+    }
+    __syncwarp();
+    TRW_FLIP;
+  }
+  TR_END(2);
+  if (!ok && (threadIdx.x & 31) == 0) atomicOr(&g_tiled_status, 2u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// row workers (512 threads): load the weights, sweep the tiles, flush the weight-gradient sums
+// ------------------------------------------------------------------------------------------------
+template <int ACT>
+__device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw) {
+  const BwdSmem m = bwd_carve(smem_raw);
+  float* const tiles = m.tiles;
+  float* const wt = m.wt;
+  SmallParams& sp = *m.sp;
+  Ctl& ctl = *m.ctl;
   const ParamTable& T = a.T;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  TR_DECL(1);
+  TR_SMEM(reinterpret_cast<long long*>((reinterpret_cast<uintptr_t>(m.ctl + 1) + 15) & ~(uintptr_t)15));
   const int q = warp & 3, c = warp >> 2, row = q * 32 + lane, col0 = c * CW;
   const int s = blockIdx.x % T.S;
   const int worker = blockIdx.x / T.S, n_workers = gridDim.x / T.S;
   const float* p = a.params + (int64_t)s * T.stack_floats;
-  float* part = a.partials + (int64_t)blockIdx.x * T.stack_floats;
   const int dx = T.d_x, O = T.O, sc_kind = a.desc.input_scaling;
-  const float* ckpt = a.ckpt + (int64_t)s * a.total_slots * R * H;
+  const float* ckpt = a.ckpt + (int64_t)s * a.total_slots * (2 * R * H);     // planes (h, z), see the forward kernel
 
   auto W = [&](int id, int lo) { return wt + (id * 2 + lo) * WT_F; };
-  auto Tl = [&](int id) { return tiles + (size_t)id * TILE_F; };
-
-  load_wtile(W(WB_ODE0, 0), W(WB_ODE0, 1), p + T.w_off[NET_ODE][0], H + dx + 2, false);
-  load_wtile(W(WB_ODE0T, 0), W(WB_ODE0T, 1), p + T.w_off[NET_ODE][0], H + dx + 2, true);
-  load_wtile(W(WB_ODE1T, 0), W(WB_ODE1T, 1), p + T.w_off[NET_ODE][1], H, true);
-  load_wtile(W(WB_OUT0, 0), W(WB_OUT0, 1), p + T.w_off[NET_OUT][0], H, false);
-  load_wtile(W(WB_OUT0T, 0), W(WB_OUT0T, 1), p + T.w_off[NET_OUT][0], H, true);
-  load_wtile(W(WB_JUMP1T, 0), W(WB_JUMP1T, 1), p + T.w_off[NET_JUMP][1], H, true);
+  load_wtile(W(WB_ODE0T, 0), W(WB_ODE0T, 1), p + T.w_off[NET_ODE][0], H + dx + 2, true, NT);
+  load_wtile(W(WB_ODE1T, 0), W(WB_ODE1T, 1), p + T.w_off[NET_ODE][1], H, true, NT);
+  load_wtile(W(WB_OUT0, 0), W(WB_OUT0, 1), p + T.w_off[NET_OUT][0], H, false, NT);
+  load_wtile(W(WB_OUT0T, 0), W(WB_OUT0T, 1), p + T.w_off[NET_OUT][0], H, true, NT);
+  load_wtile(W(WB_JUMP1T, 0), W(WB_JUMP1T, 1), p + T.w_off[NET_JUMP][1], H, true, NT);
   load_small(sp, T, p);
   // MN tiles may hold anything at start; unused rows / columns only feed accumulator cells nobody reads,
   // but NaN * 0 must not leak into used cells: XM columns beyond the 8 used ones are never addressed (N = 72).
   for (int i = tid; i < T_COUNT * TILE_F / 4; i += NT) reinterpret_cast<float4*>(tiles)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (tid == 0) {
-    umma::mbar_init(&ctl.bar_chain, 1);
-    umma::mbar_init(&ctl.bar_wgrad, 1);
-    umma::fence_mbar_init();
-    ctl.timeout = 0;
-  }
-  if (warp == 0) umma::tmem_alloc(&ctl.tmem_base, B_TMEM_COLS);
-  umma::fence_async_smem();
-  umma::fence_before_sync();
-  __syncthreads();
-  umma::fence_after_sync();
-  const uint32_t tmem = ctl.tmem_base;
+
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&ctl.tmem_base);
   const uint32_t quad_base = tmem + ((uint32_t)(q * 32) << 16);     // this warp's lane quadrant, column 0
   const uint32_t lane_base = quad_base + (uint32_t)col0;            // ... at this thread's column slice
+  const uint32_t tiles_s = umma::smem_u32(tiles);
   if (c == 0) {  // zero the persistent weight-gradient accumulators
-    uint32_t zero[32];
+    uint32_t zero[8];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) zero[i] = 0u;
-    for (uint32_t col = 256; col < 448; col += 32) umma::tmem_st32_raw(quad_base + col, zero);   // covers B_RUN_*
+    for (int i = 0; i < 8; ++i) zero[i] = 0u;
+    for (uint32_t col = 256; col < 448; col += 8) umma::tmem_st8_raw(quad_base + col, zero);   // covers B_RUN_*
     umma::wait_st();
   }
-  uint32_t ph_c = 0, ph_w = 0;
+  umma::named_bar_sync(1, NT);     // weights, zeroed tiles and accumulators are in place (the issuer learns it from the first hand-over)
+
   bool ok = true;
+  uint32_t ph_c = 0, ph_w = 0;
   float dbo[MAX_O];                 // readout-bias gradient: this row's dY summed over all tiles (c == 0 threads)
 #pragma unroll
   for (int o = 0; o < MAX_O; ++o) dbo[o] = 0.0f;
 
-  auto wait_chain = [&]() { ok = umma::mbar_wait(&ctl.bar_chain, ph_c) && ok; ph_c ^= 1; umma::fence_after_sync(); };
-  auto wait_wgrad = [&]() { ok = umma::mbar_wait(&ctl.bar_wgrad, ph_w) && ok; ph_w ^= 1; umma::fence_after_sync(); };
-  // make this thread's TMEM / smem writes visible to the MMA issuer, then barrier
-  auto publish = [&]() { umma::wait_st(); umma::fence_async_smem(); umma::fence_before_sync(); __syncthreads(); };
+  auto wait_chain = [&]() { ok = ok && umma::mbar_wait(&ctl.bar_chain, ph_c); ph_c ^= 1; umma::fence_after_sync(); };
+  auto wait_wgrad = [&]() { ok = ok && umma::mbar_wait(&ctl.bar_wgrad, ph_w); ph_w ^= 1; umma::fence_after_sync(); };
+  // make this thread's TMEM / smem operand writes visible to the tensor core, then tell the issuer
+  auto hand_over = [&]() { umma::wait_st(); umma::fence_async_smem(); umma::fence_before_sync(); umma::mbar_arrive(&ctl.bar_ops); };
+  // the same when only TMEM operands were written (no shared-memory tile since the last hand-over)
+  auto hand_over_tmem = [&]() { umma::wait_st(); umma::fence_before_sync(); umma::mbar_arrive(&ctl.bar_ops); };
   // this thread's 8 columns -> TMEM A operand (hi, lo) and/or MN tile (hi, lo)
   auto put = [&](const float (&v)[8], bool to_tmem, uint32_t c_hi, uint32_t c_lo, int tile_hi, int tile_lo) {
     uint32_t hi[8], lo[8];
     umma::split8(v, hi, lo);
     if (to_tmem) { umma::tmem_st8_raw(lane_base + c_hi, hi); umma::tmem_st8_raw(lane_base + c_lo, lo); }
-    if (tile_hi >= 0) { umma::chunk_to_mn_tile(Tl(tile_hi), row, c, hi); umma::chunk_to_mn_tile(Tl(tile_lo), row, c, lo); }
+    if (tile_hi >= 0) { umma::chunk_to_mn_tile(tiles_s + tile_hi * (TILE_F * 4), row, c, hi); umma::chunk_to_mn_tile(tiles_s + tile_lo * (TILE_F * 4), row, c, lo); }
   };
   auto put_aux = [&](const float (&xv)[8]) {       // per-row scalars: written by the c == 0 thread of the row
     if (c == 0) {
       uint32_t hi[8], lo[8];
       umma::split8(xv, hi, lo);
-      umma::chunk_to_mn_tile(Tl(T_XM_HI), row, 0, hi);
-      umma::chunk_to_mn_tile(Tl(T_XM_LO), row, 0, lo);
+      umma::chunk_to_mn_tile(tiles_s + T_XM_HI * (TILE_F * 4), row, 0, hi);
+      umma::chunk_to_mn_tile(tiles_s + T_XM_LO * (TILE_F * 4), row, 0, lo);
     }
   };
-
   // running[run + col0 ..+8) += fresh[src + col0 ..+8) ; running[run+32+2c ..+2) += fresh[src8+2c ..+2)   (IEEE adds)
   auto merge = [&](uint32_t run, uint32_t src, uint32_t src8, bool wide) {
     float f2[2], q2[2];
@@ -426,39 +587,31 @@ __global__ void __launch_bounds__(NT, 1) k_tiled_backward(SweepArgs a) {
   for (int64_t round = 0; round * n_workers < a.n_tiles; ++round) {
     const int64_t tile = snake_tile(round, worker, n_workers);
     if (tile >= a.n_tiles) continue;
-    const int64_t slot0 = a.tile_slot_off[tile];
     const int kmax = a.tile_kmax[tile];
     const int u = a.perm[tile * R + row];
     const int ke = u >= 0 ? a.kenc[u] : 0;
-    float x[MAX_DX], xs[MAX_DX];
+    // this thread's slice of the tile's checkpoint / knot slots (32-bit offsets per step from here on)
+    const float* ck = ckpt + ((int64_t)a.tile_slot_off[tile] * 2 * R + row) * H + col0;
+    const float* kn = a.knots + (int64_t)a.tile_slot_off[tile] * R + row;
+    float xs[MAX_DX];
 #pragma unroll
-    for (int e = 0; e < MAX_DX; ++e) {
-      x[e] = (e < dx && u >= 0) ? a.values[(int64_t)u * dx + e] : 0.0f;
-      xs[e] = scale_fwd_rt(sc_kind, x[e]);
-    }
-    float g[8], hrow[8], z[8], acc[8], d[8], cb[8], cw[8];
+    for (int e = 0; e < MAX_DX; ++e) xs[e] = scale_fwd_rt(sc_kind, (e < dx && u >= 0) ? a.values[(int64_t)u * dx + e] : 0.0f);
+    float g[8], hrow[8], z[8], acc[8], d[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) g[j] = 0.0f;
 
-    // ---- readout backward at a hidden state `hrow`; adds d loss / d hrow to g ----
+    // ---- readout backward at a hidden state `hrow`; adds d loss / d hrow to g (no MMA in flight at entry) ----
     auto out_backward = [&](const float* __restrict__ gsrc, int64_t obs, bool live) {
-      float dY[MAX_O];
+      float dY[MAX_O], cw[8], cb[8];
 #pragma unroll
       for (int o = 0; o < MAX_O; ++o) dY[o] = (live && o < O) ? gsrc[pred_index(T, obs, s, o)] : 0.0f;
       put(hrow, true, B_AHI, B_ALO, T_AM_HI, T_AM_LO);
-      float xv[8];
+      static_assert(MAX_O == 4, "aux column layout assumes <= 4 readout columns");
+      const float xv[8] = {1.0f, dY[0], dY[1], dY[2], dY[3], 0.0f, 0.0f, 0.0f};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) xv[i] = 0.0f;
-      xv[0] = 1.0f;
-#pragma unroll
-      for (int o = 0; o < MAX_O; ++o) { xv[1 + o] = dY[o]; dbo[o] += dY[o]; }
+      for (int o = 0; o < MAX_O; ++o) dbo[o] += dY[o];
       put_aux(xv);
-      publish();
-      if (warp == 0 && umma::elect_one()) {
-        umma::fence_after_sync();
-        issue_chain(tmem + B_ACCR, tmem + B_AHI, tmem + B_ALO, W(WB_OUT0, 0), W(WB_OUT0, 1));
-        umma::commit(&ctl.bar_chain);
-      }
+      hand_over();
       // d (readout hidden pre-activation) needs sum_o dY[o] * w_out1[o][j]: prepare while the MMA runs
       float dz[8];
 #pragma unroll
@@ -479,14 +632,7 @@ __global__ void __launch_bounds__(NT, 1) k_tiled_backward(SweepArgs a) {
       }
       put(d, true, B_DHI, B_DLO, T_D1M_HI, T_D1M_LO);
       put(z, false, 0, 0, T_D0M_HI, T_D0M_LO);
-      publish();
-      if (warp == 0 && umma::elect_one()) {
-        umma::fence_after_sync();
-        issue_chain(tmem + B_ACCD, tmem + B_DHI, tmem + B_DLO, W(WB_OUT0T, 0), W(WB_OUT0T, 1));
-        umma::commit(&ctl.bar_chain);
-        issue_wgrad<40>(tmem + B_SACC, Tl(T_D1M_HI), Tl(T_D1M_LO), Tl(T_AM_HI), Tl(T_AM_LO));
-        umma::commit(&ctl.bar_wgrad);
-      }
+      hand_over();
       wait_chain();
       umma::tmem_ld8(lane_base + B_ACCD, acc);
 #pragma unroll
@@ -496,117 +642,84 @@ __global__ void __launch_bounds__(NT, 1) k_tiled_backward(SweepArgs a) {
     };
 
     // ---- preds_before[u+1] = out(h_end) ----
-    ld8(ckpt + ((slot0 + kmax) * R + row) * H + col0, hrow);
+    ld8(ck + kmax * (2 * R * H), hrow);
     out_backward(a.grad_preds_before, (int64_t)u + 1, u >= 0 && (ke & 1));
 
     // ---- Euler steps, last to first ----
-    float hnext[8];                                   // prefetched checkpoint of the next (earlier) step
-    float tn = a.knots[(slot0 + kmax) * R + row];
-    float tc_next = kmax > 0 ? a.knots[(slot0 + kmax - 1) * R + row] : tn;
-    ld8(ckpt + ((slot0 + (kmax > 0 ? kmax - 1 : 0)) * R + row) * H + col0, hnext);
+    float tn = kn[kmax * R];
+    float tc_next = kmax > 0 ? kn[(kmax - 1) * R] : tn;
+    bool pending = false;                             // weight-gradient MMAs of the previous step still to be merged
     for (int k = kmax - 1; k >= 0; --k) {
       TR(1);
       const float tc = tc_next;
       const float delta = __fsub_rn(tn, tc);          // 0 for rows that took fewer than k+1 steps
       tn = tc;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) hrow[j] = hnext[j];
-      {  // prefetch step k-1 (or the h0 checkpoint again for the readout at the observation)
-        const int kn = k > 0 ? k - 1 : 0;
-        ld8(ckpt + ((slot0 + kn) * R + row) * H + col0, hnext);
-        tc_next = a.knots[(slot0 + kn) * R + row];
-      }
-      if (sc_kind != NJODE_SCALE_IDENTITY) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) hrow[j] = scale_fwd_rt(sc_kind, hrow[j]);
-      }
-      put(hrow, true, B_AHI, B_ALO, T_AM_HI, T_AM_LO);
-      float xv[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) xv[i] = 0.0f;
-      xv[0] = 1.0f;
-#pragma unroll
-      for (int e = 0; e < MAX_DX; ++e) if (e < dx) xv[1 + e] = xs[e];
-      xv[1 + dx] = tc;
-      xv[2 + dx] = delta;
-      put_aux(xv);
-#pragma unroll
       for (int j = 0; j < 8; ++j) d[j] = delta * g[j];                       // d loss / d f(h)
-      put(d, true, B_DHI, B_DLO, T_D1M_HI, T_D1M_LO);
+      put(d, true, B_DHI, B_DLO, -1, -1);                                    // chain operand: straight to TMEM
       TR(2);
-      publish();
+      hand_over_tmem();                                                      // -> d z0 = d1 * W1
       TR(3);
-      if (warp == 0 && umma::elect_one()) {
-        umma::fence_after_sync();
-        issue_chain(tmem + B_ACCR, tmem + B_AHI, tmem + B_ALO, W(WB_ODE0, 0), W(WB_ODE0, 1));      // recompute
-        issue_chain(tmem + B_ACCD, tmem + B_DHI, tmem + B_DLO, W(WB_ODE1T, 0), W(WB_ODE1T, 1));    // d z0
-        umma::commit(&ctl.bar_chain);
+      // This step's checkpoints and the next knot.  Issued AFTER the hand-over on purpose: scoreboards are shared,
+      // so anything that waits on an older load (delta above) or fences memory (the hand-over) would also wait for
+      // these ~1000-cycle HBM loads.  They are consumed after the weight-gradient wait below.
+      ld8(ck + k * (2 * R * H), hrow);
+      ld8(ck + k * (2 * R * H) + R * H, z);
+      tc_next = kn[(k > 0 ? k - 1 : 0) * R];
+      // the MN tiles are free once the previous step's weight-gradient MMAs are done
+      if (pending) {
+        wait_wgrad();
+        TR(4);
+        // accumulator rows 0-31 (quadrants 0,1) are the d f rows: W1 block = columns 0-31; rows 32-63 (quadrants 2,3)
+        // are the d a0 rows: W0 block = columns 32-63; column 64.. = bias, x, t, dt gradients for either
+        merge(B_RUN_ODE, B_SACC + (q < 2 ? 0 : 32), B_SACC + 64, true);
       }
-      TR(4);
-      // the part of the hidden pre-activation that does not come from the GEMM: bias + x, t, dt columns
-      ld8(sp.b_ode0 + col0, cb);
-#pragma unroll
-      for (int e = 0; e < MAX_DX; ++e) if (e < dx) {
-        ld8(sp.ext_ode0[e] + col0, cw);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) cb[j] = fmaf(cw[j], xs[e], cb[j]);
-      }
-      ld8(sp.ext_ode0[dx] + col0, cw);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) cb[j] = fmaf(cw[j], tc, cb[j]);
-      ld8(sp.ext_ode0[dx + 1] + col0, cw);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) cb[j] = fmaf(cw[j], delta, cb[j]);
-      wait_chain();
       TR(5);
-      umma::tmem_ld8_nowait(lane_base + B_ACCR, acc);
-      umma::tmem_ld8_nowait(lane_base + B_ACCD, d);
-      umma::wait_ld();
-      TR(6);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        z[j] = act_fwd<ACT>(acc[j] + cb[j]);
-        d[j] = d[j] * act_grad_from_out<ACT>(z[j]);                          // d loss / d a0
-      }
-      put(d, true, B_DHI, B_DLO, T_D0M_HI, T_D0M_LO);
+      scale8(sc_kind, hrow);
+      put(hrow, false, 0, 0, T_AM_HI, T_AM_LO);
+      put(d, false, 0, 0, T_D1M_HI, T_D1M_LO);
       put(z, false, 0, 0, T_ZM_HI, T_ZM_LO);
-      TR(7);
-      publish();
-      TR(8);
-      if (warp == 0 && umma::elect_one()) {
-        umma::fence_after_sync();
-        issue_chain(tmem + B_ACCD, tmem + B_DHI, tmem + B_DLO, W(WB_ODE0T, 0), W(WB_ODE0T, 1));    // d s(h)
-        umma::commit(&ctl.bar_chain);
-        issue_wgrad<72>(tmem + B_SACC, Tl(T_D1M_HI), Tl(T_D1M_LO), Tl(T_ZM_HI), Tl(T_ZM_LO));
-        umma::commit(&ctl.bar_wgrad);
+      {
+        // aux columns (1, s(x).., t, dt); no dynamic indexing (a local-memory array costs an L2 round trip here)
+        static_assert(MAX_DX == 2, "aux column layout assumes d_x <= 2");
+        const float xv[8] = {1.0f, xs[0], dx > 1 ? xs[1] : tc, dx > 1 ? tc : delta, dx > 1 ? delta : 0.0f, 0.0f, 0.0f, 0.0f};
+        put_aux(xv);
       }
-      TR(9);
+      TR(6);
       wait_chain();
-      TR(10);
+      TR(7);
       umma::tmem_ld8(lane_base + B_ACCD, acc);
-      if (sc_kind == NJODE_SCALE_IDENTITY) {
+      TR(8);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] += acc[j];
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] = fmaf(acc[j], scale_grad_rt(sc_kind, hrow[j]), g[j]);
-      }
-      TR(11);
-      wait_wgrad();
-      TR(12);
-      // accumulator rows 0-31 (quadrants 0,1) are the d f rows: W1 block = columns 0-31; rows 32-63 (quadrants 2,3)
-      // are the d a0 rows: W0 block = columns 32-63; column 64.. = bias, x, t, dt gradients for either
+      for (int j = 0; j < 8; ++j) d[j] = acc[j] * act_grad_from_out<ACT>(z[j]);      // d loss / d a0
+      put(d, true, B_DHI, B_DLO, T_D0M_HI, T_D0M_LO);
+      TR(9);
+      hand_over();                                                           // -> d s(h) = d0 * W0 ; weight gradients
+      pending = true;
+      TR(10);
+#if defined(NJODE_EXP) && NJODE_EXP == 1
+      wait_wgrad(); pending = false;    // experiment: idle until the whole batch is done
       merge(B_RUN_ODE, B_SACC + (q < 2 ? 0 : 32), B_SACC + 64, true);
-      TR(13);
+#endif
+      wait_chain();
+      TR(11);
+      umma::tmem_ld8(lane_base + B_ACCD, acc);
+      scale_grad_acc8(sc_kind, acc, hrow, g);
+      TR(12);
+    }
+    if (pending) {
+      wait_wgrad();
+      merge(B_RUN_ODE, B_SACC + (q < 2 ? 0 : 32), B_SACC + 64, true);
     }
 
     // ---- preds[u] = out(h0), then the jump net ----
-#pragma unroll
-    for (int j = 0; j < 8; ++j) hrow[j] = hnext[j];
-    if (kmax == 0) ld8(ckpt + ((slot0 + 0) * R + row) * H + col0, hrow);
+    ld8(ck, hrow);
     out_backward(a.grad_preds, u, u >= 0);
     {
       // z = first jump layer (recomputed), d = d loss / d (pre-activation of h0)
+      float x[MAX_DX], cw[8];
+#pragma unroll
+      for (int e = 0; e < MAX_DX; ++e) x[e] = (e < dx && u >= 0) ? a.values[(int64_t)u * dx + e] : 0.0f;
       ld8(sp.b_jump0 + col0, z);
 #pragma unroll
       for (int e = 0; e < MAX_DX; ++e) if (e < dx) {
@@ -621,21 +734,9 @@ __global__ void __launch_bounds__(NT, 1) k_tiled_backward(SweepArgs a) {
       }
       put(d, true, B_DHI, B_DLO, T_D1M_HI, T_D1M_LO);
       put(z, false, 0, 0, T_AM_HI, T_AM_LO);
-      float xv[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) xv[i] = 0.0f;
-      xv[0] = 1.0f;
-#pragma unroll
-      for (int e = 0; e < MAX_DX; ++e) if (e < dx) xv[1 + e] = x[e];
+      const float xv[8] = {1.0f, x[0], x[1], 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};     // x[1] = 0 when d_x = 1
       put_aux(xv);
-      publish();
-      if (warp == 0 && umma::elect_one()) {
-        umma::fence_after_sync();
-        issue_chain(tmem + B_ACCD, tmem + B_DHI, tmem + B_DLO, W(WB_JUMP1T, 0), W(WB_JUMP1T, 1));
-        umma::commit(&ctl.bar_chain);
-        issue_wgrad<40>(tmem + B_SACC, Tl(T_D1M_HI), Tl(T_D1M_LO), Tl(T_AM_HI), Tl(T_AM_LO));
-        umma::commit(&ctl.bar_wgrad);
-      }
+      hand_over();
       wait_chain();
       umma::tmem_ld8(lane_base + B_ACCD, acc);
 #pragma unroll
@@ -643,22 +744,19 @@ __global__ void __launch_bounds__(NT, 1) k_tiled_backward(SweepArgs a) {
       wait_wgrad();
       merge(B_RUN_J1, B_SACC, B_SACC + 32, true);
       put(d, false, 0, 0, T_D1M_HI, T_D1M_LO);
-      publish();
-      if (warp == 0 && umma::elect_one()) {
-        umma::fence_after_sync();
-        issue_wgrad<8>(tmem + B_SACC, Tl(T_D1M_HI), Tl(T_D1M_LO), Tl(T_XM_HI), Tl(T_XM_LO));
-        umma::commit(&ctl.bar_wgrad);
-      }
+      hand_over();
       wait_wgrad();
       merge(B_RUN_J0, 0, B_SACC, false);
     }
   }
 
   // ---- flush the TMEM-resident weight-gradient accumulators into this CTA's partial buffer ----
+  if (c == 0) *reinterpret_cast<float4*>(sp.red[0][row]) = make_float4(dbo[0], dbo[1], dbo[2], dbo[3]);
   umma::fence_before_sync();
-  __syncthreads();
+  umma::named_bar_sync(1, NT);
   umma::fence_after_sync();
   {
+    float* part = a.partials + (int64_t)blockIdx.x * T.stack_floats;
     const bool has_row = lane < 16;                 // M = 64 accumulator: row i lives in lane (i%16) + 32*(i/16)
     const int i = q * 16 + lane;                    // 0..63 when has_row
     const int j = i & 31;
@@ -698,19 +796,56 @@ __global__ void __launch_bounds__(NT, 1) k_tiled_backward(SweepArgs a) {
       part[T.b_off[NET_JUMP][0] + j] = v8[0];
       for (int e = 0; e < dx; ++e) part[T.w_off[NET_JUMP][0] + j * dx + e] = v8[1 + e];
     }
-    // readout bias: per-row sums -> fixed-order block reduction (deterministic)
-    if (c == 0) *reinterpret_cast<float4*>(sp.red[0][row]) = make_float4(dbo[0], dbo[1], dbo[2], dbo[3]);
-    __syncthreads();
-    if (tid < O) {
+    if (tid < O) {     // readout bias: fixed-order sum over the rows (deterministic)
       float sum = 0.0f;
       for (int r = 0; r < R; ++r) sum += sp.red[0][r][tid];
       part[T.b_off[NET_OUT][1] + tid] = sum;
     }
   }
-  if (!ok && tid == 0) atomicOr(&g_tiled_status, 2u);
+  TR_END(1);
+  if (!ok && lane == 0) atomicOr(&g_tiled_status, 2u);
+}
+
+// Reverse sweep.  Warps 0-15 are row workers (see the header), warp 16 only issues MMAs: the workers hand
+// operands over through an mbarrier (bar_ops, 512 arrivals) and never wait for the issue itself, so the
+// ~30 cycles per tcgen05.mma of issue time and the back-pressure of the MMA queue stay off their path.
+// The weight-gradient MMAs of step k (1536 tensor cycles, reading the shared-memory MN tiles) overlap the
+// data-gradient chain and the first half of step k-1: the workers write the MN tiles of a step as late as
+// possible (after waiting for the previous step's weight-gradient MMAs) and merge the previous fresh
+// accumulator at the same point.  The hidden-layer activations come from the forward sweep's checkpoints.
+// Register budget: the CTA is launched with 640 x 96 registers and setmaxnreg only moves registers inside that
+// pool, so 512 x W + 128 x I <= 61440: workers W = 104, issuer warpgroup I = 56 (W = 112 / I = 40 dead-locks in
+// setmaxnreg.inc).  The role bodies derive everything they need AFTER the re-allocation: whatever is live
+// across it gets spilled under the 96-register budget and re-loaded from local memory inside the loops -- an L2
+// round trip each with this shared-memory carve-out (measured: ~1000 cycles per step).
+template <int ACT>
+__global__ void __launch_bounds__(NT_B, 1) k_tiled_backward(SweepArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  {
+    Ctl& ctl = *bwd_carve(smem_raw).ctl;
+    if (threadIdx.x == 0) {
+      umma::mbar_init(&ctl.bar_chain, 1);
+      umma::mbar_init(&ctl.bar_wgrad, 1);
+      umma::mbar_init(&ctl.bar_ops, NT);
+      umma::fence_mbar_init();
+      ctl.timeout = 0;
+    }
+    if (warp == 0) umma::tmem_alloc(&ctl.tmem_base, B_TMEM_COLS);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+  }
+  if (warp >= NT / 32) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == NT / 32) bwd_issuer(a, smem_raw);
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    bwd_worker<ACT>(a, smem_raw);
+  }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_free(tmem, B_TMEM_COLS);
+  if (warp == 0) umma::tmem_free(*reinterpret_cast<volatile uint32_t*>(&bwd_carve(smem_raw).ctl->tmem_base), B_TMEM_COLS);
 }
 
 template <int ACT>
@@ -719,7 +854,7 @@ int launch_tiled(const SweepArgs& a, cudaStream_t st, bool backward) {
   if (backward) {
     NJODE_CUDA_OK(cudaFuncSetAttribute(k_tiled_backward<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
     njode_timing_begin(2, st);
-    k_tiled_backward<ACT><<<a.n_workers, NT, BWD_SMEM, st>>>(a);
+    k_tiled_backward<ACT><<<a.n_workers, NT_B, BWD_SMEM, st>>>(a);
     njode_timing_end(2, st);
     NJODE_LAUNCH_OK("k_tiled_backward");
   } else {
@@ -779,14 +914,18 @@ int njode_tiled_backward(const SweepArgs& a, cudaStream_t st) { return dispatch_
 // make TRACE=1 only: copy the phase trace of CTA 0 to the host and reset it; returns the number of records
 extern "C" int njode_tiled_trace_fetch(long long* out_host, int cap) {
 #ifdef NJODE_TRACE
-  int n = 0;
+  int n[3] = {0, 0, 0};
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(int));
-  if (n > cap) n = cap;
-  if (n > 0) cudaMemcpyFromSymbol(out_host, g_trace, (size_t)n * sizeof(long long));
-  const int zero = 0;
-  cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(int));
-  return n;
+  cudaMemcpyFromSymbol(n, g_trace_n, sizeof(n));
+  int total = 0;
+  for (int half = 0; half < 3; ++half) {
+    int cnt = n[half];
+    if (total + cnt > cap) cnt = cap - total;
+    if (cnt > 0) cudaMemcpyFromSymbol(out_host + total, g_trace, (size_t)cnt * sizeof(long long),
+                                      (size_t)half * (NJODE_TRACE_CAP / 3) * sizeof(long long));
+    total += cnt > 0 ? cnt : 0;
+  }
+  return total;
 #else
   (void)out_host; (void)cap;
   return -1;

@@ -67,7 +67,8 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // bounded wait: returns false on timeout (the caller records an error instead of hanging the GPU)
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
-  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
     uint32_t done;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                  : "=r"(done) : "r"(a), "r"(parity) : "memory");
@@ -218,12 +219,19 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint32_t (&hi)[8], u
 #pragma unroll
   for (int i = 0; i < 8; ++i) split1(v[i], hi[i], lo[i]);
 }
-// columns [8c, 8c+8) of row r -> MN-major tile (one 32-byte chunk, position c ^ r%4)
-__device__ __forceinline__ void chunk_to_mn_tile(float* tile, int r, int c, const uint32_t (&v)[8]) {
-  uint4* row = reinterpret_cast<uint4*>(tile + r * 32);
-  const int chunk = (c ^ (r & 3)) * 2;
-  row[chunk] = make_uint4(v[0], v[1], v[2], v[3]);
-  row[chunk + 1] = make_uint4(v[4], v[5], v[6], v[7]);
+// columns [8c, 8c+8) of row r -> MN-major tile (one 32-byte chunk, position c ^ r%4); `tile_saddr` is the
+// shared-space address of the tile (st.shared: the generic-pointer form compiles to slower generic stores)
+__device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void chunk_to_mn_tile(uint32_t tile_saddr, int r, int c, const uint32_t (&v)[8]) {
+  // Rows r and r+4 of a quarter-warp share the chunk position, so writing "low half, then high half" in every
+  // lane is a 2-way bank conflict on each st.shared.v4 (measured: 8 wavefronts instead of 4).  Odd (r/4) lanes
+  // write the high half first: 8 SELs per chunk buy back half of the shared-memory pipe time of the tile writes.
+  const bool sw = (r >> 2) & 1;
+  const uint32_t addr = tile_saddr + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 3)) * 32) + (sw ? 16u : 0u);
+  st_shared_v4(addr, sw ? v[4] : v[0], sw ? v[5] : v[1], sw ? v[6] : v[2], sw ? v[7] : v[3]);
+  st_shared_v4(addr ^ 16u, sw ? v[0] : v[4], sw ? v[1] : v[5], sw ? v[2] : v[6], sw ? v[3] : v[7]);
 }
 
 // this thread's row -> TMEM columns [col_hi, +32) and [col_lo, +32) of its lane (A operand of a chain GEMM)

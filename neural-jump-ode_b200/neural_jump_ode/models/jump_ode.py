@@ -128,7 +128,10 @@ class _SweepFunction(torch.autograd.Function):
             before = torch.empty((N, d_y, M), dtype=torch.float32, device=dev)
             ckpt = None
             if want_grad:
-                ckpt = torch.empty(S * sched.total_slots * sched.tile_rows * H, dtype=torch.float32, device=dev)
+                row_floats = lib.njode_ckpt_row_floats(desc)
+                if row_floats < 0:
+                    raise RuntimeError("njode_ckpt_row_floats: " + lib.njode_last_error().decode(errors="replace"))
+                ckpt = torch.empty(S * sched.total_slots * sched.tile_rows * row_floats, dtype=torch.float32, device=dev)
             ws_bytes = lib.njode_forward_workspace_bytes(desc)
             ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
             nat.check(lib.njode_forward(desc, nat.ptr(flat), nat.ptr(batch.times), nat.ptr(batch.values),

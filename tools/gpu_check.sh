@@ -2,7 +2,7 @@
 # Runs on the GPU box: parity tests, then the three bench workloads.  Outputs under gpurun_out/.
 TAG=${1:-run}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_${TAG}.log 2>&1; echo "pytest rc=$?"
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_${TAG}.log 2>&1; echo "pytest rc=$?"
 tail -3 gpurun_out/pytest_${TAG}.log
 timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_${TAG}_ou.json 2> gpurun_out/bench_${TAG}_ou.err; echo "bench ou rc=$?"
 timeout 300 python bench.py --workload heston_sep_b262144 --batch 65536 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${TAG}_heston64k.json 2> gpurun_out/bench_${TAG}_heston.err; echo "bench heston rc=$?"

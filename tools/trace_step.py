@@ -18,14 +18,14 @@ lib.njode_tiled_trace_fetch.argtypes = [ctypes.c_void_p, ctypes.c_int]
 torch.manual_seed(0)
 model = NeuralJumpODE(**wl["model"]).to("cuda")
 batch = make_packed_batch(wl["process"], B, wl["obs_fraction"], n_steps=wl["n_steps"], T=wl["T"], device="cuda", seed=1000, **wl["pkw"])
-buf = (ctypes.c_longlong * 8192)()
+buf = (ctypes.c_longlong * 12288)()
 for it in range(3):
     model.zero_grad()
     p, b = model.forward_packed(batch)
     loss = nj_ode_loss(batch, None, p, b, **wl["loss"])
     loss.backward()
     torch.cuda.synchronize()
-    n = lib.njode_tiled_trace_fetch(buf, 8192)
+    n = lib.njode_tiled_trace_fetch(buf, 12288)
 rec = [(buf[i] & 255, buf[i] >> 8) for i in range(n)]
 print("records", n)
 d = collections.defaultdict(list)
@@ -35,3 +35,11 @@ for k in sorted(d, key=lambda k: (k[1] >= 32, k[1], k[0])):
     v = d[k]
     if len(v) >= 3:
         print(f"{k[0]:3d} -> {k[1]:3d}: n={len(v):4d} median={statistics.median(v):8.0f} min={min(v):7d} max={max(v):8d}")
+
+# merged absolute timeline (reverse-sweep worker thread 0 and the MMA issuer share the SM clock): a few steps mid-run
+bw = sorted((t, i) for i, t in rec if (1 <= i <= 13) or i >= 64)
+if bw:
+    mid = len(bw) // 2
+    t0 = bw[mid][0]
+    print("timeline (cycles relative, id): worker ids 1-12, issuer 64=loop top 65=ops#1 seen 66=chain1 issued 67=ops#2 seen 68=chain2+wgrad issued")
+    print("  " + "  ".join(f"{t - t0}:{i}" for t, i in bw[mid:mid + 60]))
