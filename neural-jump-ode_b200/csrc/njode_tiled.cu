@@ -113,9 +113,16 @@ __device__ __forceinline__ void ld8(const float* __restrict__ src, float (&v)[8]
   const float4 q0 = reinterpret_cast<const float4*>(src)[0], q1 = reinterpret_cast<const float4*>(src)[1];
   v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
 }
+// one 256-bit global load / store per thread for its 8 checkpoint floats (LDG.256 / STG.256 on sm_100): one L2
+// request per 32-byte sector instead of two.  (Loads that bypass L1 -- ld.global.cg -- were measured slower.)
+__device__ __forceinline__ void ld8_cg(const float* __restrict__ src, float (&v)[8]) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(src));
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 __device__ __forceinline__ void st8_stream(float* __restrict__ dst, const float (&v)[8]) {
-  __stcs(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
-  __stcs(reinterpret_cast<float4*>(dst) + 1, make_float4(v[4], v[5], v[6], v[7]));
+  asm volatile("st.global.v8.f32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+               :: "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "l"(dst) : "memory");
 }
 
 // Operands are addressed through descriptor bases: every weight tile / MN tile sits at a compile-time offset
@@ -642,7 +649,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
     };
 
     // ---- preds_before[u+1] = out(h_end) ----
-    ld8(ck + kmax * (2 * R * H), hrow);
+    ld8_cg(ck + kmax * (2 * R * H), hrow);
     out_backward(a.grad_preds_before, (int64_t)u + 1, u >= 0 && (ke & 1));
 
     // ---- Euler steps, last to first ----
@@ -663,9 +670,15 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
       // This step's checkpoints and the next knot.  Issued AFTER the hand-over on purpose: scoreboards are shared,
       // so anything that waits on an older load (delta above) or fences memory (the hand-over) would also wait for
       // these ~1000-cycle HBM loads.  They are consumed after the weight-gradient wait below.
-      ld8(ck + k * (2 * R * H), hrow);
-      ld8(ck + k * (2 * R * H) + R * H, z);
+#if !(defined(NJODE_EXP) && NJODE_EXP == 2)
+      ld8_cg(ck + k * (2 * R * H), hrow);
+      ld8_cg(ck + k * (2 * R * H) + R * H, z);
       tc_next = kn[(k > 0 ? k - 1 : 0) * R];
+      if (k > 0) {   // and pull the NEXT step's checkpoints into L2 (no destination register, no scoreboard)
+        prefetch_l2(ck + (k - 1) * (2 * R * H));
+        prefetch_l2(ck + (k - 1) * (2 * R * H) + R * H);
+      }
+#endif
       // the MN tiles are free once the previous step's weight-gradient MMAs are done
       if (pending) {
         wait_wgrad();
@@ -675,6 +688,11 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
         merge(B_RUN_ODE, B_SACC + (q < 2 ? 0 : 32), B_SACC + 64, true);
       }
       TR(5);
+#if defined(NJODE_EXP) && NJODE_EXP == 2
+      ld8(ck + k * (2 * R * H), hrow);
+      ld8(ck + k * (2 * R * H) + R * H, z);
+      tc_next = kn[(k > 0 ? k - 1 : 0) * R];
+#endif
       scale8(sc_kind, hrow);
       put(hrow, false, 0, 0, T_AM_HI, T_AM_LO);
       put(d, false, 0, 0, T_D1M_HI, T_D1M_LO);
@@ -713,7 +731,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
     }
 
     // ---- preds[u] = out(h0), then the jump net ----
-    ld8(ck, hrow);
+    ld8_cg(ck, hrow);
     out_backward(a.grad_preds, u, u >= 0);
     {
       // z = first jump layer (recomputed), d = d loss / d (pre-activation of h0)
