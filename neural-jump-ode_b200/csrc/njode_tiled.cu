@@ -551,9 +551,18 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
   auto wait_chain = [&]() { ok = ok && umma::mbar_wait(&ctl.bar_chain, ph_c); ph_c ^= 1; umma::fence_after_sync(); };
   auto wait_wgrad = [&]() { ok = ok && umma::mbar_wait(&ctl.bar_wgrad, ph_w); ph_w ^= 1; umma::fence_after_sync(); };
   // make this thread's TMEM / smem operand writes visible to the tensor core, then tell the issuer
-  auto hand_over = [&]() { umma::wait_st(); umma::fence_async_smem(); umma::fence_before_sync(); umma::mbar_arrive(&ctl.bar_ops); };
+  // (one arrival per warp: 512 arrivals on one mbarrier word are 512 serialized shared-memory atomics per hand-over)
+  auto hand_over = [&]() {
+    umma::wait_st(); umma::fence_async_smem(); umma::fence_before_sync();
+    __syncwarp();
+    if (lane == 0) umma::mbar_arrive(&ctl.bar_ops);
+  };
   // the same when only TMEM operands were written (no shared-memory tile since the last hand-over)
-  auto hand_over_tmem = [&]() { umma::wait_st(); umma::fence_before_sync(); umma::mbar_arrive(&ctl.bar_ops); };
+  auto hand_over_tmem = [&]() {
+    umma::wait_st(); umma::fence_before_sync();
+    __syncwarp();
+    if (lane == 0) umma::mbar_arrive(&ctl.bar_ops);
+  };
   // this thread's 8 columns -> TMEM A operand (hi, lo) and/or MN tile (hi, lo)
   auto put = [&](const float (&v)[8], bool to_tmem, uint32_t c_hi, uint32_t c_lo, int tile_hi, int tile_lo) {
     uint32_t hi[8], lo[8];
@@ -845,7 +854,7 @@ __global__ void __launch_bounds__(NT_B, 1) k_tiled_backward(SweepArgs a) {
     if (threadIdx.x == 0) {
       umma::mbar_init(&ctl.bar_chain, 1);
       umma::mbar_init(&ctl.bar_wgrad, 1);
-      umma::mbar_init(&ctl.bar_ops, NT);
+      umma::mbar_init(&ctl.bar_ops, NT / 32);
       umma::fence_mbar_init();
       ctl.timeout = 0;
     }
