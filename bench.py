@@ -186,6 +186,7 @@ def main():
     import torch.distributed as dist
     from neural_jump_ode import NeuralJumpODE, nj_ode_loss, PackedBatch, _native as nat
     from neural_jump_ode.simulation import make_packed_batch
+    from neural_jump_ode.sharding import allreduce_gradients
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -221,8 +222,7 @@ def main():
         loss = nj_ode_loss(batch, None, preds, before, traj_scale=1.0 / B_global, **lk)
         loss.backward()
         if world > 1:                          # one all-reduce of the flat gradient (+ loss) over NVLink
-            flat = torch.cat([p.grad.reshape(-1) for p in params] + [loss.detach().reshape(1)])
-            dist.all_reduce(flat)
+            loss = allreduce_gradients(params, loss)
         return loss
 
     def sync_all():
@@ -284,12 +284,22 @@ def main():
     achieved = fl["bwd"] / (bwd_med * 1e-3) * 1e-12
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
     measured = json.load(open(peaks_file)) if os.path.exists(peaks_file) else {}
-    roofline = {"bound": "fp32-fma", "kernel": "reverse sweep (njode_backward main kernel)", "achieved": achieved,
-                "peak": float(peak.value), "unit": "TFLOP/s", "frac": achieved / float(peak.value), "traffic": None,
-                "peak_source": "FFMA micro-kernel run in this process (njode_ffma_peak); MEASURED_PEAKS.json has no "
-                               "FP32-FMA figure",
+    # measured DRAM traffic of the same kernel on this workload (one `ncu --set full` capture, profiles/)
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
+    if os.path.exists(tfile):
+        traffic = json.load(open(tfile)).get(f"{name}:{B}", {}).get("reverse_sweep_dram_bytes_per_launch")
+    peak_fma = float(peak.value)
+    bf16 = measured.get("bf16_tflops")
+    roofline = {"bound": "tensor", "pipe": "tcgen05 kind::tf32 with the 3xTF32 split (FP32-accurate), operands from TMEM / shared memory",
+                "kernel": "reverse sweep (k_tiled_backward)", "achieved": achieved,
+                "peak": peak_fma, "unit": "TFLOP/s", "frac": achieved / peak_fma, "traffic": traffic,
+                "peak_source": "FP32-FMA peak measured in this process (njode_ffma_peak): the north star's denominator for "
+                               "FP32-accurate work; MEASURED_PEAKS.json has no FP32 figure. The tensor-pipe ceilings are "
+                               "given beside it: measured bf16 / 2 (tf32) / 3 (split) for 3xTF32",
                 "kernel_ms": bwd_med, "algorithmic_flop_per_launch": fl["bwd"],
-                "frac_of_measured_bf16_tensor_peak": (achieved / measured["bf16_tflops"]) if measured.get("bf16_tflops") else None,
+                "frac_of_3xtf32_tensor_peak": (achieved / (bf16 / 6.0)) if bf16 else None,
+                "frac_of_measured_bf16_tensor_peak": (achieved / bf16) if bf16 else None,
                 "whole_step_tflops": fl["total"] * args.steps / (t_total_ms * 1e-3) * 1e-12 / max(world, 1)}
 
     # ---- end to end through the public API: pinned host inputs -> H2D -> schedule -> fwd/loss/bwd -> loss D2H ----
@@ -307,8 +317,7 @@ def main():
         loss = nj_ode_loss(b, None, preds, before, traj_scale=1.0 / B_global, **lk)
         loss.backward()
         if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in params] + [loss.detach().reshape(1)])
-            dist.all_reduce(flat)
+            loss = allreduce_gradients(params, loss)
         return loss.item()                     # device -> host read of the step's result
 
     for _ in range(3):

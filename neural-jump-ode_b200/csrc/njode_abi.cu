@@ -172,8 +172,16 @@ __global__ void k_reduce_partials(ParamTable T, const float* __restrict__ partia
   if (i >= total) return;
   const int64_t s = i / T.stack_floats;
   const int e = (int)(i - s * T.stack_floats);
-  float acc = 0.0f;
-  for (int w = (int)s; w < n_workers; w += T.S) acc += partials[(int64_t)w * T.stack_floats + e];
+  // 8 interleaved partial sums (8 loads in flight) combined in a fixed order: deterministic for a given schedule
+  float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int per_stack = (n_workers - (int)s + T.S - 1) / T.S;       // workers of this stack: s, s + S, ...
+  int j = 0;
+  for (; j + 8 <= per_stack; j += 8) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a8[u] += partials[(int64_t)((int)s + (j + u) * T.S) * T.stack_floats + e];
+  }
+  for (int u = 0; j < per_stack; ++j, ++u) a8[u] += partials[(int64_t)((int)s + j * T.S) * T.stack_floats + e];
+  const float acc = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
   int64_t dst = e;
   if (transposed) {
     int net, l;
@@ -307,7 +315,7 @@ extern "C" int njode_backward(const NjodeDesc* desc, const float* params, const 
   NJODE_CUDA_OK(cudaMemsetAsync(partials, 0, (size_t)a.n_workers * T.stack_floats * sizeof(float), st));
   rc = impl == NJODE_IMPL_TILED ? njode_tiled_backward(a, st) : njode_generic_backward(a, st);
   if (rc) return rc;
-  k_reduce_partials<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(T, partials, a.n_workers,
+  k_reduce_partials<<<(unsigned)((total + 63) / 64), 64, 0, st>>>(T, partials, a.n_workers,
                                                                     impl == NJODE_IMPL_GENERIC ? 1 : 0, grad_params, total);
   NJODE_LAUNCH_OK("k_reduce_partials");
   return NJODE_OK;

@@ -1,0 +1,63 @@
+"""Data-parallel host logic of the hot path: trajectories shard across ranks,
+every rank holds a full parameter replica, scales its loss by ``1 / B_global`` (``nj_ode_loss(...,
+traj_scale=...)``) and ONE all-reduce of the flat gradient vector with the loss appended precedes the
+optimiser step.  There is no data-path collective.  Works with any ``torch.distributed`` backend
+(NCCL over NVLink on the B200 box, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+
+def shard_bounds(n_traj: int, world_size: int, steps_per_traj: Optional[Sequence[int]] = None) -> List[int]:
+    """``world_size + 1`` trajectory indices cutting ``range(n_traj)`` into contiguous slices.
+
+    Without ``steps_per_traj`` the slices have (almost) equal trajectory counts; with it they are balanced
+    by the number of Euler steps (the work), still contiguous so a packed batch is sliced, not gathered."""
+    if world_size < 1 or n_traj < 0:
+        raise ValueError("shard_bounds: world_size must be >= 1 and n_traj >= 0")
+    if steps_per_traj is None:
+        return [(n_traj * r) // world_size for r in range(world_size + 1)]
+    if len(steps_per_traj) != n_traj:
+        raise ValueError("shard_bounds: steps_per_traj must have one entry per trajectory")
+    total = float(sum(steps_per_traj))
+    bounds, acc, b = [0], 0.0, 0
+    for r in range(1, world_size):
+        target = total * r / world_size
+        while b < n_traj and acc + steps_per_traj[b] * 0.5 <= target:
+            acc += steps_per_traj[b]
+            b += 1
+        bounds.append(b)
+    bounds.append(n_traj)
+    return bounds
+
+
+def shard_lists(batch_times: List[torch.Tensor], batch_values: List[torch.Tensor], rank: int, world_size: int,
+                steps_per_traj: Optional[Sequence[int]] = None) -> Tuple[List[torch.Tensor], List[torch.Tensor], float]:
+    """This rank's slice of a list batch and the ``traj_scale`` (= 1 / global batch) to hand to ``nj_ode_loss``."""
+    bounds = shard_bounds(len(batch_times), world_size, steps_per_traj)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    return batch_times[lo:hi], batch_values[lo:hi], 1.0 / max(len(batch_times), 1)
+
+
+def allreduce_gradients(params: Sequence[torch.Tensor], loss: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum the parameter gradients and the (already ``1/B_global``-scaled) loss over the ranks with ONE
+    all-reduce of the flat vector ``[grad_0, grad_1, ..., loss]``; gradients are written back in place
+    (a missing ``.grad`` counts as zero and is materialised).  Returns the global loss (0-dim tensor)."""
+    import torch.distributed as dist
+    pieces = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params]
+    flat = torch.cat(pieces + [loss.detach().reshape(1).to(pieces[0].dtype if pieces else loss.dtype)])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    o = 0
+    for p in params:
+        n = p.numel()
+        g = flat[o:o + n].view_as(p)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        o += n
+    return flat[o]
