@@ -47,17 +47,17 @@ def allreduce_gradients(params: Sequence[torch.Tensor], loss: torch.Tensor, grou
     all-reduce of the flat vector ``[grad_0, grad_1, ..., loss]``; gradients are written back in place
     (a missing ``.grad`` counts as zero and is materialised).  Returns the global loss (0-dim tensor)."""
     import torch.distributed as dist
-    pieces = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params]
-    flat = torch.cat(pieces + [loss.detach().reshape(1).to(pieces[0].dtype if pieces else loss.dtype)])
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    grads = [p.grad for p in params]
+    flat = torch.cat([g.reshape(-1) for g in grads] + [loss.detach().reshape(1).to(grads[0].dtype if grads else loss.dtype)])
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    o = 0
-    for p in params:
-        n = p.numel()
-        g = flat[o:o + n].view_as(p)
-        if p.grad is None:
-            p.grad = g.clone()
-        else:
-            p.grad.copy_(g)
-        o += n
+    views, o = [], 0
+    for g in grads:
+        views.append(flat[o:o + g.numel()].view_as(g))
+        o += g.numel()
+    if grads:
+        torch._foreach_copy_(grads, views)       # one multi-tensor kernel instead of one copy per parameter
     return flat[o]
