@@ -46,7 +46,29 @@ WORKLOADS = {
         n_steps=200, T=1.0, obs_fraction=0.1,
         model=dict(input_dim=1, hidden_dim=32, output_dim=1, dt_ode_step=0.005, num_moments=2),
         loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct")),
+    # BASELINE.json configs[4] (per-GPU slice of the sweep): mixed-process ragged batch, hidden 64 -> generic kernels
+    "mixed_h64_ragged": dict(
+        process="mixed", pkw=dict(), B=32768, n_steps=100, T=1.0, obs_fraction=(0.02, 0.2),
+        model=dict(input_dim=1, hidden_dim=64, output_dim=1, dt_ode_step=0.01, num_moments=2),
+        loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct")),
+    # BASELINE.json configs[3] shape at a batch the generic kernels finish in seconds (hidden 128, 3 layers, tanh)
+    "heston_h128_l3": dict(
+        process="heston", pkw=dict(mu=0.5, kappa=2.0, theta=0.04, xi=0.5, rho=-0.5, x0=1.0, v0=0.04), B=2048,
+        n_steps=1000, T=1.0, obs_fraction=0.05,
+        model=dict(input_dim=1, hidden_dim=128, output_dim=1, dt_ode_step=0.001, num_moments=2, n_hidden_layers=3,
+                   activation="tanh"),
+        loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct")),
 }
+
+
+def make_batch(wl, n_traj, device, seed):
+    """Synthetic on-device batch of the workload's shape."""
+    from neural_jump_ode.simulation import make_packed_batch, make_mixed_ragged_batch
+    if wl["process"] == "mixed":
+        lo, hi = wl["obs_fraction"]
+        return make_mixed_ragged_batch(n_traj, lo, hi, n_steps=wl["n_steps"], T=wl["T"], device=device, seed=seed)
+    return make_packed_batch(wl["process"], n_traj, wl["obs_fraction"], n_steps=wl["n_steps"], T=wl["T"],
+                             device=device, seed=seed, **wl["pkw"])
 
 
 def mac_counts(mk):
@@ -115,8 +137,7 @@ def cpu_port_baseline(wl, n_traj, repeats=1):
     from oracle import njode_oracle as orc
     from neural_jump_ode.simulation import make_packed_batch
     mk = wl["model"]
-    batch = make_packed_batch(wl["process"], n_traj, wl["obs_fraction"], n_steps=wl["n_steps"], T=wl["T"],
-                              device="cpu", seed=1234, **wl["pkw"])
+    batch = make_batch(wl, n_traj, "cpu", 1234)
     bt = list(torch.split(batch.times, batch.sizes))
     bv = list(torch.split(batch.values, batch.sizes))
     cfg = orc.make_cfg(mk["input_dim"], mk["hidden_dim"], mk["output_dim"], mk.get("dt_ode_step"),
@@ -206,8 +227,7 @@ def main():
     params = model.flat_parameters()
     B = wl["B"]                                # per GPU: weak scaling
     B_global = B * world
-    batch = make_packed_batch(wl["process"], B, wl["obs_fraction"], n_steps=wl["n_steps"], T=wl["T"], device=dev,
-                              seed=1000 + rank, **wl["pkw"])
+    batch = make_batch(wl, B, dev, 1000 + rank)
     desc = model.descriptor()
     sched = batch.schedule(desc)               # --cache-data: schedule built once, outside the timed region
     total_steps_rank = sched.total_steps

@@ -65,7 +65,7 @@ enum { NJODE_SCALE_IDENTITY = 0, NJODE_SCALE_TANH = 1, NJODE_SCALE_SIGMOID = 2 }
 /* jump_ode.py:333 / :346 */
 enum { NJODE_VAR_DIRECT = 0, NJODE_VAR_SECOND_MOMENT = 1 };
 /* kernel flavour: AUTO picks TILED when the shape is supported, else GENERIC */
-enum { NJODE_IMPL_AUTO = 0, NJODE_IMPL_GENERIC = 1, NJODE_IMPL_TILED = 2 };
+enum { NJODE_IMPL_AUTO = 0, NJODE_IMPL_GENERIC = 1, NJODE_IMPL_TILED = 2, NJODE_IMPL_ROWTILE = 3 };
 
 typedef struct NjodeDesc {
   int32_t d_x;              /* input_dim */

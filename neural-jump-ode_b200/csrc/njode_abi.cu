@@ -105,14 +105,20 @@ extern "C" int64_t njode_param_count(const NjodeDesc* d) {
   return per < 0 ? -1 : per * njode_num_stacks(d);
 }
 
-// which flavour runs for this descriptor: 0 = error, NJODE_IMPL_GENERIC or NJODE_IMPL_TILED
+// which flavour runs for this descriptor: 0 = error, else NJODE_IMPL_GENERIC / _TILED / _ROWTILE.
+// AUTO prefers the tcgen05 tiled kernels (hidden 32, one layer), then the row-tiled FP32 kernels, then generic.
 static int pick_impl(const NjodeDesc* d, const char** why) {
   if (!njode_desc_ok(d, why)) return 0;
   if (d->impl == NJODE_IMPL_TILED) {
     if (!njode_tiled_supported(d)) { *why = "impl=TILED requested but this shape is not supported by the tiled kernels"; return 0; }
     return NJODE_IMPL_TILED;
   }
+  if (d->impl == NJODE_IMPL_ROWTILE) {
+    if (!njode_rowtile_supported(d)) { *why = "impl=ROWTILE requested but this shape is not supported by the row-tiled kernels"; return 0; }
+    return NJODE_IMPL_ROWTILE;
+  }
   if (d->impl == NJODE_IMPL_AUTO && njode_tiled_supported(d)) return NJODE_IMPL_TILED;
+  if (d->impl == NJODE_IMPL_AUTO && njode_rowtile_supported(d)) return NJODE_IMPL_ROWTILE;
   if (d->impl != NJODE_IMPL_AUTO && d->impl != NJODE_IMPL_GENERIC) { *why = "unknown impl code"; return 0; }
   if (!njode_generic_supported(d, why)) return 0;
   return NJODE_IMPL_GENERIC;
@@ -235,7 +241,9 @@ extern "C" size_t njode_forward_workspace_bytes(const NjodeDesc* desc) {
 }
 
 static int workers_for(const NjodeDesc* desc, int impl, int64_t n_tiles) {
-  return impl == NJODE_IMPL_TILED ? njode_tiled_workers(desc, n_tiles) : njode_generic_workers(desc, n_tiles);
+  if (impl == NJODE_IMPL_TILED) return njode_tiled_workers(desc, n_tiles);
+  if (impl == NJODE_IMPL_ROWTILE) return njode_rowtile_workers(desc, n_tiles);
+  return njode_generic_workers(desc, n_tiles);
 }
 
 extern "C" size_t njode_backward_workspace_bytes(const NjodeDesc* desc, int64_t n_tiles) {
@@ -280,7 +288,9 @@ extern "C" int njode_forward(const NjodeDesc* desc, const float* params, const f
   a.n_workers = workers_for(desc, impl, n_tiles);
   // preds_before of each trajectory's first observation stays 0 (jump_ode.py:161)
   NJODE_CUDA_OK(cudaMemsetAsync(preds_before, 0, (size_t)N * desc->d_y * desc->num_moments * sizeof(float), st));
-  return impl == NJODE_IMPL_TILED ? njode_tiled_forward(a, st) : njode_generic_forward(a, st);
+  if (impl == NJODE_IMPL_TILED) return njode_tiled_forward(a, st);
+  if (impl == NJODE_IMPL_ROWTILE) return njode_rowtile_forward(a, st);
+  return njode_generic_forward(a, st);
 }
 
 extern "C" int njode_backward(const NjodeDesc* desc, const float* params, const float* times, const float* values,
@@ -313,10 +323,11 @@ extern "C" int njode_backward(const NjodeDesc* desc, const float* params, const 
   a.partials = partials;
   a.n_workers = workers_for(desc, impl, n_tiles);
   NJODE_CUDA_OK(cudaMemsetAsync(partials, 0, (size_t)a.n_workers * T.stack_floats * sizeof(float), st));
-  rc = impl == NJODE_IMPL_TILED ? njode_tiled_backward(a, st) : njode_generic_backward(a, st);
+  rc = impl == NJODE_IMPL_TILED ? njode_tiled_backward(a, st)
+     : impl == NJODE_IMPL_ROWTILE ? njode_rowtile_backward(a, st) : njode_generic_backward(a, st);
   if (rc) return rc;
   k_reduce_partials<<<(unsigned)((total + 63) / 64), 64, 0, st>>>(T, partials, a.n_workers,
-                                                                    impl == NJODE_IMPL_GENERIC ? 1 : 0, grad_params, total);
+                                                                    impl == NJODE_IMPL_TILED ? 0 : 1, grad_params, total);
   NJODE_LAUNCH_OK("k_reduce_partials");
   return NJODE_OK;
 }

@@ -172,6 +172,13 @@ int  njode_generic_workers(const NjodeDesc* d, int64_t n_tiles);
 int  njode_generic_forward(const SweepArgs& a, cudaStream_t st);
 int  njode_generic_backward(const SweepArgs& a, cudaStream_t st);
 
+// row-tiled FP32 kernels (njode_rowtile.cu): hidden_dim in {32,64,96,128}, <= 3 hidden layers; same tile rows and
+// checkpoint layout as the generic flavour
+int  njode_rowtile_supported(const NjodeDesc* d);
+int  njode_rowtile_workers(const NjodeDesc* d, int64_t n_tiles);
+int  njode_rowtile_forward(const SweepArgs& a, cudaStream_t st);
+int  njode_rowtile_backward(const SweepArgs& a, cudaStream_t st);
+
 #define NJODE_TILED_TILE_ROWS 128
 int  njode_tiled_supported(const NjodeDesc* d);
 int  njode_tiled_workers(const NjodeDesc* d, int64_t n_tiles);

@@ -18,7 +18,7 @@ ABI_VERSION = 1
 ACT = {"relu": 0, "tanh": 1, "sigmoid": 2, "elu": 3, "leaky_relu": 4, "selu": 5}
 SCALE = {"identity": 0, "none": 0, "tanh": 1, "sigmoid": 2}
 VAR = {"direct": 0, "second_moment": 1}
-IMPL = {"auto": 0, "generic": 1, "tiled": 2}
+IMPL = {"auto": 0, "generic": 1, "tiled": 2, "rowtile": 3}
 HDR_TOTAL_STEPS, HDR_TOTAL_SLOTS, HDR_NUM_TILES, HDR_KMAX, HDR_WORDS = 0, 1, 2, 3, 8
 
 

@@ -1,6 +1,8 @@
 """Synthetic path generators producing the packed batch format directly on the device
 (recurrences of reference simulation/data_generation.py)."""
 
-from .device_paths import simulate_paths, sample_observations, make_packed_batch
+from .device_paths import (simulate_paths, sample_observations, sample_observations_ragged, make_packed_batch,
+                           make_mixed_ragged_batch, concat_batches)
 
-__all__ = ["simulate_paths", "sample_observations", "make_packed_batch"]
+__all__ = ["simulate_paths", "sample_observations", "sample_observations_ragged", "make_packed_batch",
+           "make_mixed_ragged_batch", "concat_batches"]

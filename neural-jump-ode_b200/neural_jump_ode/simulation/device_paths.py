@@ -124,3 +124,34 @@ def make_packed_batch(process_type: str, n_paths: int, obs_fraction: float = 0.1
     times, X = simulate_paths(process_type, n_paths, n_steps=n_steps, T=T, device=device, generator=g,
                               **process_kwargs)
     return sample_observations(times, X, obs_fraction, generator=g)
+
+
+def concat_batches(batches) -> PackedBatch:
+    """Concatenate packed batches (same device, same d_x) into one."""
+    batches = list(batches)
+    times = torch.cat([b.times for b in batches])
+    values = torch.cat([b.values for b in batches])
+    offs, base = [batches[0].offsets[:1]], 0
+    for b in batches:
+        offs.append(b.offsets[1:] + base)
+        base += b.N
+    return PackedBatch(times, values, torch.cat(offs))
+
+
+def make_mixed_ragged_batch(n_paths: int, frac_lo: float = 0.02, frac_hi: float = 0.2, n_steps: int = 100,
+                            T: float = 1.0, device="cuda", seed: int = 0) -> PackedBatch:
+    """BASELINE config 5: equal parts Black-Scholes / OU / Heston paths (experiment_hybrid.py-style mixed batch,
+    default process parameters of the experiment scripts) with a per-path observation fraction U[frac_lo, frac_hi]."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    procs = [("black_scholes", dict(mu=0.1, sigma=0.5, x0=1.0)),
+             ("ornstein_uhlenbeck", dict(theta=1.0, mu=0.5, sigma=0.3, x0=0.0)),
+             ("heston", dict(mu=0.5, kappa=2.0, theta=0.04, xi=0.5, rho=-0.5, x0=1.0, v0=0.04))]
+    parts, left = [], n_paths
+    for i, (name, kw) in enumerate(procs):
+        n = left if i == len(procs) - 1 else n_paths // len(procs)
+        left -= n
+        if n <= 0:
+            continue
+        times, X = simulate_paths(name, n, n_steps=n_steps, T=T, device=device, generator=g, **kw)
+        parts.append(sample_observations_ragged(times, X, frac_lo, frac_hi, generator=g))
+    return concat_batches(parts)

@@ -35,6 +35,14 @@ def _cfg(mk):
                         mk.get("shared_network", False), mk.get("input_scaling", "identity"))
 
 
+def _impl_ok(mk, impl):
+    """Shapes the flavour supports (njode_tiled_supported / njode_rowtile_supported); generic and auto take all."""
+    H, L = mk["hidden_dim"], mk.get("n_hidden_layers", 1)
+    if impl == "rowtile":
+        return H % 32 == 0 and 32 <= H <= 128 and L <= 3
+    return True
+
+
 def _run(model, bt, bv, loss_kwargs):
     from neural_jump_ode import nj_ode_loss
     bt = [t.to(DEV) for t in bt]
@@ -46,11 +54,13 @@ def _run(model, bt, bv, loss_kwargs):
     return preds, before, loss
 
 
-@pytest.mark.parametrize("impl", ["generic", "auto"])
+@pytest.mark.parametrize("impl", ["generic", "rowtile", "auto"])
 @pytest.mark.parametrize("name", golden_names())
 def test_golden_parity(name, impl):
     """Same inputs and weights as the unmodified reference -> same preds, preds_before, loss, grads."""
     g = load_golden(name)
+    if not _impl_ok(g["model"], impl):
+        pytest.skip("shape not supported by this kernel flavour")
     model = _model(g, impl)
     preds, before, loss = _run(model, g["batch_times"], g["batch_values"], g["loss"])
     assert len(preds) == len(g["batch_times"])
@@ -105,34 +115,40 @@ CASES = [
     dict(input_dim=1, hidden_dim=32, output_dim=1, dt_ode_step=None, num_moments=2),
     dict(input_dim=1, hidden_dim=48, output_dim=1, dt_ode_step=0.02, num_moments=1, n_hidden_layers=2,
          activation="tanh", input_scaling="tanh"),
+    dict(input_dim=1, hidden_dim=128, output_dim=1, dt_ode_step=0.02, num_moments=2, n_hidden_layers=3,
+         activation="tanh"),                                                    # BASELINE config 4 shape
+    dict(input_dim=2, hidden_dim=96, output_dim=2, dt_ode_step=0.05, num_moments=2, n_hidden_layers=2,
+         activation="elu", input_scaling="sigmoid", shared_network=True),
 ]
 
 
-def _random_batch(B, seed, n_steps=100, ragged=True):
+def _random_batch(B, seed, n_steps=100, ragged=True, d_x=1):
     rng = np.random.RandomState(seed)
     bt, bv = [], []
     for b in range(B):
         n = rng.randint(2, 14) if ragged else 10
         idx = np.sort(np.concatenate([[0, n_steps], rng.choice(np.arange(1, n_steps), n - 2, replace=False)]))
         t = torch.linspace(0.0, 1.0, n_steps + 1)[torch.from_numpy(idx)]
-        v = torch.from_numpy((1.0 + 0.4 * rng.randn(n, 1)).astype(np.float32))
+        v = torch.from_numpy((1.0 + 0.4 * rng.randn(n, d_x)).astype(np.float32))
         bt.append(t)
         bv.append(v)
     return bt, bv
 
 
-@pytest.mark.parametrize("impl", ["generic", "auto"])
+@pytest.mark.parametrize("impl", ["generic", "rowtile", "auto"])
 @pytest.mark.parametrize("case", range(len(CASES)))
 def test_oracle_parity_random(case, impl):
     """Seeded ragged batch of 96 trajectories against the float64 interval-flattened oracle."""
     from neural_jump_ode import NeuralJumpODE
     mk = CASES[case]
+    if not _impl_ok(mk, impl):
+        pytest.skip("shape not supported by this kernel flavour")
     torch.manual_seed(100 + case)
     model = NeuralJumpODE(**mk)
     P = {k: v.detach().clone() for k, v in model.state_dict().items()}
     model.kernel_impl = impl
     model = model.to(DEV)
-    bt, bv = _random_batch(96, seed=case)
+    bt, bv = _random_batch(96, seed=case, d_x=mk["input_dim"])
     lk = dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct")
     preds, before, loss = _run(model, bt, bv, lk)
     ref = orc.run_flat(P, _cfg(mk), bt, bv, lk, dtype=torch.float64)
