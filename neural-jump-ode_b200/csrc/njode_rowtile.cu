@@ -208,7 +208,9 @@ __device__ __forceinline__ void layer_wgrad(const ParamTable& T, int net, int l,
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int j = jq + JQ * i;
-        if (j < n_out) gWt[(int64_t)k * n_out + j] += acc[i][m];
+        // fire-and-forget reduction (RED.ADD): this thread is the only writer of the element in this CTA's private
+        // partial buffer, so the order of the adds is its program order -- deterministic, and no load latency
+        if (j < n_out) atomicAdd(&gWt[(int64_t)k * n_out + j], acc[i][m]);
       }
     }
   }
@@ -219,7 +221,7 @@ __device__ __forceinline__ void layer_wgrad(const ParamTable& T, int net, int l,
     float s = 0.0f;
 #pragma unroll
     for (int c = 0; c < RT; c += 4) { const float4 q = *reinterpret_cast<const float4*>(dr + c); s += (q.x + q.y) + (q.z + q.w); }
-    gb[j] += s;
+    atomicAdd(&gb[j], s);
   }
 }
 
