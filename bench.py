@@ -207,8 +207,6 @@ def main():
     import torch.distributed as dist
     from neural_jump_ode import NeuralJumpODE, nj_ode_loss, PackedBatch, _native as nat
     from neural_jump_ode.simulation import make_packed_batch
-    from neural_jump_ode.sharding import allreduce_gradients
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -224,6 +222,8 @@ def main():
     model = NeuralJumpODE(**mk)
     model.kernel_impl = args.kernel_impl
     model = model.to(dev)
+    if world > 1:
+        model.enable_data_parallel()           # gradient all-reduce (NCCL over NVLink) inside the reverse sweep
     params = model.flat_parameters()
     B = wl["B"]                                # per GPU: weak scaling
     B_global = B * world
@@ -240,9 +240,7 @@ def main():
             p.grad = None
         preds, before = model.forward_packed(batch)
         loss = nj_ode_loss(batch, None, preds, before, traj_scale=1.0 / B_global, **lk)
-        loss.backward()
-        if world > 1:                          # one all-reduce of the flat gradient (+ loss) over NVLink
-            loss = allreduce_gradients(params, loss)
+        loss.backward()                        # world > 1: ONE in-place all-reduce of the flat gradient inside backward
         return loss
 
     def sync_all():
@@ -336,9 +334,7 @@ def main():
         preds, before = model.forward_packed(b)
         loss = nj_ode_loss(b, None, preds, before, traj_scale=1.0 / B_global, **lk)
         loss.backward()
-        if world > 1:
-            loss = allreduce_gradients(params, loss)
-        return loss.item()                     # device -> host read of the step's result
+        return loss.item()                     # device -> host read of the step's result (this rank's share of the loss)
 
     for _ in range(3):
         e2e_step()

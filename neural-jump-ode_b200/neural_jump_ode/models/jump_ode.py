@@ -115,7 +115,7 @@ class _SweepFunction(torch.autograd.Function):
     hidden-state checkpoints when a gradient will be needed), backward = ``njode_backward``."""
 
     @staticmethod
-    def forward(ctx, desc, batch: PackedBatch, sched, want_grad: bool, *params):
+    def forward(ctx, desc, batch: PackedBatch, sched, want_grad: bool, dp_group, *params):
         lib = nat.load()
         dev = batch.device
         N, B = batch.N, batch.B
@@ -141,6 +141,7 @@ class _SweepFunction(torch.autograd.Function):
                                         nat.ptr(preds), nat.ptr(before), nat.ptr(ckpt), nat.ptr(ws), ws_bytes, stream),
                       "njode_forward")
         ctx.desc, ctx.batch, ctx.sched = desc, batch, sched
+        ctx.dp_group = dp_group
         ctx.shapes = [p.shape for p in params]
         ctx.flat, ctx.ckpt = flat, ckpt
         return preds, before
@@ -166,6 +167,11 @@ class _SweepFunction(torch.autograd.Function):
                                          nat.ptr(g_preds), nat.ptr(g_before), nat.ptr(ctx.ckpt), nat.ptr(grad_flat),
                                          nat.ptr(ws), ws_bytes, stream), "njode_backward")
         ctx.ckpt = None     # checkpoints are the big buffer: release them as soon as they are consumed
+        if ctx.dp_group is not None:
+            # data parallel: the reverse sweep left this rank's share of the gradient (the loss is scaled by
+            # 1/B_global) in ONE flat buffer -- sum it over the ranks in place, no gather / scatter copies
+            import torch.distributed as dist
+            dist.all_reduce(grad_flat, op=dist.ReduceOp.SUM, group=None if ctx.dp_group is True else ctx.dp_group)
         # Stacks of moments >= 2 get an all-zero gradient from nj_ode_loss (jump_ode.py:328-378); the
         # reference reports zero tensors for them too (torch.stack backward), so nothing is special-cased.
         grads, o = [], 0
@@ -173,7 +179,7 @@ class _SweepFunction(torch.autograd.Function):
             n = shp.numel()
             grads.append(grad_flat[o:o + n].view(shp))
             o += n
-        return (None, None, None, None, *grads)
+        return (None, None, None, None, None, *grads)
 
 
 class _LossFunction(torch.autograd.Function):
@@ -250,7 +256,16 @@ class NeuralJumpODE(nn.Module):
         self.activation = activation
         self.input_scaling = input_scaling
         self.dropout_rate = dropout_rate
-        self.kernel_impl = "auto"                 # 'auto' | 'generic' | 'tiled' (testing / profiling knob)
+        self.kernel_impl = "auto"                 # 'auto' | 'generic' | 'rowtile' | 'tiled' (testing / profiling knob)
+        self._dp_group = None                     # see enable_data_parallel
+
+    def enable_data_parallel(self, group=True):
+        """Sum the parameter gradients over the ranks of ``group`` (``True`` = the default process group, ``None``
+        = off) inside the reverse sweep: one in-place all-reduce of the flat gradient buffer per backward.  Every
+        rank must hold the same parameters, integrate its own slice of the batch and scale its loss with
+        ``nj_ode_loss(..., traj_scale=1 / B_global)`` (see ``neural_jump_ode.sharding``)."""
+        self._dp_group = group
+        return self
 
     # -- reference-compatible small-tensor API (plotting, tests) ---------------------------------
     def euler_step(self, h_list, x_last, t_last, t_next):
@@ -315,7 +330,7 @@ class NeuralJumpODE(nn.Module):
         desc = self.descriptor()
         sched = batch.schedule(desc)
         want_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        return _SweepFunction.apply(desc, batch, sched, want_grad, *params)
+        return _SweepFunction.apply(desc, batch, sched, want_grad, self._dp_group, *params)
 
     def forward(self, batch_times, batch_values=None):
         """batch_times / batch_values: lists of (n_i,) / (n_i, d_x) tensors (reference jump_ode.py:218-233),

@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "neural-jump-ode
 import torch
 from bench import WORKLOADS
 from neural_jump_ode import NeuralJumpODE, nj_ode_loss
-from neural_jump_ode.simulation import make_packed_batch
+from bench import make_batch
 
 name = sys.argv[1] if len(sys.argv) > 1 else "ou_shared_b4096"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else WORKLOADS[name]["B"]
@@ -13,7 +13,7 @@ n = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 wl = WORKLOADS[name]
 torch.manual_seed(0)
 model = NeuralJumpODE(**wl["model"]).to("cuda")
-batch = make_packed_batch(wl["process"], B, wl["obs_fraction"], n_steps=wl["n_steps"], T=wl["T"], device="cuda", seed=1000, **wl["pkw"])
+batch = make_batch(wl, B, "cuda", 1000)
 for _ in range(n):
     model.zero_grad()
     p, b = model.forward_packed(batch)
