@@ -136,7 +136,10 @@ extern "C" int64_t njode_ckpt_row_floats(const NjodeDesc* d) {
   const int impl = pick_impl(d, &why);
   if (!impl) { njode_set_error("njode_ckpt_row_floats: %s", why); return -1; }
   // the tiled kernels also keep the hidden-layer activation of every step (see njode_tiled.cu)
-  return impl == NJODE_IMPL_TILED ? 2 * d->hidden : d->hidden;
+  if (impl == NJODE_IMPL_TILED) return 2 * d->hidden;
+  // the row-tiled kernels keep every hidden-layer output of the ODE net (no re-computation in the reverse sweep)
+  if (impl == NJODE_IMPL_ROWTILE) return (int64_t)(1 + d->n_hidden_layers) * d->hidden;
+  return d->hidden;
 }
 
 // ------------------------------------------------------------------------------------------------

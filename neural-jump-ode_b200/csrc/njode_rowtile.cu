@@ -152,12 +152,34 @@ __device__ __forceinline__ void layer_forward(const ParamTable& T, int net, int 
 
 // whole net forward; hidden-layer outputs z_0 .. z_{L-1} go to zbuf[l] (transposed), the last layer's output is
 // returned in registers.  `in_T` holds the vector input in rows [0,H) and the ext scalars in rows [H, H+n_ext).
+// a thread's elements <-> a row-major [32][H] plane in global memory (coalesced: lanes = consecutive columns)
+template <int NB>
+__device__ __forceinline__ void store_plane(float* __restrict__ dst, const Tile<NB>& t) {
+  const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) dst[(4 * ty + i) * (32 * NB) + tx + 32 * j] = t.v[i][j];
+}
+template <int NB>
+__device__ __forceinline__ void load_plane(const float* __restrict__ src, Tile<NB>& t) {
+  const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) t.v[i][j] = src[(4 * ty + i) * (32 * NB) + tx + 32 * j];
+}
+
 template <int NB>
 __device__ __forceinline__ void net_forward(const ParamTable& T, int net, const float* p, const float* pt,
-                                            const float* in_T, float* const* zbuf, float* wbuf, int act_kind, Tile<NB>& out) {
+                                            const float* in_T, float* const* zbuf, float* wbuf, int act_kind, Tile<NB>& out,
+                                            float* __restrict__ zck = nullptr) {
   for (int l = 0; l <= T.L; ++l) {
     layer_forward<NB>(T, net, l, p, pt, l == 0 ? in_T : zbuf[l - 1], wbuf, act_kind, out);
-    if (l < T.L) put_tile<NB>(zbuf[l], out, T.n_out[net][l]);     // (the next layer_forward synchronises)
+    if (l < T.L) {
+      put_tile<NB>(zbuf[l], out, T.n_out[net][l]);                // (the next layer_forward synchronises)
+      if (zck) store_plane<NB>(zck + (int64_t)l * RT * 32 * NB, out);   // checkpoint plane 1 + l of this slot
+    }
   }
 }
 
@@ -292,16 +314,14 @@ __global__ void __launch_bounds__(NTH) k_rowtile_forward(SweepArgs a) {
   const float* p = a.params + (int64_t)s * T.stack_floats;
   const float* pt = a.params_t + (int64_t)s * T.stack_floats;
   const int dx = T.d_x, act_kind = a.desc.activation, sc_kind = a.desc.input_scaling;
-  float* ckpt = a.ckpt ? a.ckpt + (int64_t)s * a.total_slots * RT * H : nullptr;
+  // checkpoints: [stack][slot][plane][row][H]; plane 0 = hidden state before the step of this slot (after the last
+  // step for the tile's final slot), planes 1..L = hidden-layer outputs z_0..z_{L-1} of the ODE net in that step
+  const int planes = 1 + T.L;
+  float* ckpt = a.ckpt ? a.ckpt + (int64_t)s * a.total_slots * planes * RT * H : nullptr;
   float* ext = hbuf + H * LDA;                    // ext rows: [e][row]
 
   auto store_ckpt = [&](int64_t slot, const Tile<NB>& h) {
-    if (!ckpt) return;
-    float* dst = ckpt + slot * RT * H;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < NB; ++j) dst[(4 * ty + i) * H + tx + 32 * j] = h.v[i][j];
+    if (ckpt) store_plane<NB>(ckpt + slot * planes * RT * H, h);
   };
   // y = out(h) for the tile (h is in hbuf); rows with write[r] get their O readouts stored
   auto readout = [&](float* __restrict__ dst, bool before) {
@@ -352,7 +372,8 @@ __global__ void __launch_bounds__(NTH) k_rowtile_forward(SweepArgs a) {
         put_tile<NB>(hbuf, sh, H);
       }
       Tile<NB> f;
-      net_forward<NB>(T, NET_ODE, p, pt, hbuf, zb, wbuf, act_kind, f);
+      net_forward<NB>(T, NET_ODE, p, pt, hbuf, zb, wbuf, act_kind, f,
+                      ckpt ? ckpt + ((slot0 + k) * planes + 1) * RT * H : nullptr);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = 4 * ty + i;
@@ -395,16 +416,11 @@ __global__ void __launch_bounds__(NTH) k_rowtile_backward(SweepArgs a) {
   const float* pt = a.params_t + (int64_t)s * T.stack_floats;
   float* part = a.partials + (int64_t)blockIdx.x * T.stack_floats;
   const int dx = T.d_x, act_kind = a.desc.activation, sc_kind = a.desc.input_scaling;
-  const float* ckpt = a.ckpt + (int64_t)s * a.total_slots * RT * H;
+  const int planes = 1 + T.L;                     // see the forward kernel
+  const float* ckpt = a.ckpt + (int64_t)s * a.total_slots * planes * RT * H;
   float* ext = hbuf + H * LDA;
 
-  auto load_ckpt = [&](int64_t slot, Tile<NB>& h) {
-    const float* src = ckpt + slot * RT * H;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < NB; ++j) h.v[i][j] = src[(4 * ty + i) * H + tx + 32 * j];
-  };
+  auto load_ckpt = [&](int64_t slot, Tile<NB>& h) { load_plane<NB>(ckpt + slot * planes * RT * H, h); };
   // readout backward at the hidden state in `h` (also stored to hbuf): g += d loss / d h
   auto out_backward = [&](const Tile<NB>& h, const float* __restrict__ gsrc, bool before, Tile<NB>& g) {
     __syncthreads();
@@ -465,7 +481,10 @@ __global__ void __launch_bounds__(NTH) k_rowtile_backward(SweepArgs a) {
       scale_tile<NB>(sc_kind, h);                     // h := s(h_k), the ODE net's vector input
       put_tile<NB>(hbuf, h, H);
       Tile<NB> d;
-      net_forward<NB>(T, NET_ODE, p, pt, hbuf, zb, wbuf, act_kind, d);     // re-computes z_0 .. z_{L-1}; output unused
+      for (int l = 0; l < T.L; ++l) {                 // hidden-layer outputs of this step: from the checkpoints
+        load_plane<NB>(ckpt + ((slot0 + k) * planes + 1 + l) * RT * H, d);
+        put_tile<NB>(zb[l], d, H);
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float delta = m_delta[4 * ty + i];
