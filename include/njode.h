@@ -125,8 +125,10 @@ int njode_schedule_knots(const float* times, const int32_t* kenc, const int32_t*
                          float* knots, void* stream);
 
 /* ---- forward sweep -----------------------------------------------------------------------------
- * ckpt: float32 [S][total_slots][tile_rows][Hc] hidden state before every Euler step and after the
- *       last one (Hc = njode_ckpt_row_floats); pass NULL for inference (no checkpoints written).
+ * ckpt: float32 [S][total_slots][tile_rows * Hc] per-slot checkpoints (Hc = njode_ckpt_row_floats): the hidden
+ *       state before every Euler step and after the last one, plus -- tiled / row-tiled flavours -- the ODE
+ *       net's hidden-layer outputs of that step; opaque to the caller, written by njode_forward and read by
+ *       njode_backward.  Pass NULL for inference (no checkpoints written).
  * workspace: njode_forward_workspace_bytes (re-laid-out weights). */
 int64_t njode_ckpt_row_floats(const NjodeDesc* desc);
 size_t  njode_forward_workspace_bytes(const NjodeDesc* desc);
