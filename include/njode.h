@@ -180,6 +180,9 @@ int njode_set_kernel_timing(int32_t which, void* ev_start, void* ev_stop);
 /* sticky device-side diagnostic word of the tiled kernels (0 = healthy; bit 0 / bit 1: a forward / reverse
  * sweep CTA gave up waiting on an MMA-completion barrier).  Synchronises the device. */
 int njode_device_status(uint32_t* status_host);
+/* Number of CUDA kernels this library has launched in this process (every launch site counts itself);
+ * reset != 0 returns the count and sets it to zero.  Measurement aid for bench.py's `gpu_launches`. */
+int64_t njode_kernel_launches(int32_t reset);
 int njode_ffma_peak(float* tflops_host);
 
 #ifdef __cplusplus

@@ -82,6 +82,12 @@ extern "C" int njode_ffma_peak(float* tflops_host) {
 }
 extern "C" int32_t njode_abi_version(void) { return NJODE_ABI_VERSION; }
 
+static std::atomic<long long> g_launches{0};
+void njode_count_launch(int n) { g_launches.fetch_add(n); }
+extern "C" int64_t njode_kernel_launches(int32_t reset) {
+  return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
 extern "C" int njode_device_status(uint32_t* status_host) {
   if (!status_host) NJODE_FAIL(NJODE_EINVAL, "njode_device_status: null output");
   unsigned v = 0;
@@ -283,8 +289,10 @@ extern "C" int njode_forward(const NjodeDesc* desc, const float* params, const f
   cudaStream_t st = (cudaStream_t)stream;
   if (N == 0) return NJODE_OK;
   float* params_t = (float*)workspace;
-  rc = relayout(desc, params, params_t, st);
-  if (rc) return rc;
+  if (impl != NJODE_IMPL_TILED) {          // the tcgen05 kernels build their own (split, swizzled) weight tiles
+    rc = relayout(desc, params, params_t, st);
+    if (rc) return rc;
+  }
   SweepArgs a = make_args(desc, params, params_t, times, values, kenc, perm, tile_kmax, tile_slot_off, knots, N, n_tiles,
                           total_slots, tile_rows);
   a.preds = preds; a.preds_before = preds_before; a.ckpt = ckpt;
@@ -318,8 +326,10 @@ extern "C" int njode_backward(const NjodeDesc* desc, const float* params, const 
     NJODE_FAIL(NJODE_EWORKSPACE, "njode_backward: workspace too small");
   float* params_t = (float*)workspace;
   float* partials = (float*)((char*)workspace + params_bytes(desc));
-  rc = relayout(desc, params, params_t, st);
-  if (rc) return rc;
+  if (impl != NJODE_IMPL_TILED) {
+    rc = relayout(desc, params, params_t, st);
+    if (rc) return rc;
+  }
   SweepArgs a = make_args(desc, params, params_t, times, values, kenc, perm, tile_kmax, tile_slot_off, knots, N, n_tiles,
                           total_slots, tile_rows);
   a.grad_preds = grad_preds; a.grad_preds_before = grad_preds_before; a.ckpt = const_cast<float*>(ckpt);

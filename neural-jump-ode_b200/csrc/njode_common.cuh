@@ -128,9 +128,12 @@ void njode_set_error(const char* fmt, ...);
 #define NJODE_CUDA_OK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { \
     njode_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
     return NJODE_ECUDA; } } while (0)
-#define NJODE_LAUNCH_OK(what) do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) { \
+#define NJODE_LAUNCH_OK(what) do { njode_count_launch(1); cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) { \
     njode_set_error("launch of %s failed: %s (%s:%d)", what, cudaGetErrorString(e__), __FILE__, __LINE__); \
     return NJODE_ECUDA; } } while (0)
+
+// every kernel launch of the library bumps this counter (njode_kernel_launches: bench.py's gpu_launches claim)
+void njode_count_launch(int n);
 
 // one-shot CUDA events around the main sweep kernel (njode_set_kernel_timing)
 void njode_timing_begin(int which, cudaStream_t st);

@@ -934,8 +934,11 @@ int njode_tiled_workers(const NjodeDesc* d, int64_t n_tiles) {
 int njode_tiled_forward(const SweepArgs& a_in, cudaStream_t st) {
   SweepArgs a = a_in;
   // forward CTAs use 128 TMEM columns, ~45 KB smem and 512 threads: 2 per SM
+  // (measured on the default workload, 320 tiles: one CTA per SM is 7 % slower -- the second resident CTA hides
+  //  more latency than it costs even when every CTA has a single tile)
   const int S = a.T.S;
-  int64_t per_stack = (int64_t)sm_count() * 2 / S;
+  const int ctas_per_sm = 2;
+  int64_t per_stack = (int64_t)sm_count() * ctas_per_sm / S;
   if (per_stack > a.n_tiles) per_stack = a.n_tiles > 0 ? a.n_tiles : 1;
   a.n_workers = (int)(per_stack * S);
   return dispatch_tiled(a, st, false);
