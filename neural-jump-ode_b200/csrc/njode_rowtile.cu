@@ -485,6 +485,7 @@ __global__ void __launch_bounds__(NTH) k_rowtile_backward(SweepArgs a) {
         load_plane<NB>(ckpt + ((slot0 + k) * planes + 1 + l) * RT * H, d);
         put_tile<NB>(zb[l], d, H);
       }
+      __syncthreads();                                // m_delta / ext rows written by the first warp above
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float delta = m_delta[4 * ty + i];

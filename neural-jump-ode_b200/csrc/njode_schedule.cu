@@ -6,9 +6,12 @@
 // About 65 % of intervals get a closing step of ~1e-8 because k float32 additions of dt land a few
 // ulp short of t_next; "observation indexing must be bit-exact" therefore means exact __fadd_rn and
 // the two exact comparisons -- never FMA contraction, never double.
+#include <cub/device/device_radix_sort.cuh>
+
 #include "njode_common.cuh"
 
 #define NJODE_BINS 2048
+#define NJODE_BIN_BITS 11
 #define NJODE_KCAP (1 << 24)
 
 __device__ __forceinline__ int count_steps(float t0, float t1, int has_dt, float dt) {
@@ -26,10 +29,13 @@ __device__ __forceinline__ int count_steps(float t0, float t1, int has_dt, float
   return K;
 }
 
-// one thread per trajectory: step counts of its intervals, histogram of counts, total step count
+// one thread per trajectory: step counts of its intervals, the sort key / value of every unit, total step count.
+// key = BINS-1 - min(K, BINS-1): an ascending STABLE sort of the keys puts the longest units first (longest-
+// processing-time order) and keeps the batch order inside a step count, so the tiling -- and with it every
+// summation order downstream -- is the same on every run (an atomic-cursor counting sort is not).
 __global__ void k_count_steps(const float* __restrict__ times, const int64_t* __restrict__ off, int64_t B,
-                              int has_dt, float dt, int32_t* __restrict__ kenc, int32_t* __restrict__ hist,
-                              unsigned long long* __restrict__ header) {
+                              int has_dt, float dt, int32_t* __restrict__ kenc, uint32_t* __restrict__ keys,
+                              int32_t* __restrict__ vals, unsigned long long* __restrict__ header) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long total = 0;
   if (b < B) {
@@ -42,7 +48,8 @@ __global__ void k_count_steps(const float* __restrict__ times, const int64_t* __
       }
       kenc[o] = (K << 1) | has_next;
       total += (unsigned long long)K;
-      atomicAdd(&hist[min(K, NJODE_BINS - 1)], 1);
+      keys[o] = (uint32_t)(NJODE_BINS - 1 - min(K, NJODE_BINS - 1));
+      vals[o] = (int32_t)o;
     }
   }
   // warp-reduce the step total before the single atomic
@@ -50,25 +57,10 @@ __global__ void k_count_steps(const float* __restrict__ times, const int64_t* __
   if ((threadIdx.x & 31) == 0 && total) atomicAdd(&header[NJODE_HDR_TOTAL_STEPS], total);
 }
 
-// descending exclusive scan over the histogram: longest units first (longest-processing-time order)
-__global__ void k_scan_bins(const int32_t* __restrict__ hist, int32_t* __restrict__ start) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    int acc = 0;
-    for (int b = NJODE_BINS - 1; b >= 0; --b) { start[b] = acc; acc += hist[b]; }
-  }
-}
-
-__global__ void k_scatter(const int32_t* __restrict__ kenc, int64_t N, int64_t Npad,
-                          const int32_t* __restrict__ start, int32_t* __restrict__ cursor,
-                          int32_t* __restrict__ perm) {
-  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (o < N) {
-    const int bin = min(kenc[o] >> 1, NJODE_BINS - 1);
-    const int pos = start[bin] + atomicAdd(&cursor[bin], 1);
-    perm[pos] = (int32_t)o;
-  } else if (o < Npad) {
-    perm[o] = -1;
-  }
+// rows of the last tile that hold no unit
+__global__ void k_pad_perm(int64_t N, int64_t Npad, int32_t* __restrict__ perm) {
+  const int64_t o = N + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o < Npad) perm[o] = -1;
 }
 
 __global__ void k_tile_kmax(const int32_t* __restrict__ kenc, const int32_t* __restrict__ perm,
@@ -139,9 +131,18 @@ __global__ void k_fill_knots(const float* __restrict__ times, const int32_t* __r
 }
 
 // ------------------------------------------------------------------------------------------------
+static size_t sort_temp_bytes(int64_t N) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr,
+                                  (int32_t*)nullptr, (int)N, 0, NJODE_BIN_BITS);
+  return bytes;
+}
+
+// workspace: sort keys in / out, unit indices in (the sorted indices go straight to `perm`), cub scratch
 extern "C" size_t njode_schedule_workspace_bytes(int64_t B, int64_t N, int32_t tile_rows) {
-  (void)B; (void)N; (void)tile_rows;
-  return 3 * NJODE_BINS * sizeof(int32_t);
+  (void)B; (void)tile_rows;
+  if (N <= 0) return 256;
+  return 3 * njode_align_up((size_t)N * sizeof(int32_t), 256) + njode_align_up(sort_temp_bytes(N), 256);
 }
 
 extern "C" int njode_schedule_build(const NjodeDesc* desc, const float* times, const int64_t* obs_offsets,
@@ -157,20 +158,26 @@ extern "C" int njode_schedule_build(const NjodeDesc* desc, const float* times, c
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n_tiles = (N + tile_rows - 1) / tile_rows;
   const int64_t Npad = n_tiles * tile_rows;
-  int32_t* hist = (int32_t*)workspace;
-  int32_t* start = hist + NJODE_BINS;
-  int32_t* cursor = start + NJODE_BINS;
-  NJODE_CUDA_OK(cudaMemsetAsync(workspace, 0, 3 * NJODE_BINS * sizeof(int32_t), st));
   NJODE_CUDA_OK(cudaMemsetAsync(header, 0, NJODE_HDR_WORDS * sizeof(int64_t), st));
   if (N == 0) return NJODE_OK;
+  const size_t seg = njode_align_up((size_t)N * sizeof(int32_t), 256);
+  uint32_t* keys_in = (uint32_t*)workspace;
+  uint32_t* keys_out = (uint32_t*)((char*)workspace + seg);
+  int32_t* vals_in = (int32_t*)((char*)workspace + 2 * seg);
+  void* temp = (char*)workspace + 3 * seg;
+  size_t temp_bytes = sort_temp_bytes(N);
   const int TB = 128;
-  k_count_steps<<<(unsigned)((B + TB - 1) / TB), TB, 0, st>>>(times, obs_offsets, B, desc->has_dt, desc->dt, kenc, hist,
-                                                             (unsigned long long*)header);
+  k_count_steps<<<(unsigned)((B + TB - 1) / TB), TB, 0, st>>>(times, obs_offsets, B, desc->has_dt, desc->dt, kenc, keys_in,
+                                                             vals_in, (unsigned long long*)header);
   NJODE_LAUNCH_OK("k_count_steps");
-  k_scan_bins<<<1, 32, 0, st>>>(hist, start);
-  NJODE_LAUNCH_OK("k_scan_bins");
-  k_scatter<<<(unsigned)((Npad + 255) / 256), 256, 0, st>>>(kenc, N, Npad, start, cursor, perm);
-  NJODE_LAUNCH_OK("k_scatter");
+  // stable LSD radix sort over the 11 key bits: perm = unit indices, longest first, batch order within a step count
+  NJODE_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, perm, (int)N, 0,
+                                                NJODE_BIN_BITS, st));
+  njode_count_launch(2);
+  if (Npad > N) {
+    k_pad_perm<<<(unsigned)((Npad - N + 255) / 256), 256, 0, st>>>(N, Npad, perm);
+    NJODE_LAUNCH_OK("k_pad_perm");
+  }
   k_tile_kmax<<<(unsigned)((n_tiles + 127) / 128), 128, 0, st>>>(kenc, perm, n_tiles, tile_rows, tile_kmax);
   NJODE_LAUNCH_OK("k_tile_kmax");
   k_tile_scan<<<1, 1024, 0, st>>>(tile_kmax, n_tiles, tile_slot_off, (long long*)header);
