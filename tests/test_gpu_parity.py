@@ -193,6 +193,44 @@ def test_oracle_parity_many_tiles(impl, hidden):
     assert status.value == 0          # no mbarrier wait timed out in the tcgen05 kernels
 
 
+@pytest.mark.parametrize("workload,B", [("heston_sep_b262144", 16384), ("mixed_h64_ragged", 4096)])
+def test_additivity_over_trajectories_at_scale(workload, B):
+    """Size-independent property at sizes the oracle cannot reach: the loss and every gradient of a batch equal the
+    sum over its two halves when each half is scaled by 1/B_full (trajectories are independent, jump_ode.py:383).
+    The halves get different tilings, step schedules and CTA assignments than the full batch."""
+    import bench
+    from neural_jump_ode import NeuralJumpODE, nj_ode_loss, PackedBatch
+    wl = bench.WORKLOADS[workload]
+    torch.manual_seed(0)
+    model = NeuralJumpODE(**wl["model"]).to(DEV)
+    full = bench.make_batch(wl, B, DEV, 4321)
+    lk = wl["loss"]
+
+    def run(batch, scale):
+        model.zero_grad(set_to_none=True)
+        p, b = model.forward_packed(batch)
+        loss = nj_ode_loss(batch, None, p, b, traj_scale=scale, **lk)
+        loss.backward()
+        return loss.detach().double(), {k: q.grad.double().clone() for k, q in model.named_parameters()}, p.detach()
+
+    l_full, g_full, p_full = run(full, 1.0 / B)
+    cut = B // 2 + 37                                              # uneven halves
+    off = full.offsets
+    n_cut = int(off[cut])
+    halves = [PackedBatch(full.times[:n_cut], full.values[:n_cut], off[:cut + 1].clone()),
+              PackedBatch(full.times[n_cut:], full.values[n_cut:], (off[cut:] - n_cut).clone())]
+    l_sum, g_sum, preds = 0.0, None, []
+    for h in halves:
+        l, g, p = run(h, 1.0 / B)
+        l_sum = l_sum + l
+        g_sum = g if g_sum is None else {k: g_sum[k] + g[k] for k in g}
+        preds.append(p)
+    assert torch.equal(torch.cat(preds), p_full)                   # a unit's forward does not depend on its tile
+    assert abs(float(l_sum) - float(l_full)) <= TOL_LOSS * abs(float(l_full))
+    for k in g_full:
+        assert rel_err(g_sum[k], g_full[k]) <= TOL, k
+
+
 @pytest.mark.parametrize("variance_method", ["direct", "second_moment"])
 @pytest.mark.parametrize("ignore_first", [False, True])
 @pytest.mark.parametrize("M", [1, 2, 3])
