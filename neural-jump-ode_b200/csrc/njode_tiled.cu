@@ -195,7 +195,7 @@ __device__ __forceinline__ int64_t snake_tile(int64_t round, int worker, int n_w
 // ------------------------------------------------------------------------------------------------
 enum { FW_ODE0 = 0, FW_ODE1, FW_JUMP1, FW_OUT0, FW_COUNT };
 constexpr uint32_t F_AHI = 0, F_ALO = 32, F_ACC = 64, F_TMEM_COLS = 128;
-constexpr size_t FWD_SMEM = 1024 + FW_COUNT * 2 * WT_F * 4 + sizeof(SmallParams) + sizeof(Ctl);
+constexpr size_t FWD_SMEM = 1024 + FW_COUNT * 2 * WT_F * 4 + sizeof(SmallParams) + sizeof(Ctl) + 16 + NJODE_TRACE_SMEM_BYTES;
 
 template <int ACT>
 __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
   const ParamTable& T = a.T;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   TR_DECL(0);
+  TR_SMEM(reinterpret_cast<long long*>((reinterpret_cast<uintptr_t>(&ctl + 1) + 15) & ~(uintptr_t)15));
   const int q = warp & 3, c = warp >> 2, row = q * 32 + lane, col0 = c * CW;
   const int s = blockIdx.x % T.S;
   const int worker = blockIdx.x / T.S, n_workers = gridDim.x / T.S;
@@ -332,10 +333,12 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
       tn = tn_ahead;
       tn_ahead = a.knots[(slot0 + (k + 2 <= kmax ? k + 2 : kmax)) * R + row];
       const float delta = __fsub_rn(tn, tc);
+      TR(32 + 7);
 #pragma unroll
       for (int j = 0; j < 8; ++j) z[j] = h[j];
       scale8(sc_kind, z);
       gemm(z, FW_ODE0, acc);
+      TR(32 + 9);
       ld8(sp.b_ode0 + col0, cb);
 #pragma unroll
       for (int j = 0; j < 8; ++j) z[j] = acc[j] + cb[j];
@@ -353,6 +356,7 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
       for (int j = 0; j < 8; ++j) z[j] = act_fwd<ACT>(fmaf(cw[j], delta, z[j]));
       if (ckpt) st8_stream(ckpt + (((slot0 + k) * 2 + 1) * R + row) * H + col0, z);
       gemm(z, FW_ODE1, acc);
+      TR(32 + 8);
       if (k < K) {
         ld8(sp.b_ode1 + col0, cb);
 #pragma unroll
