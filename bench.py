@@ -192,6 +192,7 @@ def main():
     ap.add_argument("--kernel-impl", default="auto", choices=["auto", "generic", "tiled"])
     ap.add_argument("--cpu-sample", type=int, default=384, help="trajectories in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cuda-graph", action="store_true", help="launch the timed steps eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -252,6 +253,31 @@ def main():
         step()
     sync_all()
 
+    # The step is a fixed sequence of ~10 launches on a cached batch (--cache-data): capture it once in a CUDA graph
+    # and replay it, so the host (8 ranks share the box's cores) is out of the timed region's critical path.
+    # Same kernels, same work; falls back to eager launches if capture is not possible.
+    run_step, graphed = step, False
+    if not args.no_cuda_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step()                                 # allocator warm-up on the capture stream
+            torch.cuda.current_stream().wait_stream(side)
+            sync_all()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+            sync_all()
+            graph.replay()
+            sync_all()
+            run_step, graphed = graph.replay, True
+        except Exception as exc:                       # noqa: BLE001 - report and measure eagerly
+            if rank == 0:
+                print(f"bench.py: CUDA graph capture unavailable ({type(exc).__name__}: {exc}); eager launches", file=sys.stderr)
+            torch.cuda.synchronize()
+            run_step, graphed = step, False
+
     # ---- timed region: K steps, device-timed with CUDA events, L2 flushed between steps ----
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -264,12 +290,17 @@ def main():
     for i in range(args.steps):
         flush.zero_()
         ev[i][0].record()
-        step()
+        run_step()
         ev[i][1].record()
     sync_all()
     wall = time.perf_counter() - wall0
     torch.cuda.profiler.stop()
     launches = int(lib.njode_kernel_launches(0))
+    if graphed:                                # replays do not pass through the library's launch counter: count one eager step
+        lib.njode_kernel_launches(1)
+        step()
+        torch.cuda.synchronize()
+        launches = int(lib.njode_kernel_launches(0)) * args.steps
     clocks = sampler.stop() if rank == 0 else None
     ms = [a.elapsed_time(b) for a, b in ev]
     t_dev = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
@@ -372,6 +403,7 @@ def main():
                           "trajectory_ode_steps_per_gpu": total_steps_rank, "observations_per_gpu": batch.N,
                           "parallelism": f"dp{world}", "kernel_impl": args.kernel_impl,
                           "tile_rows": sched.tile_rows, "l2": "flushed between steps (256 MiB write)",
+                          "cuda_graph": graphed,
                           "flop_per_trajectory_step_ode": fl["per_step_ode"]},
                "e2e": {"value": e2e_value, "unit": "trajectory-ODE-steps/s", "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h, "includes": "H2D of packed inputs from pinned memory, schedule "
@@ -379,8 +411,21 @@ def main():
                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
                "wall_s_timed_region": wall}
         print(json.dumps(out), flush=True)
+    sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        # tear-down must never hang the launcher: release the captured graph (it pins NCCL work) first, and leave
+        # through a watchdog if destroy_process_group still blocks (seen once with a captured all-reduce)
+        watchdog = threading.Timer(15.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
+        graph = None
+        run_step = None
+        torch.cuda.synchronize()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        finally:
+            watchdog.cancel()
 
 
 if __name__ == "__main__":
