@@ -687,7 +687,6 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
       // This step's checkpoints and the next knot.  Issued AFTER the hand-over on purpose: scoreboards are shared,
       // so anything that waits on an older load (delta above) or fences memory (the hand-over) would also wait for
       // these ~1000-cycle HBM loads.  They are consumed after the weight-gradient wait below.
-#if !(defined(NJODE_EXP) && NJODE_EXP == 2)
       ld8_cg(ck + k * (2 * R * H), hrow);
       ld8_cg(ck + k * (2 * R * H) + R * H, z);
       tc_next = kn[(k > 0 ? k - 1 : 0) * R];
@@ -695,7 +694,6 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
         prefetch_l2(ck + (k - 1) * (2 * R * H));
         prefetch_l2(ck + (k - 1) * (2 * R * H) + R * H);
       }
-#endif
       // the MN tiles are free once the previous step's weight-gradient MMAs are done
       if (pending) {
         wait_wgrad();
@@ -705,11 +703,6 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
         merge(B_RUN_ODE, B_SACC + (q < 2 ? 0 : 32), B_SACC + 64, true);
       }
       TR(5);
-#if defined(NJODE_EXP) && NJODE_EXP == 2
-      ld8(ck + k * (2 * R * H), hrow);
-      ld8(ck + k * (2 * R * H) + R * H, z);
-      tc_next = kn[(k > 0 ? k - 1 : 0) * R];
-#endif
       scale8(sc_kind, hrow);
       put(hrow, false, 0, 0, T_AM_HI, T_AM_LO);
       put(d, false, 0, 0, T_D1M_HI, T_D1M_LO);
@@ -732,10 +725,6 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
       hand_over();                                                           // -> d s(h) = d0 * W0 ; weight gradients
       pending = true;
       TR(10);
-#if defined(NJODE_EXP) && NJODE_EXP == 1
-      wait_wgrad(); pending = false;    // experiment: idle until the whole batch is done
-      merge(B_RUN_ODE, B_SACC + (q < 2 ? 0 : 32), B_SACC + 64, true);
-#endif
       wait_chain();
       TR(11);
       umma::tmem_ld8(lane_base + B_ACCD, acc);
