@@ -4,6 +4,7 @@ alexander-dybdahl/neural-jump-ode: same import surface as the reference package
 
 from .models.jump_ode import NeuralJumpODE, nj_ode_loss
 from .packed import PackedBatch
+from .optim import FlatAdam
 
 __version__ = "0.1.0"
-__all__ = ["NeuralJumpODE", "nj_ode_loss", "PackedBatch"]
+__all__ = ["NeuralJumpODE", "nj_ode_loss", "PackedBatch", "FlatAdam"]

@@ -7,6 +7,9 @@ generators follow the same recurrences, vectorised over the batch, and emit a ``
 * black_scholes   log-Euler, data_generation.py:26-43
 * ornstein_uhlenbeck   exact one-step transition, data_generation.py:76-91
 * heston          full-truncation Euler with correlated increments, data_generation.py:186-216
+* hybrid_ou_bs    OU up to a per-path switch time (U[0.2T, 0.8T] unless given), then Black-Scholes in log space from
+                  the value reached, data_generation.py:130-160 (a path whose OU leg is <= 0 at the switch is NaN in
+                  the reference, ~1 in 2000; here such paths are re-drawn from the valid ones so batches stay finite)
 * observation rule: first and last grid point always observed plus a uniform random interior subset,
   n_obs = max(2, int(obs_fraction * n_grid)) (data_generation.py:235-249)
 
@@ -26,6 +29,7 @@ _DEFAULTS = {
     "black_scholes": dict(mu=0.0, sigma=0.2, x0=1.0),
     "ornstein_uhlenbeck": dict(theta=1.0, mu=0.0, sigma=0.3, x0=0.0),
     "heston": dict(mu=0.0, kappa=2.0, theta=0.04, xi=0.5, rho=-0.5, x0=1.0, v0=0.04),
+    "hybrid_ou_bs": dict(theta_ou=1.0, mu_ou=0.0, sigma_ou=0.3, mu_bs=0.0, sigma_bs=0.2, x0=1.0, switch_time=None),
 }
 
 
@@ -59,6 +63,32 @@ def simulate_paths(process_type: str, n_paths: int, n_steps: int = 100, T: float
         for i in range(n_steps):
             cols.append(cols[-1] * decay + shift + noise[:, i])
         X = torch.stack(cols, dim=1)
+    elif process_type == "hybrid_ou_bs":
+        th = p["theta_ou"]
+        decay = math.exp(-th * dt)
+        shift = p["mu_ou"] * (1.0 - decay)
+        amp = p["sigma_ou"] * (math.sqrt((1.0 - math.exp(-2.0 * th * dt)) / (2.0 * th)) if th > 0 else math.sqrt(dt))
+        noise = amp * randn()
+        cols = [torch.full((n_paths,), float(p["x0"]), device=device)]
+        for i in range(n_steps):
+            cols.append(cols[-1] * decay + shift + noise[:, i])
+        ou = torch.stack(cols, dim=1)                                         # OU leg on the whole grid
+        if p["switch_time"] is None:
+            sw = 0.2 * T + 0.6 * T * torch.rand(n_paths, device=device, generator=generator)
+        else:
+            sw = torch.full((n_paths,), float(p["switch_time"]), device=device)
+        sidx = torch.clamp((sw / dt).long(), max=n_steps)                     # int(switch_time / dt)
+        incr = (p["mu_bs"] - 0.5 * p["sigma_bs"] ** 2) * dt + p["sigma_bs"] * math.sqrt(dt) * randn()
+        csum = torch.cat([torch.zeros(n_paths, 1, device=device), torch.cumsum(incr, dim=1)], dim=1)   # (n, n_steps+1)
+        x_sw = torch.gather(ou, 1, sidx[:, None])                             # value at the switch
+        c_sw = torch.gather(csum, 1, sidx[:, None])
+        bs = torch.exp(torch.log(x_sw) + csum - c_sw)                         # log-space BS leg (NaN if x_sw <= 0)
+        grid = torch.arange(n_steps + 1, device=device)[None, :]
+        X = torch.where(grid <= sidx[:, None], ou, bs)
+        bad = ~torch.isfinite(X).all(dim=1)
+        if bool(bad.any()) and not bool(bad.all()):
+            good = torch.nonzero(~bad).flatten()
+            X[bad] = X[good[torch.arange(int(bad.sum()), device=device) % good.numel()]]
     else:  # heston
         z1, z2 = randn(), randn()
         sq = math.sqrt(dt)
@@ -140,12 +170,13 @@ def concat_batches(batches) -> PackedBatch:
 
 def make_mixed_ragged_batch(n_paths: int, frac_lo: float = 0.02, frac_hi: float = 0.2, n_steps: int = 100,
                             T: float = 1.0, device="cuda", seed: int = 0) -> PackedBatch:
-    """BASELINE config 5: equal parts Black-Scholes / OU / Heston paths (experiment_hybrid.py-style mixed batch,
-    default process parameters of the experiment scripts) with a per-path observation fraction U[frac_lo, frac_hi]."""
+    """BASELINE config 5: equal parts Black-Scholes / OU / Heston / hybrid OU->BS paths (experiment_hybrid.py-style
+    mixed batch, process parameters of the experiment scripts) with a per-path observation fraction U[frac_lo, frac_hi]."""
     g = torch.Generator(device=device).manual_seed(seed)
     procs = [("black_scholes", dict(mu=0.1, sigma=0.5, x0=1.0)),
              ("ornstein_uhlenbeck", dict(theta=1.0, mu=0.5, sigma=0.3, x0=0.0)),
-             ("heston", dict(mu=0.5, kappa=2.0, theta=0.04, xi=0.5, rho=-0.5, x0=1.0, v0=0.04))]
+             ("heston", dict(mu=0.5, kappa=2.0, theta=0.04, xi=0.5, rho=-0.5, x0=1.0, v0=0.04)),
+             ("hybrid_ou_bs", dict(theta_ou=1.0, mu_ou=0.5, sigma_ou=0.3, mu_bs=0.1, sigma_bs=0.3, x0=1.0))]
     parts, left = [], n_paths
     for i, (name, kw) in enumerate(procs):
         n = left if i == len(procs) - 1 else n_paths // len(procs)

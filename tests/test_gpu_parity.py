@@ -321,6 +321,39 @@ def test_adam_kernel_matches_torch():
     assert rel_err(p.cpu(), ref.detach().cpu()) <= 1e-6
 
 
+def test_flat_adam_matches_torch_adam_on_a_training_run():
+    """Row N1: FlatAdam (one njode_adam_step launch on the flat buffer) follows torch.optim.Adam(lr, weight_decay)
+    through 8 optimizer steps of the real model (utils/training.py:396 semantics), and keeps state_dict keys/values."""
+    from neural_jump_ode import NeuralJumpODE, nj_ode_loss, FlatAdam
+    mk = dict(input_dim=1, hidden_dim=32, output_dim=1, dt_ode_step=0.01, num_moments=2)
+    bt, bv = _random_batch(64, seed=4)
+    btc, bvc = [t.to(DEV) for t in bt], [v.to(DEV) for v in bv]
+    lk = dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0])
+    models, opts = [], []
+    for flat in (False, True):
+        torch.manual_seed(1)
+        m = NeuralJumpODE(**mk).to(DEV)
+        keys = list(m.state_dict().keys())
+        o = FlatAdam(m.parameters(), lr=1e-2, weight_decay=5e-4) if flat else torch.optim.Adam(m.parameters(), lr=1e-2, weight_decay=5e-4)
+        assert list(m.state_dict().keys()) == keys
+        models.append(m)
+        opts.append(o)
+    losses = [[], []]
+    for step in range(8):
+        for i, (m, o) in enumerate(zip(models, opts)):
+            o.zero_grad()
+            p, b = m(btc, bvc)
+            loss = nj_ode_loss(btc, bvc, p, b, **lk)
+            loss.backward()
+            o.step()
+            losses[i].append(loss.item())
+    assert losses[0][-1] < losses[0][0]                               # it trains
+    for a, b in zip(losses[0], losses[1]):
+        assert abs(a - b) <= 1e-4 * abs(a)
+    for (k, pa), (_, pb) in zip(models[0].named_parameters(), models[1].named_parameters()):
+        assert rel_err(pb.detach().cpu(), pa.detach().cpu()) <= 1e-4, k
+
+
 def test_error_paths():
     from neural_jump_ode import NeuralJumpODE, nj_ode_loss
     m = NeuralJumpODE(1, 8, 1)

@@ -108,3 +108,37 @@ def test_packed_batch_host_logic():
     with pytest.raises(RuntimeError, match="CUDA only"):
         from neural_jump_ode import NeuralJumpODE
         b.schedule(NeuralJumpODE(1, 8, 1, dt_ode_step=0.1).descriptor())
+
+
+@pytest.mark.parametrize("process", ["black_scholes", "ornstein_uhlenbeck", "heston", "hybrid_ou_bs"])
+def test_path_generators_and_observation_rule(process):
+    """Vectorised generators (row N2): shapes, the reference's observation rule (first and last grid point always
+    observed, n_obs = max(2, int(frac * n_grid)), data_generation.py:235-249), strictly increasing float32 grid
+    times, finite values, determinism in the seed."""
+    from neural_jump_ode.simulation import simulate_paths, sample_observations, make_packed_batch
+    g = torch.Generator().manual_seed(3)
+    times, X = simulate_paths(process, 257, n_steps=100, T=1.0, device="cpu", generator=g)
+    assert times.shape == (101,) and X.shape == (257, 101) and X.dtype == torch.float32
+    assert torch.isfinite(X).all() and torch.equal(times, torch.linspace(0.0, 1.0, 101))
+    batch = sample_observations(times, X, 0.1, generator=g)
+    assert batch.B == 257 and batch.sizes == [10] * 257 and batch.N == 2570
+    t = batch.times.view(257, 10)
+    assert float(t[:, 0].max()) == 0.0 and float(t[:, -1].min()) == 1.0
+    assert bool((t[:, 1:] > t[:, :-1]).all())
+    a = make_packed_batch(process, 33, 0.1, device="cpu", seed=5)
+    b = make_packed_batch(process, 33, 0.1, device="cpu", seed=5)
+    assert torch.equal(a.values, b.values) and torch.equal(a.times, b.times)
+    with pytest.raises(ValueError):
+        simulate_paths("no_such_process", 4, device="cpu")
+
+
+def test_mixed_ragged_batch():
+    from neural_jump_ode.simulation import make_mixed_ragged_batch
+    b = make_mixed_ragged_batch(101, 0.02, 0.2, n_steps=100, device="cpu", seed=2)
+    assert b.B == 101 and b.N == sum(b.sizes) and int(b.offsets[-1]) == b.N
+    assert min(b.sizes) >= 2 and max(b.sizes) <= 20 and len(set(b.sizes)) > 3          # ragged
+    off = b.offsets.tolist()
+    for i in range(b.B):
+        t = b.times[off[i]:off[i + 1]]
+        assert float(t[0]) == 0.0 and float(t[-1]) == 1.0 and bool((t[1:] > t[:-1]).all())
+    assert torch.isfinite(b.values).all()
