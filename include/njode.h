@@ -131,6 +131,9 @@ int njode_schedule_knots(const float* times, const int32_t* kenc, const int32_t*
  *       njode_backward.  Pass NULL for inference (no checkpoints written).
  * workspace: njode_forward_workspace_bytes (re-laid-out weights). */
 int64_t njode_ckpt_row_floats(const NjodeDesc* desc);
+/* Number of tiles the schedule of N observation units has (tiles hold tile_rows rows, of which a flavour- and
+ * size-dependent number carries units; the rest is padding).  Sizes perm (n_tiles * tile_rows), tile_kmax, tile_slot_off. */
+int64_t njode_num_tiles(const NjodeDesc* desc, int64_t N);
 size_t  njode_forward_workspace_bytes(const NjodeDesc* desc);
 int njode_forward(const NjodeDesc* desc, const float* params, const float* times, const float* values,
                   const int64_t* obs_offsets, int64_t B, int64_t N,

@@ -137,6 +137,34 @@ extern "C" int32_t njode_tile_rows(const NjodeDesc* d) {
   return impl == NJODE_IMPL_TILED ? NJODE_TILED_TILE_ROWS : NJODE_GENERIC_TILE_ROWS;
 }
 
+static int sm_count_abi() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+int32_t njode_tile_units(const NjodeDesc* d, int64_t N) {
+  const char* why = nullptr;
+  const int impl = pick_impl(d, &why);
+  if (impl != NJODE_IMPL_TILED) return NJODE_GENERIC_TILE_ROWS;
+  const int S = d->shared_network ? 1 : d->num_moments;
+  const int64_t full_tiles = (N + NJODE_TILED_TILE_ROWS - 1) / NJODE_TILED_TILE_ROWS;
+  const int64_t sms_per_stack = sm_count_abi() / S > 0 ? sm_count_abi() / S : 1;
+  // measured: partial tiles pay only while full tiles would leave SMs idle (default workload, 2.2 full tiles per SM:
+  // half tiles are 13 % slower; configs[0] at batch 128, 0.14 tiles per SM: quarter tiles are 5 % faster)
+  if (4 * full_tiles <= sms_per_stack) return NJODE_TILED_TILE_ROWS / 4;
+  if (full_tiles <= sms_per_stack) return NJODE_TILED_TILE_ROWS / 2;
+  return NJODE_TILED_TILE_ROWS;
+}
+
+extern "C" int64_t njode_num_tiles(const NjodeDesc* d, int64_t N) {
+  const char* why = nullptr;
+  if (!pick_impl(d, &why)) { njode_set_error("njode_num_tiles: %s", why); return -1; }
+  if (N < 0) { njode_set_error("njode_num_tiles: negative size"); return -1; }
+  const int u = njode_tile_units(d, N);
+  return (N + u - 1) / u;
+}
+
 extern "C" int64_t njode_ckpt_row_floats(const NjodeDesc* d) {
   const char* why = nullptr;
   const int impl = pick_impl(d, &why);
@@ -227,7 +255,8 @@ static int check_common(const char* fn, const NjodeDesc* desc, const float* para
   if (B < 0 || N < 0) NJODE_FAIL(NJODE_EINVAL, "%s: negative size", fn);
   const int want = *impl == NJODE_IMPL_TILED ? NJODE_TILED_TILE_ROWS : NJODE_GENERIC_TILE_ROWS;
   if (tile_rows != want) NJODE_FAIL(NJODE_EINVAL, "%s: schedule was built for tile_rows=%d, kernels need %d", fn, tile_rows, want);
-  if (n_tiles != (N + tile_rows - 1) / tile_rows) NJODE_FAIL(NJODE_EINVAL, "%s: n_tiles does not match N", fn);
+  const int units = njode_tile_units(desc, N);
+  if (n_tiles != (N + units - 1) / units) NJODE_FAIL(NJODE_EINVAL, "%s: n_tiles does not match N (njode_num_tiles)", fn);
   return NJODE_OK;
 }
 
@@ -242,6 +271,7 @@ static SweepArgs make_args(const NjodeDesc* desc, const float* params, const flo
   a.params = params; a.params_t = params_t; a.times = times; a.values = values;
   a.kenc = kenc; a.perm = perm; a.tile_kmax = tile_kmax; a.tile_slot_off = tile_slot_off; a.knots = knots;
   a.N = N; a.n_tiles = n_tiles; a.total_slots = total_slots; a.tile_rows = tile_rows;
+  a.tile_units = njode_tile_units(desc, N);
   return a;
 }
 

@@ -144,6 +144,12 @@ static inline size_t njode_align_up(size_t v, size_t a) { return (v + a - 1) / a
 // ------------------------------------------------------------------------------------------------
 // kernel flavours (implemented in njode_generic.cu / njode_tiled.cu)
 // ------------------------------------------------------------------------------------------------
+// Units packed into each tile (<= tile_rows; the remaining rows of a tile are padding).  The tcgen05 kernels are
+// latency chains: with few tiles per SM their time is (steps of the longest tile) x (latency of one step), and the
+// weight-gradient MMAs (contraction over the tile's rows) are the long pole of a step -- half- or quarter-filled
+// tiles shorten that pole and spread the work over more SMs.  Every entry point derives this from (desc, N).
+int32_t njode_tile_units(const NjodeDesc* d, int64_t N);
+
 struct SweepArgs {
   NjodeDesc desc;
   ParamTable T;
@@ -158,6 +164,7 @@ struct SweepArgs {
   const float* knots;
   int64_t N, n_tiles, total_slots;
   int32_t tile_rows;
+  int32_t tile_units;        // units per tile (rows >= tile_units of every tile are padding)
   // forward outputs
   float* preds;
   float* preds_before;

@@ -57,10 +57,15 @@ __global__ void k_count_steps(const float* __restrict__ times, const int64_t* __
   if ((threadIdx.x & 31) == 0 && total) atomicAdd(&header[NJODE_HDR_TOTAL_STEPS], total);
 }
 
-// rows of the last tile that hold no unit
-__global__ void k_pad_perm(int64_t N, int64_t Npad, int32_t* __restrict__ perm) {
-  const int64_t o = N + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (o < Npad) perm[o] = -1;
+// sorted unit list -> tiles of `tile_rows` rows with `units` units each (the other rows hold no unit: -1)
+__global__ void k_spread_perm(const int32_t* __restrict__ sorted, int64_t N, int64_t Npad, int tile_rows, int units,
+                              int32_t* __restrict__ perm) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Npad) return;
+  const int64_t tile = idx / tile_rows;
+  const int r = (int)(idx - tile * tile_rows);
+  const int64_t j = tile * units + r;
+  perm[idx] = (r < units && j < N) ? sorted[j] : -1;
 }
 
 __global__ void k_tile_kmax(const int32_t* __restrict__ kenc, const int32_t* __restrict__ perm,
@@ -142,7 +147,7 @@ static size_t sort_temp_bytes(int64_t N) {
 extern "C" size_t njode_schedule_workspace_bytes(int64_t B, int64_t N, int32_t tile_rows) {
   (void)B; (void)tile_rows;
   if (N <= 0) return 256;
-  return 3 * njode_align_up((size_t)N * sizeof(int32_t), 256) + njode_align_up(sort_temp_bytes(N), 256);
+  return 4 * njode_align_up((size_t)N * sizeof(int32_t), 256) + njode_align_up(sort_temp_bytes(N), 256);
 }
 
 extern "C" int njode_schedule_build(const NjodeDesc* desc, const float* times, const int64_t* obs_offsets,
@@ -156,7 +161,9 @@ extern "C" int njode_schedule_build(const NjodeDesc* desc, const float* times, c
   if (workspace_bytes < njode_schedule_workspace_bytes(B, N, tile_rows))
     NJODE_FAIL(NJODE_EWORKSPACE, "njode_schedule_build: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t n_tiles = (N + tile_rows - 1) / tile_rows;
+  const int units = njode_tile_units(desc, N);
+  if (units > tile_rows) NJODE_FAIL(NJODE_EINVAL, "njode_schedule_build: tile_rows does not match this descriptor (njode_tile_rows)");
+  const int64_t n_tiles = (N + units - 1) / units;
   const int64_t Npad = n_tiles * tile_rows;
   NJODE_CUDA_OK(cudaMemsetAsync(header, 0, NJODE_HDR_WORDS * sizeof(int64_t), st));
   if (N == 0) return NJODE_OK;
@@ -164,20 +171,19 @@ extern "C" int njode_schedule_build(const NjodeDesc* desc, const float* times, c
   uint32_t* keys_in = (uint32_t*)workspace;
   uint32_t* keys_out = (uint32_t*)((char*)workspace + seg);
   int32_t* vals_in = (int32_t*)((char*)workspace + 2 * seg);
-  void* temp = (char*)workspace + 3 * seg;
+  int32_t* sorted = (int32_t*)((char*)workspace + 3 * seg);
+  void* temp = (char*)workspace + 4 * seg;
   size_t temp_bytes = sort_temp_bytes(N);
   const int TB = 128;
   k_count_steps<<<(unsigned)((B + TB - 1) / TB), TB, 0, st>>>(times, obs_offsets, B, desc->has_dt, desc->dt, kenc, keys_in,
                                                              vals_in, (unsigned long long*)header);
   NJODE_LAUNCH_OK("k_count_steps");
   // stable LSD radix sort over the 11 key bits: perm = unit indices, longest first, batch order within a step count
-  NJODE_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, perm, (int)N, 0,
+  NJODE_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, sorted, (int)N, 0,
                                                 NJODE_BIN_BITS, st));
   njode_count_launch(2);
-  if (Npad > N) {
-    k_pad_perm<<<(unsigned)((Npad - N + 255) / 256), 256, 0, st>>>(N, Npad, perm);
-    NJODE_LAUNCH_OK("k_pad_perm");
-  }
+  k_spread_perm<<<(unsigned)((Npad + 255) / 256), 256, 0, st>>>(sorted, N, Npad, tile_rows, units, perm);
+  NJODE_LAUNCH_OK("k_spread_perm");
   k_tile_kmax<<<(unsigned)((n_tiles + 127) / 128), 128, 0, st>>>(kenc, perm, n_tiles, tile_rows, tile_kmax);
   NJODE_LAUNCH_OK("k_tile_kmax");
   k_tile_scan<<<1, 1024, 0, st>>>(tile_kmax, n_tiles, tile_slot_off, (long long*)header);

@@ -144,16 +144,17 @@ __device__ __forceinline__ void issue_chain(uint32_t tmem_acc, uint32_t tmem_a_h
   for (int ks = 0; ks < 4; ++ks) umma::mma_ts(tmem_acc, tmem_a_hi + 8 * ks, dbh + 2 * ks, idesc, 1);
 }
 
-// 3xTF32 row-contraction GEMM: acc[64 x N] = [A0|A1]^T (MN-major tiles, rows = contraction) * [B0|B1|..]
+// 3xTF32 row-contraction GEMM: acc[64 x N] = [A0|A1]^T (MN-major tiles, rows = contraction) * [B0|B1|..] over the
+// first 8 * nks rows of the tiles (nks = 16 for full tiles; partially filled tiles contract over their units only)
 template <int N>
-__device__ __forceinline__ void issue_wgrad(uint32_t tmem_acc, uint64_t dah, uint64_t dal, uint64_t dbh, uint64_t dbl) {
+__device__ __forceinline__ void issue_wgrad(uint32_t tmem_acc, uint64_t dah, uint64_t dal, uint64_t dbh, uint64_t dbl, int nks) {
   constexpr uint32_t idesc = umma::idesc_tf32(64, N, 1, 1);
-#pragma unroll
-  for (int ks = 0; ks < 16; ++ks) umma::mma_ss(tmem_acc, dal + 64 * ks, dbh + 64 * ks, idesc, ks > 0);   // fresh accumulator
-#pragma unroll
-  for (int ks = 0; ks < 16; ++ks) umma::mma_ss(tmem_acc, dah + 64 * ks, dbl + 64 * ks, idesc, 1);
-#pragma unroll
-  for (int ks = 0; ks < 16; ++ks) umma::mma_ss(tmem_acc, dah + 64 * ks, dbh + 64 * ks, idesc, 1);
+#pragma unroll 4
+  for (int ks = 0; ks < nks; ++ks) umma::mma_ss(tmem_acc, dal + 64 * ks, dbh + 64 * ks, idesc, ks > 0);   // fresh accumulator
+#pragma unroll 4
+  for (int ks = 0; ks < nks; ++ks) umma::mma_ss(tmem_acc, dah + 64 * ks, dbl + 64 * ks, idesc, 1);
+#pragma unroll 4
+  for (int ks = 0; ks < nks; ++ks) umma::mma_ss(tmem_acc, dah + 64 * ks, dbh + 64 * ks, idesc, 1);
 }
 
 // input scaling of 8 values with ONE warp-uniform switch (a per-element runtime switch bloats the loops)
@@ -416,6 +417,7 @@ __device__ __forceinline__ void bwd_issuer(const SweepArgs& a, uint8_t* smem_raw
   const int worker = blockIdx.x / S, n_workers = gridDim.x / S;
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&ctl.tmem_base);
   const uint64_t wbase0 = umma::desc_k(umma::smem_u32(m.wt)), tbase0 = umma::desc_mn(umma::smem_u32(m.tiles), TILE_F * 4);
+  const int nks = a.tile_units / 8;               // K-slices of the row contraction: the tile's units only
   TR_DECL(2);
   TR_SMEM(reinterpret_cast<long long*>((reinterpret_cast<uintptr_t>(m.ctl + 1) + 15) & ~(uintptr_t)15) + NJODE_TRACE_SMEM_REC);
   bool ok = true;
@@ -442,7 +444,7 @@ __device__ __forceinline__ void bwd_issuer(const SweepArgs& a, uint8_t* smem_raw
     if (umma::elect_one()) {
       issue_chain(tmem + B_ACCD, tmem + B_DHI, tmem + B_DLO, wdesc(wbase, WB_OUT0T, 0), wdesc(wbase, WB_OUT0T, 1));
       umma::commit(&ctl.bar_chain);
-      issue_wgrad<40>(tmem + B_SACC, tdesc(tbase, T_D1M_HI), tdesc(tbase, T_D1M_LO), tdesc(tbase, T_AM_HI), tdesc(tbase, T_AM_LO));
+      issue_wgrad<40>(tmem + B_SACC, tdesc(tbase, T_D1M_HI), tdesc(tbase, T_D1M_LO), tdesc(tbase, T_AM_HI), tdesc(tbase, T_AM_LO), nks);
       umma::commit(&ctl.bar_wgrad);
     }
     __syncwarp();
@@ -470,7 +472,7 @@ __device__ __forceinline__ void bwd_issuer(const SweepArgs& a, uint8_t* smem_raw
       if (umma::elect_one()) {
         issue_chain(tmem + B_ACCD, tmem + B_DHI, tmem + B_DLO, wdesc(wbase, WB_ODE0T, 0), wdesc(wbase, WB_ODE0T, 1));    // d s(h)
         umma::commit(&ctl.bar_chain);
-        issue_wgrad<72>(tmem + B_SACC, tdesc(tbase, T_D1M_HI), tdesc(tbase, T_D1M_LO), tdesc(tbase, T_ZM_HI), tdesc(tbase, T_ZM_LO));
+        issue_wgrad<72>(tmem + B_SACC, tdesc(tbase, T_D1M_HI), tdesc(tbase, T_D1M_LO), tdesc(tbase, T_ZM_HI), tdesc(tbase, T_ZM_LO), nks);
         umma::commit(&ctl.bar_wgrad);
       }
       __syncwarp();
@@ -487,7 +489,7 @@ __device__ __forceinline__ void bwd_issuer(const SweepArgs& a, uint8_t* smem_raw
     if (umma::elect_one()) {
       issue_chain(tmem + B_ACCD, tmem + B_DHI, tmem + B_DLO, wdesc(wbase, WB_JUMP1T, 0), wdesc(wbase, WB_JUMP1T, 1));
       umma::commit(&ctl.bar_chain);
-      issue_wgrad<40>(tmem + B_SACC, tdesc(tbase, T_D1M_HI), tdesc(tbase, T_D1M_LO), tdesc(tbase, T_AM_HI), tdesc(tbase, T_AM_LO));
+      issue_wgrad<40>(tmem + B_SACC, tdesc(tbase, T_D1M_HI), tdesc(tbase, T_D1M_LO), tdesc(tbase, T_AM_HI), tdesc(tbase, T_AM_LO), nks);
       umma::commit(&ctl.bar_wgrad);
     }
     __syncwarp();
@@ -495,7 +497,7 @@ __device__ __forceinline__ void bwd_issuer(const SweepArgs& a, uint8_t* smem_raw
     wait_ops();
     fresh();
     if (umma::elect_one()) {
-      issue_wgrad<8>(tmem + B_SACC, tdesc(tbase, T_D1M_HI), tdesc(tbase, T_D1M_LO), tdesc(tbase, T_XM_HI), tdesc(tbase, T_XM_LO));
+      issue_wgrad<8>(tmem + B_SACC, tdesc(tbase, T_D1M_HI), tdesc(tbase, T_D1M_LO), tdesc(tbase, T_XM_HI), tdesc(tbase, T_XM_LO), nks);
       umma::commit(&ctl.bar_wgrad);
     }
     __syncwarp();
@@ -541,6 +543,8 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
   const uint32_t quad_base = tmem + ((uint32_t)(q * 32) << 16);     // this warp's lane quadrant, column 0
   const uint32_t lane_base = quad_base + (uint32_t)col0;            // ... at this thread's column slice
   const uint32_t tiles_s = umma::smem_u32(tiles);
+  // rows >= tile_units of every tile are padding: the row contraction stops before them, so they skip the tile stores
+  const bool has_unit_row = row < a.tile_units;
   if (c == 0) {  // zero the persistent weight-gradient accumulators
     uint32_t zero[8];
 #pragma unroll
@@ -576,10 +580,10 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
     uint32_t hi[8], lo[8];
     umma::split8(v, hi, lo);
     if (to_tmem) { umma::tmem_st8_raw(lane_base + c_hi, hi); umma::tmem_st8_raw(lane_base + c_lo, lo); }
-    if (tile_hi >= 0) { umma::chunk_to_mn_tile(tiles_s + tile_hi * (TILE_F * 4), row, c, hi); umma::chunk_to_mn_tile(tiles_s + tile_lo * (TILE_F * 4), row, c, lo); }
+    if (tile_hi >= 0 && has_unit_row) { umma::chunk_to_mn_tile(tiles_s + tile_hi * (TILE_F * 4), row, c, hi); umma::chunk_to_mn_tile(tiles_s + tile_lo * (TILE_F * 4), row, c, lo); }
   };
   auto put_aux = [&](const float (&xv)[8]) {       // per-row scalars: written by the c == 0 thread of the row
-    if (c == 0) {
+    if (c == 0 && has_unit_row) {
       uint32_t hi[8], lo[8];
       umma::split8(xv, hi, lo);
       umma::chunk_to_mn_tile(tiles_s + T_XM_HI * (TILE_F * 4), row, 0, hi);

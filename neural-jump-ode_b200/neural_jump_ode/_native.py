@@ -52,6 +52,7 @@ SIGNATURES = {
     "njode_schedule_build": (C.c_int, [_DESC, _P, _P, _I64, _I64, _I32, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "njode_schedule_knots": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I32, _DESC, _P, _P]),
     "njode_ckpt_row_floats": (_I64, [_DESC]),
+    "njode_num_tiles": (_I64, [_DESC, _I64]),
     "njode_forward_workspace_bytes": (_SZ, [_DESC]),
     "njode_forward": (C.c_int, [_DESC, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _I64, _I64, _I32,
                                 _P, _P, _P, _P, _SZ, _P]),

@@ -102,7 +102,9 @@ class PackedBatch:
                                "move the model and the batch to a CUDA device")
         dev = self.device
         N, B = self.N, self.B
-        n_tiles = (N + tile_rows - 1) // tile_rows
+        n_tiles = lib.njode_num_tiles(desc, N)        # tiles may be partially filled (small batches, tcgen05 flavour)
+        if n_tiles < 0:
+            nat.check(-1, "njode_num_tiles")
         s = Schedule()
         s.tile_rows, s.n_tiles = tile_rows, n_tiles
         with torch.cuda.device(dev):
