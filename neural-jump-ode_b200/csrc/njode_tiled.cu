@@ -114,10 +114,18 @@ __device__ __forceinline__ void ld8(const float* __restrict__ src, float (&v)[8]
   v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
 }
 // one 256-bit global load / store per thread for its 8 checkpoint floats (LDG.256 / STG.256 on sm_100): one L2
-// request per 32-byte sector instead of two.  (Loads that bypass L1 -- ld.global.cg -- were measured slower.)
+// request per 32-byte sector instead of two, and no L1 allocation (the fills compete with the tensor core's
+// shared-memory operand fetch: -6.5 % on the reverse sweep).  128-bit ld.global.cg pairs were measured slower.
 __device__ __forceinline__ void ld8_cg(const float* __restrict__ src, float (&v)[8]) {
-  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+  asm volatile("ld.global.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(src));
+}
+// scalar global load that does not allocate in L1 (L1 fills share the SRAM data path with the tensor core's
+// shared-memory operand fetch: checkpoint / knot loads in flight measurably slow the weight-gradient MMA batch)
+__device__ __forceinline__ float ld_na(const float* __restrict__ p) {
+  float v;
+  asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 __device__ __forceinline__ void st8_stream(float* __restrict__ dst, const float (&v)[8]) {
@@ -327,12 +335,12 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
     // Euler steps with x held constant                              jump_ode.py:188-203, :122-140
     // knots are loaded one step ahead: a load consumed in the step that issues it is an exposed global-memory
     // latency on this latency-bound chain (it was the top stall site of the forward kernel, 17 % of its samples)
-    float tn = a.knots[(slot0 + 0) * R + row];
-    float tn_ahead = kmax > 0 ? a.knots[(slot0 + 1) * R + row] : tn;
+    float tn = ld_na(a.knots + (slot0 + 0) * R + row);
+    float tn_ahead = kmax > 0 ? ld_na(a.knots + (slot0 + 1) * R + row) : tn;
     for (int k = 0; k < kmax; ++k) {
       const float tc = tn;
       tn = tn_ahead;
-      tn_ahead = a.knots[(slot0 + (k + 2 <= kmax ? k + 2 : kmax)) * R + row];
+      tn_ahead = ld_na(a.knots + (slot0 + (k + 2 <= kmax ? k + 2 : kmax)) * R + row);
       const float delta = __fsub_rn(tn, tc);
       TR(32 + 7);
 #pragma unroll
@@ -674,8 +682,8 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
     out_backward(a.grad_preds_before, (int64_t)u + 1, u >= 0 && (ke & 1));
 
     // ---- Euler steps, last to first ----
-    float tn = kn[kmax * R];
-    float tc_next = kmax > 0 ? kn[(kmax - 1) * R] : tn;
+    float tn = ld_na(kn + kmax * R);
+    float tc_next = kmax > 0 ? ld_na(kn + (kmax - 1) * R) : tn;
     bool pending = false;                             // weight-gradient MMAs of the previous step still to be merged
     for (int k = kmax - 1; k >= 0; --k) {
       TR(1);
@@ -693,7 +701,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
       // these ~1000-cycle HBM loads.  They are consumed after the weight-gradient wait below.
       ld8_cg(ck + k * (2 * R * H), hrow);
       ld8_cg(ck + k * (2 * R * H) + R * H, z);
-      tc_next = kn[(k > 0 ? k - 1 : 0) * R];
+      tc_next = ld_na(kn + (k > 0 ? k - 1 : 0) * R);
       if (k > 0) {   // and pull the NEXT step's checkpoints into L2 (no destination register, no scoreboard)
         prefetch_l2(ck + (k - 1) * (2 * R * H));
         prefetch_l2(ck + (k - 1) * (2 * R * H) + R * H);
