@@ -54,7 +54,8 @@ enum {
   NJODE_OK = 0,
   NJODE_EINVAL = -1,      /* bad argument / unsupported configuration */
   NJODE_ECUDA = -2,       /* CUDA runtime error */
-  NJODE_EWORKSPACE = -3   /* workspace too small */
+  NJODE_EWORKSPACE = -3,  /* workspace too small */
+  NJODE_ECAPACITY = -4    /* njode_forward_batch: arena / checkpoint buffer smaller than this batch needs (header_host is valid) */
 };
 
 /* jump_ode.py:6-13; unknown names map to RELU on the Python side (jump_ode.py:18) */
@@ -142,6 +143,28 @@ int njode_forward(const NjodeDesc* desc, const float* params, const float* times
                   int64_t n_tiles, int64_t total_slots, int32_t tile_rows,
                   float* preds, float* preds_before, float* ckpt,
                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- un-cached batch in ONE call: schedule build -> header to the host -> knots -> forward sweep -------------
+ * What NeuralJumpODE.forward (jump_ode.py:218-233) costs when every training step brings a new batch: the three
+ * calls above need a host round trip in the middle (the header sizes knots / checkpoints), and whatever the host
+ * does around that round trip is time the GPU idles.  Here the caller passes buffers sized from a guess:
+ *   arena   device, persistent for the life of the schedule: kenc, perm, tile_kmax, tile_slot_off, header, knots at
+ *           the byte offsets njode_batch_arena_bytes reports in layout[NJODE_ARENA_*] (all but knots are independent
+ *           of total_slots; knots come last, so an arena that is too large is fine)
+ *   ckpt    device, ckpt_floats >= S * total_slots * tile_rows * njode_ckpt_row_floats, or want_ckpt = 0
+ *   scratch device, njode_batch_scratch_bytes, free again when the call's work on `stream` is done
+ *   header_host  host int64[NJODE_HDR_WORDS] (pinned for a truly asynchronous copy); valid on return
+ * The call synchronises `stream` once, after the schedule is built.  If arena or ckpt turn out too small it returns
+ * NJODE_ECAPACITY before any sweep work: size them from header_host[NJODE_HDR_TOTAL_SLOTS] and call again. */
+enum { NJODE_ARENA_KENC = 0, NJODE_ARENA_PERM, NJODE_ARENA_TILE_KMAX, NJODE_ARENA_TILE_SLOT_OFF, NJODE_ARENA_HEADER,
+       NJODE_ARENA_KNOTS, NJODE_ARENA_WORDS = 8 };
+size_t njode_batch_arena_bytes(const NjodeDesc* desc, int64_t B, int64_t N, int64_t total_slots, int64_t* layout);
+size_t njode_batch_scratch_bytes(const NjodeDesc* desc, int64_t B, int64_t N);
+int njode_forward_batch(const NjodeDesc* desc, const float* params, const float* times, const float* values,
+                        const int64_t* obs_offsets, int64_t B, int64_t N,
+                        void* arena, size_t arena_bytes, int32_t want_ckpt, float* ckpt, int64_t ckpt_floats,
+                        void* scratch, size_t scratch_bytes, int64_t* header_host,
+                        float* preds, float* preds_before, void* stream);
 
 /* ---- loss: value and gradient w.r.t. preds / preds_before in one pass --------------------------
  * loss_out: device float[1].  grad_* may be NULL (value only).  traj_scale = 1/B_global so that

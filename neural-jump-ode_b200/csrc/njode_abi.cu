@@ -339,6 +339,72 @@ extern "C" int njode_forward(const NjodeDesc* desc, const float* params, const f
   return njode_generic_forward(a, st);
 }
 
+// ------------------------------------------------------------------------------------------------
+// one call for an un-cached batch (see include/njode.h)
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t njode_batch_arena_bytes(const NjodeDesc* desc, int64_t B, int64_t N, int64_t total_slots, int64_t* layout) {
+  (void)B;
+  const int tile_rows = njode_tile_rows(desc);
+  const int64_t n_tiles = njode_num_tiles(desc, N);
+  if (tile_rows < 1 || n_tiles < 0 || total_slots < 0) return 0;
+  size_t o = 0;
+  int64_t lay[NJODE_ARENA_WORDS] = {0};
+  auto take = [&](int word, size_t bytes) { lay[word] = (int64_t)o; o += njode_align_up(bytes > 0 ? bytes : 4, 256); };
+  take(NJODE_ARENA_KENC, (size_t)N * sizeof(int32_t));
+  take(NJODE_ARENA_PERM, (size_t)n_tiles * tile_rows * sizeof(int32_t));
+  take(NJODE_ARENA_TILE_KMAX, (size_t)n_tiles * sizeof(int32_t));
+  take(NJODE_ARENA_TILE_SLOT_OFF, (size_t)(n_tiles + 1) * sizeof(int64_t));
+  take(NJODE_ARENA_HEADER, NJODE_HDR_WORDS * sizeof(int64_t));
+  take(NJODE_ARENA_KNOTS, (size_t)total_slots * tile_rows * sizeof(float));
+  if (layout) memcpy(layout, lay, sizeof(lay));
+  return o;
+}
+
+extern "C" size_t njode_batch_scratch_bytes(const NjodeDesc* desc, int64_t B, int64_t N) {
+  const int tile_rows = njode_tile_rows(desc);
+  if (tile_rows < 1) return 0;
+  return njode_align_up(njode_schedule_workspace_bytes(B, N, tile_rows), 256) + njode_align_up(njode_forward_workspace_bytes(desc), 256);
+}
+
+extern "C" int njode_forward_batch(const NjodeDesc* desc, const float* params, const float* times, const float* values,
+                                   const int64_t* obs_offsets, int64_t B, int64_t N,
+                                   void* arena, size_t arena_bytes, int32_t want_ckpt, float* ckpt, int64_t ckpt_floats,
+                                   void* scratch, size_t scratch_bytes, int64_t* header_host,
+                                   float* preds, float* preds_before, void* stream) {
+  const int tile_rows = njode_tile_rows(desc);
+  if (tile_rows < 1) return NJODE_EINVAL;                      // (njode_tile_rows set the error text)
+  if (!arena || !scratch || !header_host) NJODE_FAIL(NJODE_EINVAL, "njode_forward_batch: null arena / scratch / header_host");
+  int64_t lay[NJODE_ARENA_WORDS];
+  const size_t fixed = njode_batch_arena_bytes(desc, B, N, 0, lay);
+  if (arena_bytes < fixed) NJODE_FAIL(NJODE_EWORKSPACE, "njode_forward_batch: arena smaller than its size-independent part (njode_batch_arena_bytes(..., 0))");
+  if (scratch_bytes < njode_batch_scratch_bytes(desc, B, N)) NJODE_FAIL(NJODE_EWORKSPACE, "njode_forward_batch: scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* base = (char*)arena;
+  int32_t* kenc = (int32_t*)(base + lay[NJODE_ARENA_KENC]);
+  int32_t* perm = (int32_t*)(base + lay[NJODE_ARENA_PERM]);
+  int32_t* tile_kmax = (int32_t*)(base + lay[NJODE_ARENA_TILE_KMAX]);
+  int64_t* tile_slot_off = (int64_t*)(base + lay[NJODE_ARENA_TILE_SLOT_OFF]);
+  int64_t* header = (int64_t*)(base + lay[NJODE_ARENA_HEADER]);
+  float* knots = (float*)(base + lay[NJODE_ARENA_KNOTS]);
+  const size_t sched_ws = njode_align_up(njode_schedule_workspace_bytes(B, N, tile_rows), 256);
+  int rc = njode_schedule_build(desc, times, obs_offsets, B, N, tile_rows, kenc, perm, tile_kmax, tile_slot_off, header,
+                                scratch, sched_ws, stream);
+  if (rc) return rc;
+  NJODE_CUDA_OK(cudaMemcpyAsync(header_host, header, NJODE_HDR_WORDS * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  NJODE_CUDA_OK(cudaStreamSynchronize(st));
+  const int64_t total_slots = header_host[NJODE_HDR_TOTAL_SLOTS];
+  const int64_t n_tiles = njode_num_tiles(desc, N);
+  const int S = desc->shared_network ? 1 : desc->num_moments;
+  const int64_t need_ckpt = want_ckpt ? (int64_t)S * total_slots * tile_rows * njode_ckpt_row_floats(desc) : 0;
+  if (arena_bytes < njode_batch_arena_bytes(desc, B, N, total_slots, nullptr) || (want_ckpt && (ckpt_floats < need_ckpt || (!ckpt && need_ckpt > 0))))
+    NJODE_FAIL(NJODE_ECAPACITY, "njode_forward_batch: this batch has %lld checkpoint slots; arena / ckpt are too small for it", (long long)total_slots);
+  rc = njode_schedule_knots(times, kenc, perm, tile_kmax, tile_slot_off, N, n_tiles, tile_rows, desc, knots, stream);
+  if (rc) return rc;
+  return njode_forward(desc, params, times, values, obs_offsets, B, N, kenc, perm, tile_kmax, tile_slot_off, knots, n_tiles,
+                       total_slots, tile_rows, preds, preds_before, want_ckpt ? ckpt : nullptr,
+                       (char*)scratch + sched_ws, scratch_bytes - sched_ws, stream);
+}
+
 extern "C" int njode_backward(const NjodeDesc* desc, const float* params, const float* times, const float* values,
                               const int64_t* obs_offsets, int64_t B, int64_t N,
                               const int32_t* kenc, const int32_t* perm, const int32_t* tile_kmax,

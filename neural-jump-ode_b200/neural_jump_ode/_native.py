@@ -5,6 +5,7 @@ import of the hot path fails loudly -- there is no CPU or eager fallback.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 
@@ -20,6 +21,8 @@ SCALE = {"identity": 0, "none": 0, "tanh": 1, "sigmoid": 2}
 VAR = {"direct": 0, "second_moment": 1}
 IMPL = {"auto": 0, "generic": 1, "tiled": 2, "rowtile": 3}
 HDR_TOTAL_STEPS, HDR_TOTAL_SLOTS, HDR_NUM_TILES, HDR_KMAX, HDR_WORDS = 0, 1, 2, 3, 8
+ARENA_KENC, ARENA_PERM, ARENA_TILE_KMAX, ARENA_TILE_SLOT_OFF, ARENA_HEADER, ARENA_KNOTS, ARENA_WORDS = 0, 1, 2, 3, 4, 5, 8
+EINVAL, ECUDA, EWORKSPACE, ECAPACITY = -1, -2, -3, -4
 
 
 class NjodeDesc(C.Structure):
@@ -56,6 +59,9 @@ SIGNATURES = {
     "njode_forward_workspace_bytes": (_SZ, [_DESC]),
     "njode_forward": (C.c_int, [_DESC, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _I64, _I64, _I32,
                                 _P, _P, _P, _P, _SZ, _P]),
+    "njode_batch_arena_bytes": (_SZ, [_DESC, _I64, _I64, _I64, _P]),
+    "njode_batch_scratch_bytes": (_SZ, [_DESC, _I64, _I64]),
+    "njode_forward_batch": (C.c_int, [_DESC, _P, _P, _P, _P, _I64, _I64, _P, _SZ, _I32, _P, _I64, _P, _SZ, _P, _P, _P, _P]),
     "njode_loss_workspace_bytes": (_SZ, [_I64]),
     "njode_loss": (C.c_int, [_LDESC, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _F, _P, _P, _P, _P, _SZ, _P]),
     "njode_backward_workspace_bytes": (_SZ, [_DESC, _I64]),
@@ -69,7 +75,7 @@ SIGNATURES = {
 }
 
 # kernels launched by each ABI call (bench.py's gpu_launches claim): name -> count
-KERNELS_PER_CALL = {"njode_schedule_build": 5, "njode_schedule_knots": 1, "njode_forward": 2, "njode_loss": 2,
+KERNELS_PER_CALL = {"njode_schedule_build": 5, "njode_schedule_knots": 1, "njode_forward": 2, "njode_forward_batch": 8, "njode_loss": 2,
                     "njode_backward": 3, "njode_adam_step": 1}
 launch_count = 0
 
@@ -113,6 +119,24 @@ def check(rc, what):
     if rc != 0:
         msg = load().njode_last_error().decode(errors="replace")
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+_NULLCTX = contextlib.nullcontext()
+
+
+def on_device(dev):
+    """``torch.cuda.device(dev)`` when dev is not current, else nothing (the context manager costs ~8 us per use)."""
+    import torch
+    return _NULLCTX if dev.index is None or torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
+
+
+def current_stream(dev):
+    """Raw handle of torch's current stream on dev."""
+    import torch
+    try:
+        return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device() if dev.index is None else dev.index)
+    except AttributeError:                  # private API moved: the public (slower) one
+        return torch.cuda.current_stream(dev).cuda_stream
 
 
 def ptr(t):

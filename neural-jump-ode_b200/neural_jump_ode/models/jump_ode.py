@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from .. import _native as nat
-from ..packed import PackedBatch, PredList
+from ..packed import PackedBatch, PredList, Schedule, pinned_header
 
 # name -> module class; anything else silently means ReLU, as in the reference (jump_ode.py:6-13, :18)
 ACTIVATION_FUNCTIONS = {
@@ -111,59 +111,95 @@ class OutputNN(nn.Module):
 # ------------------------------------------------------------------------------------------------
 
 class _SweepFunction(torch.autograd.Function):
-    """preds, preds_before = sweep(batch; params).  Forward = ``njode_forward`` (writes per-step
-    hidden-state checkpoints when a gradient will be needed), backward = ``njode_backward``."""
+    """preds, preds_before = sweep(batch; params).  Forward = ``njode_forward`` on a batch whose schedule is cached,
+    ``njode_forward_batch`` (schedule + knots + sweep in one call) on a new one; per-step hidden-state checkpoints
+    are written when a gradient will be needed.  Backward = ``njode_backward``."""
 
     @staticmethod
-    def forward(ctx, desc, batch: PackedBatch, sched, want_grad: bool, dp_group, *params):
+    def forward(ctx, model, desc, batch: PackedBatch, want_grad: bool, *params):
         lib = nat.load()
         dev = batch.device
         N, B = batch.N, batch.B
-        d_y, M, H = desc.d_y, desc.num_moments, desc.hidden
+        d_y, M = desc.d_y, desc.num_moments
         S = 1 if desc.shared_network else M
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            flat = torch.cat([p.detach().reshape(-1) for p in params]).float()
-            preds = torch.empty((N, d_y, M), dtype=torch.float32, device=dev)
-            before = torch.empty((N, d_y, M), dtype=torch.float32, device=dev)
+        tile_rows = lib.njode_tile_rows(desc)
+        n_tiles = lib.njode_num_tiles(desc, N)
+        row_floats = lib.njode_ckpt_row_floats(desc)
+        if tile_rows < 1 or n_tiles < 0 or row_floats < 0:
+            raise RuntimeError("NeuralJumpODE: " + lib.njode_last_error().decode(errors="replace"))
+        key = batch.schedule_key(desc, tile_rows, n_tiles)
+        sched = batch._schedules.get(key)
+        with nat.on_device(dev):
+            stream = nat.current_stream(dev)
+            flat = model._flat_view(params)
+            out = torch.empty((2, N, d_y, M), dtype=torch.float32, device=dev)
+            preds, before = out[0], out[1]
             ckpt = None
-            if want_grad:
-                row_floats = lib.njode_ckpt_row_floats(desc)
-                if row_floats < 0:
-                    raise RuntimeError("njode_ckpt_row_floats: " + lib.njode_last_error().decode(errors="replace"))
-                ckpt = torch.empty(S * sched.total_slots * sched.tile_rows * row_floats, dtype=torch.float32, device=dev)
-            ws_bytes = lib.njode_forward_workspace_bytes(desc)
-            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
-            nat.check(lib.njode_forward(desc, nat.ptr(flat), nat.ptr(batch.times), nat.ptr(batch.values),
-                                        nat.ptr(batch.offsets), B, N, nat.ptr(sched.kenc), nat.ptr(sched.perm),
-                                        nat.ptr(sched.tile_kmax), nat.ptr(sched.tile_slot_off), nat.ptr(sched.knots),
-                                        sched.n_tiles, sched.total_slots, sched.tile_rows,
-                                        nat.ptr(preds), nat.ptr(before), nat.ptr(ckpt), nat.ptr(ws), ws_bytes, stream),
-                      "njode_forward")
+            if sched is not None:
+                if want_grad:
+                    ckpt = torch.empty(S * sched.total_slots * tile_rows * row_floats, dtype=torch.float32, device=dev)
+                ws_bytes = lib.njode_forward_workspace_bytes(desc)
+                ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+                nat.check(lib.njode_forward(desc, nat.ptr(flat), nat.ptr(batch.times), nat.ptr(batch.values),
+                                            nat.ptr(batch.offsets), B, N, *sched.ptrs,
+                                            n_tiles, sched.total_slots, tile_rows,
+                                            nat.ptr(preds), nat.ptr(before), nat.ptr(ckpt), nat.ptr(ws), ws_bytes, stream),
+                          "njode_forward")
+            else:
+                # new batch: everything is sized from a guess of its checkpoint slot count (exact when a batch of
+                # this shape was seen before) so that no Python runs between the schedule's host sync and the sweep
+                slots = model._guess_slots(N, B, n_tiles)
+                scratch_bytes = lib.njode_batch_scratch_bytes(desc, B, N)
+                scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
+                host = pinned_header(dev)
+                layout = (nat.C.c_int64 * nat.ARENA_WORDS)()
+                for attempt in (0, 1):
+                    arena_bytes = lib.njode_batch_arena_bytes(desc, B, N, slots, layout)
+                    arena = torch.empty(arena_bytes, dtype=torch.uint8, device=dev)
+                    ckpt_floats = S * slots * tile_rows * row_floats if want_grad else 0
+                    ckpt = torch.empty(max(ckpt_floats, 1), dtype=torch.float32, device=dev) if want_grad else None
+                    rc = lib.njode_forward_batch(desc, nat.ptr(flat), nat.ptr(batch.times), nat.ptr(batch.values),
+                                                 nat.ptr(batch.offsets), B, N, nat.ptr(arena), arena_bytes,
+                                                 1 if want_grad else 0, nat.ptr(ckpt), ckpt_floats,
+                                                 nat.ptr(scratch), scratch_bytes, host.data_ptr(),
+                                                 nat.ptr(preds), nat.ptr(before), stream)
+                    if rc == nat.ECAPACITY and attempt == 0:
+                        arena = ckpt = None
+                        slots = int(host[nat.HDR_TOTAL_SLOTS])     # the schedule is known now: size exactly, run again
+                        continue
+                    nat.check(rc, "njode_forward_batch")
+                    break
+                sched = Schedule(arena, layout, N, tile_rows, n_tiles, host.tolist())
+                model._note_slots(N, B, n_tiles, sched.total_slots)
+                batch._schedules[key] = sched
         ctx.desc, ctx.batch, ctx.sched = desc, batch, sched
-        ctx.dp_group = dp_group
+        ctx.dp_group = model._dp_group
         ctx.shapes = [p.shape for p in params]
         ctx.flat, ctx.ckpt = flat, ckpt
+        ctx.versions = sum(p._version for p in params)
+        ctx.params = params
         return preds, before
 
     @staticmethod
     def backward(ctx, g_preds, g_before):
         if ctx.ckpt is None:
             raise RuntimeError("NeuralJumpODE: backward requested but the forward sweep ran without checkpoints")
+        if sum(p._version for p in ctx.params) != ctx.versions:
+            raise RuntimeError("NeuralJumpODE: a parameter was modified in place between the forward sweep and its "
+                               "backward (the reverse sweep reads the parameters where they live)")
         lib = nat.load()
         desc, batch, sched = ctx.desc, ctx.batch, ctx.sched
         dev = batch.device
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
+        with nat.on_device(dev):
+            stream = nat.current_stream(dev)
             g_preds = g_preds.contiguous().float()
             g_before = g_before.contiguous().float()
             grad_flat = torch.empty_like(ctx.flat)
             ws_bytes = lib.njode_backward_workspace_bytes(desc, sched.n_tiles)
             ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
             nat.check(lib.njode_backward(desc, nat.ptr(ctx.flat), nat.ptr(batch.times), nat.ptr(batch.values),
-                                         nat.ptr(batch.offsets), batch.B, batch.N, nat.ptr(sched.kenc),
-                                         nat.ptr(sched.perm), nat.ptr(sched.tile_kmax), nat.ptr(sched.tile_slot_off),
-                                         nat.ptr(sched.knots), sched.n_tiles, sched.total_slots, sched.tile_rows,
+                                         nat.ptr(batch.offsets), batch.B, batch.N, *sched.ptrs,
+                                         sched.n_tiles, sched.total_slots, sched.tile_rows,
                                          nat.ptr(g_preds), nat.ptr(g_before), nat.ptr(ctx.ckpt), nat.ptr(grad_flat),
                                          nat.ptr(ws), ws_bytes, stream), "njode_backward")
         ctx.ckpt = None     # checkpoints are the big buffer: release them as soon as they are consumed
@@ -174,12 +210,8 @@ class _SweepFunction(torch.autograd.Function):
             dist.all_reduce(grad_flat, op=dist.ReduceOp.SUM, group=None if ctx.dp_group is True else ctx.dp_group)
         # Stacks of moments >= 2 get an all-zero gradient from nj_ode_loss (jump_ode.py:328-378); the
         # reference reports zero tensors for them too (torch.stack backward), so nothing is special-cased.
-        grads, o = [], 0
-        for shp in ctx.shapes:
-            n = shp.numel()
-            grads.append(grad_flat[o:o + n].view(shp))
-            o += n
-        return (None, None, None, None, None, *grads)
+        grads = [g.view(shp) for g, shp in zip(grad_flat.split([shp.numel() for shp in ctx.shapes]), ctx.shapes)]
+        return (None, None, None, None, *grads)
 
 
 class _LossFunction(torch.autograd.Function):
@@ -191,27 +223,28 @@ class _LossFunction(torch.autograd.Function):
         lib = nat.load()
         dev = preds.device
         N, d, M = preds.shape
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
+        with nat.on_device(dev):
+            stream = nat.current_stream(dev)
             preds_c = preds.detach().contiguous().float()
             before_c = before.detach().contiguous().float()
             loss = torch.empty((), dtype=torch.float32, device=dev)
-            gp = torch.empty_like(preds_c) if want_grad else None
-            gb = torch.empty_like(before_c) if want_grad else None
+            g = torch.empty((2, N, d, M), dtype=torch.float32, device=dev) if want_grad else None   # (d preds, d preds_before)
             ws_bytes = lib.njode_loss_workspace_bytes(batch.B)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             nat.check(lib.njode_loss(ldesc, nat.ptr(batch.values), nat.ptr(preds_c), nat.ptr(before_c),
                                      nat.ptr(batch.offsets), batch.B, N, d, M, float(traj_scale),
-                                     nat.ptr(loss), nat.ptr(gp), nat.ptr(gb), nat.ptr(ws), ws_bytes, stream),
+                                     nat.ptr(loss), nat.ptr(g[0]) if want_grad else None,
+                                     nat.ptr(g[1]) if want_grad else None, nat.ptr(ws), ws_bytes, stream),
                       "njode_loss")
-        ctx.gp, ctx.gb = gp, gb
+        ctx.g = g
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        if ctx.gp is None:
+        if ctx.g is None:
             raise RuntimeError("nj_ode_loss: backward requested but gradients were not computed")
-        return None, None, None, None, ctx.gp * g, ctx.gb * g
+        scaled = ctx.g * g                      # one launch for both gradients
+        return None, None, None, None, scaled[0], scaled[1]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -258,6 +291,8 @@ class NeuralJumpODE(nn.Module):
         self.dropout_rate = dropout_rate
         self.kernel_impl = "auto"                 # 'auto' | 'generic' | 'rowtile' | 'tiled' (testing / profiling knob)
         self._dp_group = None                     # see enable_data_parallel
+        self.auto_flatten = True                  # see flatten_parameters
+        self._slots_memo, self._slots_per_tile = {}, 0.0
 
     def enable_data_parallel(self, group=True):
         """Sum the parameter gradients over the ranks of ``group`` (``True`` = the default process group, ``None``
@@ -266,6 +301,61 @@ class NeuralJumpODE(nn.Module):
         ``nj_ode_loss(..., traj_scale=1 / B_global)`` (see ``neural_jump_ode.sharding``)."""
         self._dp_group = group
         return self
+
+    # -- parameters as one flat buffer ---------------------------------------------------------------
+    def flatten_parameters(self):
+        """Re-home every parameter as a view of ONE flat float32 buffer in the C-ABI's order (values, ``Parameter``
+        objects and ``state_dict`` are unchanged -- the ``nn.RNN.flatten_parameters`` idea): the sweeps then read
+        the parameters where they live instead of gathering 6 * (L + 1) tensors per call.  Done automatically by the
+        first sweep while every parameter still owns its storage (``auto_flatten = False`` to opt out), redone after
+        ``.to()``.  ``FlatAdam`` adopts this buffer when it is built afterwards."""
+        params = self.flat_parameters()
+        dev = params[0].device
+        total = sum(p.numel() for p in params)
+        flat = torch.empty(total, dtype=torch.float32, device=dev)
+        o = 0
+        with torch.no_grad():
+            for p in params:
+                k = p.numel()
+                flat[o:o + k].copy_(p.detach().reshape(-1))
+                p.data = flat[o:o + k].view(p.shape)
+                o += k
+        return self
+
+    def _flat_view(self, params) -> torch.Tensor:
+        """The parameters as one flat float32 tensor: a zero-copy view when they sit back to back in one storage
+        (``flatten_parameters`` / ``FlatAdam``), else a gathered copy."""
+        for attempt in (0, 1):
+            p0 = params[0]
+            addr, total, ok = p0.data_ptr(), 0, True
+            for p in params:
+                if p.data_ptr() != addr + 4 * total or not p.is_contiguous():
+                    ok = False
+                    break
+                total += p.numel()
+            if ok and p0.untyped_storage().nbytes() >= (p0.storage_offset() + total) * 4:
+                return p0.detach().as_strided((total,), (1,), p0.storage_offset())
+            # (never re-home parameters that are views of someone else's buffer, e.g. a FlatAdam built first)
+            if attempt == 0 and self.auto_flatten and all(
+                    p.is_leaf and p.storage_offset() == 0 and p.untyped_storage().nbytes() == 4 * p.numel() for p in params):
+                self.flatten_parameters()
+                continue
+            break
+        return torch.cat([p.detach().reshape(-1) for p in params]).float()
+
+    # -- checkpoint-slot guesses for batches whose schedule is not known yet (njode_forward_batch) -------
+    def _guess_slots(self, N, B, n_tiles) -> int:
+        exact = self._slots_memo.get((N, B))
+        if exact is not None:
+            return exact
+        return int(self._slots_per_tile * n_tiles * 1.03) + 2 if self._slots_per_tile > 0 else 0
+
+    def _note_slots(self, N, B, n_tiles, total_slots):
+        if len(self._slots_memo) > 256:
+            self._slots_memo.clear()
+        self._slots_memo[(N, B)] = total_slots
+        if n_tiles > 0:
+            self._slots_per_tile = max(self._slots_per_tile, total_slots / n_tiles)
 
     # -- reference-compatible small-tensor API (plotting, tests) ---------------------------------
     def euler_step(self, h_list, x_last, t_last, t_next):
@@ -328,9 +418,8 @@ class NeuralJumpODE(nn.Module):
         if batch.values.shape[1] != self.input_dim:
             raise ValueError(f"values have d_x={batch.values.shape[1]}, model expects {self.input_dim}")
         desc = self.descriptor()
-        sched = batch.schedule(desc)
         want_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        return _SweepFunction.apply(desc, batch, sched, want_grad, self._dp_group, *params)
+        return _SweepFunction.apply(self, desc, batch, want_grad, *params)
 
     def forward(self, batch_times, batch_values=None):
         """batch_times / batch_values: lists of (n_i,) / (n_i, d_x) tensors (reference jump_ode.py:218-233),

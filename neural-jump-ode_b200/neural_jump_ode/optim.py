@@ -39,16 +39,38 @@ class FlatAdam(torch.optim.Optimizer):
                 raise RuntimeError("FlatAdam needs float32 parameters on one CUDA device (no CPU fallback); "
                                    "build the optimizer after model.to('cuda')")
             n = sum(p.numel() for p in ps)
-            flat = torch.empty(n, dtype=torch.float32, device=dev)
-            o = 0
-            with torch.no_grad():
-                for p in ps:
-                    k = p.numel()
-                    flat[o:o + k].copy_(p.detach().reshape(-1))
-                    p.data = flat[o:o + k].view(p.shape)          # the parameter now lives in the flat buffer
-                    o += k
+            flat = self._adopt(ps, n)
+            if flat is not None:
+                # already tiling one storage (model.flatten_parameters()): step on that buffer, in its order -- which
+                # is also the order of the reverse sweep's flat gradient, so nothing is ever gathered
+                ps = sorted(ps, key=lambda p: p.data_ptr())
+            else:
+                flat = torch.empty(n, dtype=torch.float32, device=dev)
+                o = 0
+                with torch.no_grad():
+                    for p in ps:
+                        k = p.numel()
+                        flat[o:o + k].copy_(p.detach().reshape(-1))
+                        p.data = flat[o:o + k].view(p.shape)          # the parameter now lives in the flat buffer
+                        o += k
             self._flat.append(dict(params=ps, flat=flat, grad=torch.zeros_like(flat), exp_avg=torch.zeros_like(flat),
                                    exp_avg_sq=torch.zeros_like(flat), step=0))
+
+    @staticmethod
+    def _adopt(ps, n):
+        """The flat tensor the parameters already tile (in some order, back to back in one storage), or None."""
+        if any(not p.is_contiguous() for p in ps):
+            return None
+        order = sorted(ps, key=lambda p: p.data_ptr())
+        first = order[0]
+        addr = first.data_ptr()
+        for p in order:
+            if p.data_ptr() != addr:
+                return None
+            addr += 4 * p.numel()
+        if first.untyped_storage().nbytes() < (first.storage_offset() + n) * 4:
+            return None
+        return first.detach().as_strided((n,), (1,), first.storage_offset())
 
     def _gather_grads(self, st):
         """The flat gradient.  The reverse sweep hands out views of one flat buffer in parameter order: if the

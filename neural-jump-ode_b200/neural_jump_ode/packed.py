@@ -19,11 +19,55 @@ class Schedule:
     """Device-resident Euler step schedule of one packed batch for one (dt, tile_rows).
 
     Built by ``njode_schedule_build`` / ``njode_schedule_knots`` (jump_ode.py:188-203 reproduced in
-    float32 on the device).  ``total_steps`` is the number of trajectory-ODE-steps of the batch.
+    float32 on the device), or by ``njode_forward_batch`` together with the first forward sweep.
+    ``total_steps`` is the number of trajectory-ODE-steps of the batch.  The arrays live in one arena
+    (layout: ``njode_batch_arena_bytes``); ``kenc`` / ``perm`` / ``tile_kmax`` / ``tile_slot_off`` /
+    ``knots`` are tensor views of it, made on first use -- the kernels only need ``ptrs``.
     """
 
-    __slots__ = ("kenc", "perm", "tile_kmax", "tile_slot_off", "knots", "tile_rows", "n_tiles",
-                 "total_steps", "total_slots", "kmax")
+    _FIELDS = {"kenc": (nat.ARENA_KENC, torch.int32), "perm": (nat.ARENA_PERM, torch.int32),
+               "tile_kmax": (nat.ARENA_TILE_KMAX, torch.int32), "tile_slot_off": (nat.ARENA_TILE_SLOT_OFF, torch.int64),
+               "knots": (nat.ARENA_KNOTS, torch.float32)}
+
+    def __init__(self, arena, layout, N, tile_rows, n_tiles, header, knots_buf=None):
+        self._arena, self._layout, self._N = arena, list(layout), N
+        self._knots_buf = knots_buf            # separate tensor when the arena was sized without knots
+        self.tile_rows, self.n_tiles = tile_rows, n_tiles
+        self.total_steps, self.total_slots = header[nat.HDR_TOTAL_STEPS], header[nat.HDR_TOTAL_SLOTS]
+        self.kmax = header[nat.HDR_KMAX]
+        base = arena.data_ptr()
+        knots_ptr = knots_buf.data_ptr() if knots_buf is not None else base + layout[nat.ARENA_KNOTS]
+        # (kenc, perm, tile_kmax, tile_slot_off, knots) as the C-ABI takes them
+        self.ptrs = tuple(nat.C.c_void_p(base + layout[w]) for w in (nat.ARENA_KENC, nat.ARENA_PERM, nat.ARENA_TILE_KMAX,
+                                                                    nat.ARENA_TILE_SLOT_OFF)) + (nat.C.c_void_p(knots_ptr),)
+
+    def __getattr__(self, name):               # only reached for attributes not set yet: the lazy views
+        f = Schedule._FIELDS.get(name)
+        if f is None:
+            raise AttributeError(name)
+        word, dtype = f
+        count = {"kenc": max(self._N, 1), "perm": max(self.n_tiles * self.tile_rows, 1), "tile_kmax": max(self.n_tiles, 1),
+                 "tile_slot_off": self.n_tiles + 1, "knots": max(self.total_slots * self.tile_rows, 1)}[name]
+        item = 8 if dtype == torch.int64 else 4
+        if name == "knots" and self._knots_buf is not None:
+            t = self._knots_buf
+        else:
+            o = self._layout[word]
+            t = self._arena[o:o + count * item].view(dtype)
+        setattr(self, name, t)
+        return t
+
+
+_HDR_HOST = {}
+
+
+def pinned_header(dev):
+    """A pinned int64[HDR_WORDS] host buffer per device for the schedule header read-back (read synchronously
+    right after the call that fills it, so one buffer is enough)."""
+    h = _HDR_HOST.get(dev)
+    if h is None:
+        h = _HDR_HOST[dev] = torch.empty(nat.HDR_WORDS, dtype=torch.int64).pin_memory()
+    return h
 
 
 class PackedBatch:
@@ -93,7 +137,10 @@ class PackedBatch:
         tile_rows = lib.njode_tile_rows(desc)
         if tile_rows < 1:
             nat.check(-1, "njode_tile_rows")
-        key = (bool(desc.has_dt), float(desc.dt), int(tile_rows))
+        n_tiles = lib.njode_num_tiles(desc, self.N)   # tiles may be partially filled (small batches, tcgen05 flavour)
+        if n_tiles < 0:
+            nat.check(-1, "njode_num_tiles")
+        key = self.schedule_key(desc, tile_rows, n_tiles)
         s = self._schedules.get(key)
         if s is not None:
             return s
@@ -102,32 +149,34 @@ class PackedBatch:
                                "move the model and the batch to a CUDA device")
         dev = self.device
         N, B = self.N, self.B
-        n_tiles = lib.njode_num_tiles(desc, N)        # tiles may be partially filled (small batches, tcgen05 flavour)
-        if n_tiles < 0:
-            nat.check(-1, "njode_num_tiles")
-        s = Schedule()
-        s.tile_rows, s.n_tiles = tile_rows, n_tiles
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            s.kenc = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
-            s.perm = torch.empty(max(n_tiles * tile_rows, 1), dtype=torch.int32, device=dev)
-            s.tile_kmax = torch.empty(max(n_tiles, 1), dtype=torch.int32, device=dev)
-            s.tile_slot_off = torch.empty(n_tiles + 1, dtype=torch.int64, device=dev)
-            header = torch.empty(nat.HDR_WORDS, dtype=torch.int64, device=dev)
+        with nat.on_device(dev):
+            stream = nat.current_stream(dev)
+            layout = (nat.C.c_int64 * nat.ARENA_WORDS)()
+            arena_bytes = lib.njode_batch_arena_bytes(desc, B, N, 0, layout)      # everything but the knots
+            arena = torch.empty(arena_bytes, dtype=torch.uint8, device=dev)
+            base = arena.data_ptr()
+            at = lambda w: nat.C.c_void_p(base + layout[w])
             ws_bytes = lib.njode_schedule_workspace_bytes(B, N, tile_rows)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             nat.check(lib.njode_schedule_build(desc, nat.ptr(self.times), nat.ptr(self.offsets), B, N, tile_rows,
-                                               nat.ptr(s.kenc), nat.ptr(s.perm), nat.ptr(s.tile_kmax),
-                                               nat.ptr(s.tile_slot_off), nat.ptr(header), nat.ptr(ws), ws_bytes,
+                                               at(nat.ARENA_KENC), at(nat.ARENA_PERM), at(nat.ARENA_TILE_KMAX),
+                                               at(nat.ARENA_TILE_SLOT_OFF), at(nat.ARENA_HEADER), nat.ptr(ws), ws_bytes,
                                                stream), "njode_schedule_build")
-            hdr = header.cpu().tolist()     # the one host sync of the schedule: sizes the checkpoints
-            s.total_steps, s.total_slots, s.kmax = hdr[nat.HDR_TOTAL_STEPS], hdr[nat.HDR_TOTAL_SLOTS], hdr[nat.HDR_KMAX]
-            s.knots = torch.empty(max(s.total_slots * tile_rows, 1), dtype=torch.float32, device=dev)
-            nat.check(lib.njode_schedule_knots(nat.ptr(self.times), nat.ptr(s.kenc), nat.ptr(s.perm),
-                                               nat.ptr(s.tile_kmax), nat.ptr(s.tile_slot_off), N, n_tiles, tile_rows,
-                                               desc, nat.ptr(s.knots), stream), "njode_schedule_knots")
+            host = pinned_header(dev)
+            host.copy_(arena[layout[nat.ARENA_HEADER]:layout[nat.ARENA_HEADER] + 8 * nat.HDR_WORDS].view(torch.int64),
+                       non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()   # the one host sync of the schedule: sizes the checkpoints
+            hdr = host.tolist()
+            knots = torch.empty(max(hdr[nat.HDR_TOTAL_SLOTS] * tile_rows, 1), dtype=torch.float32, device=dev)
+            s = Schedule(arena, layout, N, tile_rows, n_tiles, hdr, knots_buf=knots)
+            nat.check(lib.njode_schedule_knots(nat.ptr(self.times), *s.ptrs[:4], N, n_tiles, tile_rows,
+                                               desc, s.ptrs[4], stream), "njode_schedule_knots")
         self._schedules[key] = s
         return s
+
+    @staticmethod
+    def schedule_key(desc, tile_rows, n_tiles):
+        return (bool(desc.has_dt), float(desc.dt), int(tile_rows), int(n_tiles))
 
     def step_counts(self, desc) -> torch.Tensor:
         """Per-observation Euler step counts (int32, device); the last observation of a trajectory has 0."""

@@ -284,6 +284,99 @@ def test_packed_path_equals_list_path_and_no_grad():
     assert torch.equal(y, p1[0]) and torch.equal(yb, b1[0])
 
 
+def _grads_of(model, batch, lk):
+    from neural_jump_ode import nj_ode_loss
+    model.zero_grad(set_to_none=True)
+    p, b = model.forward_packed(batch)
+    loss = nj_ode_loss(batch, None, p, b, **lk)
+    loss.backward()
+    return p.detach().clone(), b.detach().clone(), loss.item(), [q.grad.clone() for q in model.flat_parameters()]
+
+
+@pytest.mark.parametrize("hidden,shared", [(32, True), (32, False), (64, False)])
+def test_one_call_batch_path_equals_cached_schedule_path(hidden, shared):
+    """A batch seen for the first time goes through njode_forward_batch (schedule + knots + sweep in one call, buffers
+    sized from a guess); a batch whose schedule is cached goes through njode_forward.  Same bits either way --
+    also after the guess was too small (first call of a model; a later batch with longer gaps) and too large."""
+    from neural_jump_ode import NeuralJumpODE, PackedBatch
+    torch.manual_seed(5)
+    model = NeuralJumpODE(1, hidden, 1, dt_ode_step=0.01, num_moments=2, shared_network=shared).to(DEV)
+    lk = dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0])
+    desc = model.descriptor()
+    # batches with few / many steps per observation interval, in an order that makes the slot guess under- and overshoot
+    for seed, B, per_tile in [(1, 300, None), (2, 300, None), (3, 700, None), (4, 300, 1.0), (5, 50, 400.0), (5, 50, None)]:
+        bt, bv = _random_batch(B, seed=seed)
+        fresh = PackedBatch.from_lists(bt, bv, device=DEV)
+        assert not fresh._schedules
+        if per_tile is not None:                                # force the guess far below / above what the batch needs
+            model._slots_memo.clear()
+            model._slots_per_tile = per_tile
+        one = _grads_of(model, fresh, lk)                       # njode_forward_batch
+        assert len(fresh._schedules) == 1
+        again = _grads_of(model, fresh, lk)                     # cached schedule of the one-call path -> njode_forward
+        cached = PackedBatch.from_lists(bt, bv, device=DEV)
+        sched = cached.schedule(desc)                           # njode_schedule_build + njode_schedule_knots
+        two = _grads_of(model, cached, lk)
+        s1 = next(iter(fresh._schedules.values()))
+        assert (s1.total_steps, s1.total_slots, s1.kmax, s1.n_tiles) == (sched.total_steps, sched.total_slots, sched.kmax, sched.n_tiles)
+        for name in ("kenc", "perm", "tile_kmax", "tile_slot_off", "knots"):
+            assert torch.equal(getattr(s1, name), getattr(sched, name)), name
+        for other in (again, two):
+            assert torch.equal(one[0], other[0]) and torch.equal(one[1], other[1]) and one[2] == other[2]
+            for g1, g2 in zip(one[3], other[3]):
+                assert torch.equal(g1, g2)
+    with torch.no_grad():                                       # inference: no checkpoint buffer at all
+        bt, bv = _random_batch(64, seed=9)
+        f = PackedBatch.from_lists(bt, bv, device=DEV)
+        p1, b1 = model.forward_packed(f)
+        c = PackedBatch.from_lists(bt, bv, device=DEV)
+        c.schedule(desc)
+        p2, b2 = model.forward_packed(c)
+        assert torch.equal(p1, p2) and torch.equal(b1, b2)
+
+
+def test_flatten_parameters_keeps_the_module_intact():
+    """The sweeps read the parameters from one flat buffer (model.flatten_parameters, automatic): Parameter objects,
+    state_dict, torch optimizers and .to() keep working, and the flat view follows in-place updates."""
+    from neural_jump_ode import NeuralJumpODE, PackedBatch
+    torch.manual_seed(6)
+    model = NeuralJumpODE(1, 32, 1, dt_ode_step=0.01, num_moments=2).to(DEV)
+    ref = NeuralJumpODE(1, 32, 1, dt_ode_step=0.01, num_moments=2).to(DEV)
+    ref.load_state_dict(model.state_dict())
+    ref.auto_flatten = False                                   # gathers a copy of the parameters per call
+    ids = [id(p) for p in model.parameters()]
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    lk = dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0])
+    batch = PackedBatch.from_lists(*_random_batch(200, seed=3), device=DEV)
+    opt, opt_ref = torch.optim.Adam(model.parameters(), lr=1e-2), torch.optim.Adam(ref.parameters(), lr=1e-2)
+    for it in range(3):
+        a, b = _grads_of(model, batch, lk), _grads_of(ref, batch, lk)
+        assert a[2] == b[2] and all(torch.equal(x, y) for x, y in zip(a[3], b[3]))
+        opt.step(); opt_ref.step()
+    params = model.flat_parameters()
+    assert [id(p) for p in model.parameters()] == ids
+    assert all(p.data_ptr() == params[0].data_ptr() + 4 * sum(q.numel() for q in params[:i]) for i, p in enumerate(params))
+    assert set(model.state_dict()) == set(sd) and all(model.state_dict()[k].shape == v.shape for k, v in sd.items())
+    for (k, v), (k2, v2) in zip(model.state_dict().items(), ref.state_dict().items()):
+        assert k == k2 and torch.equal(v, v2)
+    model.load_state_dict(sd); ref.load_state_dict(sd)         # copies into the flat buffer
+    a, b = _grads_of(model, batch, lk), _grads_of(ref, batch, lk)
+    assert a[2] == b[2] and all(torch.equal(x, y) for x, y in zip(a[3], b[3]))
+    with torch.no_grad():
+        p, _ = model.forward_packed(batch)
+        params[0].add_(0.25)                                    # in-place update is seen without any re-gathering
+        p2, _ = model.forward_packed(batch)
+        assert not torch.equal(p, p2)
+    # a parameter modified between forward and backward is an error, as with stock autograd
+    from neural_jump_ode import nj_ode_loss
+    p, b = model.forward_packed(batch)
+    loss = nj_ode_loss(batch, None, p, b, **lk)
+    with torch.no_grad():
+        params[1].mul_(1.5)
+    with pytest.raises(RuntimeError, match="modified in place"):
+        loss.backward()
+
+
 def test_submodules_and_euler_step_agree_with_kernels():
     """plotting.py drives jump_nns / euler_step / output_nns directly; they must describe the same model."""
     from neural_jump_ode import NeuralJumpODE
@@ -330,15 +423,19 @@ def test_flat_adam_matches_torch_adam_on_a_training_run():
     btc, bvc = [t.to(DEV) for t in bt], [v.to(DEV) for v in bv]
     lk = dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0])
     models, opts = [], []
-    for flat in (False, True):
+    for flat in (False, True, "adopt"):
         torch.manual_seed(1)
         m = NeuralJumpODE(**mk).to(DEV)
         keys = list(m.state_dict().keys())
+        if flat == "adopt":
+            m.flatten_parameters()               # FlatAdam then steps on the model's own flat buffer, nothing is gathered
         o = FlatAdam(m.parameters(), lr=1e-2, weight_decay=5e-4) if flat else torch.optim.Adam(m.parameters(), lr=1e-2, weight_decay=5e-4)
+        if flat == "adopt":
+            assert o._flat[0]["flat"].data_ptr() == m.flat_parameters()[0].data_ptr()
         assert list(m.state_dict().keys()) == keys
         models.append(m)
         opts.append(o)
-    losses = [[], []]
+    losses = [[], [], []]
     for step in range(8):
         for i, (m, o) in enumerate(zip(models, opts)):
             o.zero_grad()
@@ -348,10 +445,17 @@ def test_flat_adam_matches_torch_adam_on_a_training_run():
             o.step()
             losses[i].append(loss.item())
     assert losses[0][-1] < losses[0][0]                               # it trains
-    for a, b in zip(losses[0], losses[1]):
-        assert abs(a - b) <= 1e-4 * abs(a)
-    for (k, pa), (_, pb) in zip(models[0].named_parameters(), models[1].named_parameters()):
-        assert rel_err(pb.detach().cpu(), pa.detach().cpu()) <= 1e-4, k
+    for other in (1, 2):
+        for a, b in zip(losses[0], losses[other]):
+            assert abs(a - b) <= 1e-4 * abs(a)
+        for (k, pa), (_, pb) in zip(models[0].named_parameters(), models[other].named_parameters()):
+            assert rel_err(pb.detach().cpu(), pa.detach().cpu()) <= 1e-4, k
+    # the adopted layout is the reverse sweep's own: its flat gradient is consumed in place
+    st = opts[2]._flat[0]
+    models[2].zero_grad(set_to_none=True)
+    p, b = models[2](btc, bvc)
+    nj_ode_loss(btc, bvc, p, b, **lk).backward()
+    assert opts[2]._gather_grads(st).data_ptr() == st["params"][0].grad.data_ptr()
 
 
 def test_error_paths():
