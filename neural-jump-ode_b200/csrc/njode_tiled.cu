@@ -223,10 +223,13 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
   const int worker = blockIdx.x / T.S, n_workers = gridDim.x / T.S;
   const float* p = a.params + (int64_t)s * T.stack_floats;
   const int dx = T.d_x, O = T.O, sc_kind = a.desc.input_scaling;
-  // checkpoints: [stack][slot][plane][row][32]; plane 0 = hidden state before the step of this slot (after the
-  // last step for the tile's final slot), plane 1 = hidden-layer activation z of that step (saves the reverse
-  // sweep the re-computation GEMM and its epilogue)
-  float* ckpt = a.ckpt ? a.ckpt + (int64_t)s * a.total_slots * (2 * R * H) : nullptr;
+  // checkpoints: [stack][slot][plane][column chunk c][row][8]; plane 0 = hidden state before the step of this slot
+  // (after the last step for the tile's final slot), plane 1 = hidden-layer activation z of that step (saves the
+  // reverse sweep the re-computation GEMM and its epilogue).  Chunk-major inside a plane: a warp (one c, 32 rows)
+  // stores / loads 1 KB contiguous = 8 full lines; row-major [row][32] made every 256-bit access of a warp touch 32
+  // different lines, and the LSU time of those (512 line visits per plane and CTA) delayed the shared-memory loads
+  // queued behind them on this latency-bound chain.
+  float* ckpt = a.ckpt ? a.ckpt + (int64_t)s * a.total_slots * (2 * R * H) + (c * R + row) * CW : nullptr;
 
   load_wtile(wt + (FW_ODE0 * 2) * WT_F, wt + (FW_ODE0 * 2 + 1) * WT_F, p + T.w_off[NET_ODE][0], H + dx + 2, false, NT);
   load_wtile(wt + (FW_ODE1 * 2) * WT_F, wt + (FW_ODE1 * 2 + 1) * WT_F, p + T.w_off[NET_ODE][1], H, false, NT);
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
     ld8(sp.b_jump1 + col0, cb);
 #pragma unroll
     for (int j = 0; j < 8; ++j) h[j] = act_fwd<ACT>(acc[j] + cb[j]);
-    if (ckpt) st8_stream(ckpt + ((slot0 + 0) * 2 * R + row) * H + col0, h);
+    if (ckpt) st8_stream(ckpt + (slot0 + 0) * (2 * R * H), h);
 
     // readout: y = out(h)                                           jump_ode.py:170 / :177, :205-212
     auto readout = [&](float* __restrict__ dst, int64_t obs, bool write) {
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
       ld8(sp.ext_ode0[dx + 1] + col0, cw);
 #pragma unroll
       for (int j = 0; j < 8; ++j) z[j] = act_fwd<ACT>(fmaf(cw[j], delta, z[j]));
-      if (ckpt) st8_stream(ckpt + (((slot0 + k) * 2 + 1) * R + row) * H + col0, z);
+      if (ckpt) st8_stream(ckpt + ((slot0 + k) * 2 + 1) * (R * H), z);
       gemm(z, FW_ODE1, acc);
       TR(32 + 8);
       if (k < K) {
@@ -371,7 +374,7 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) h[j] = fmaf(delta, acc[j] + cb[j], h[j]);
       }
-      if (ckpt) st8_stream(ckpt + ((slot0 + k + 1) * 2 * R + row) * H + col0, h);
+      if (ckpt) st8_stream(ckpt + (slot0 + k + 1) * (2 * R * H), h);
     }
     readout(a.preds_before, (int64_t)u + 1, u >= 0 && (ke & 1));
   }
@@ -627,7 +630,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
     const int u = a.perm[tile * R + row];
     const int ke = u >= 0 ? a.kenc[u] : 0;
     // this thread's slice of the tile's checkpoint / knot slots (32-bit offsets per step from here on)
-    const float* ck = ckpt + ((int64_t)a.tile_slot_off[tile] * 2 * R + row) * H + col0;
+    const float* ck = ckpt + (int64_t)a.tile_slot_off[tile] * (2 * R * H) + (c * R + row) * CW;
     const float* kn = a.knots + (int64_t)a.tile_slot_off[tile] * R + row;
     float xs[MAX_DX];
 #pragma unroll
