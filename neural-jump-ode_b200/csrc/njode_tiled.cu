@@ -108,10 +108,12 @@ __device__ __forceinline__ void load_small(SmallParams& sp, const ParamTable& T,
   }
 }
 
-// 8 consecutive floats (32-byte aligned) from shared / global memory
+// 8 consecutive floats (32-byte aligned) from SHARED memory.  Explicit ld.shared: through the struct reference the
+// compiler had lost the address space and emitted generic LD.E.128, which the LSU orders like a global access.
 __device__ __forceinline__ void ld8(const float* __restrict__ src, float (&v)[8]) {
-  const float4 q0 = reinterpret_cast<const float4*>(src)[0], q1 = reinterpret_cast<const float4*>(src)[1];
-  v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(src);
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a));
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(a));
 }
 // one 256-bit global load / store per thread for its 8 checkpoint floats (LDG.256 / STG.256 on sm_100): one L2
 // request per 32-byte sector instead of two, and no L1 allocation (the fills compete with the tensor core's
@@ -343,7 +345,9 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
     for (int k = 0; k < kmax; ++k) {
       const float tc = tn;
       tn = tn_ahead;
-      tn_ahead = ld_na(a.knots + (slot0 + (k + 2 <= kmax ? k + 2 : kmax)) * R + row);
+      // (lands in its own register and is moved into tn_ahead at the END of the step: assigned here, the compiler's
+      // register-rotation move followed the load directly and waited out the whole global-memory latency every step)
+      const float tn_loaded = ld_na(a.knots + (slot0 + (k + 2 <= kmax ? k + 2 : kmax)) * R + row);
       const float delta = __fsub_rn(tn, tc);
       TR(32 + 7);
 #pragma unroll
@@ -375,6 +379,7 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
         for (int j = 0; j < 8; ++j) h[j] = fmaf(delta, acc[j] + cb[j], h[j]);
       }
       if (ckpt) st8_stream(ckpt + (slot0 + k + 1) * (2 * R * H), h);
+      asm volatile("mov.f32 %0, %1;" : "=f"(tn_ahead) : "f"(tn_loaded));
     }
     readout(a.preds_before, (int64_t)u + 1, u >= 0 && (ke & 1));
   }
