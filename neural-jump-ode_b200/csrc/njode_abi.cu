@@ -1,6 +1,7 @@
 // njode_abi.cu -- extern "C" entry points of libnjode_b200.so (see include/njode.h).
 // Argument validation, flavour selection, weight re-layout and the deterministic reduction of the
 // per-CTA weight-gradient partial sums.  No torch headers, no persistent allocations.
+#include <cstdlib>
 #include <stdarg.h>
 #include <string.h>
 
@@ -157,12 +158,36 @@ int32_t njode_tile_units(const NjodeDesc* d, int64_t N) {
   return NJODE_TILED_TILE_ROWS;
 }
 
+TilePlan njode_tile_plan(const NjodeDesc* d, int64_t N) {
+  TilePlan p;
+  p.units = njode_tile_units(d, N);
+  p.units_small = p.units;
+  p.n_small = 0;
+  const char* why = nullptr;
+  if (pick_impl(d, &why) == NJODE_IMPL_TILED && p.units == NJODE_TILED_TILE_ROWS) {
+    const int S = d->shared_network ? 1 : d->num_moments;
+    const int64_t sms_per_stack = sm_count_abi() / S > 0 ? sm_count_abi() / S : 1;
+    const int64_t full_tiles = (N + p.units - 1) / p.units;
+    // up to ~8 full tiles per SM the longest tile is a large part of a sweep's time (default workload: 2.2 full
+    // tiles per SM, longest tile 78 steps against an average of 12 per CTA): one quarter tile per SM for the
+    // longest units.  Beyond that the sweeps are throughput-bound and the extra tile-steps only cost.
+    static const int tail = [] { const char* e = getenv("NJODE_TAIL_TILES"); return e ? atoi(e) : 1; }();   // (A/B knob)
+    if (tail && full_tiles <= 8 * sms_per_stack) {
+      p.units_small = NJODE_TILED_TILE_ROWS / 4;
+      p.n_small = sms_per_stack;
+      if (p.n_small * p.units_small > N) p.n_small = N / p.units_small;
+    }
+  }
+  const int64_t rest = N - p.n_small * p.units_small;
+  p.n_tiles = p.n_small + (rest + p.units - 1) / p.units;
+  return p;
+}
+
 extern "C" int64_t njode_num_tiles(const NjodeDesc* d, int64_t N) {
   const char* why = nullptr;
   if (!pick_impl(d, &why)) { njode_set_error("njode_num_tiles: %s", why); return -1; }
   if (N < 0) { njode_set_error("njode_num_tiles: negative size"); return -1; }
-  const int u = njode_tile_units(d, N);
-  return (N + u - 1) / u;
+  return njode_tile_plan(d, N).n_tiles;
 }
 
 extern "C" int64_t njode_ckpt_row_floats(const NjodeDesc* d) {
@@ -255,8 +280,7 @@ static int check_common(const char* fn, const NjodeDesc* desc, const float* para
   if (B < 0 || N < 0) NJODE_FAIL(NJODE_EINVAL, "%s: negative size", fn);
   const int want = *impl == NJODE_IMPL_TILED ? NJODE_TILED_TILE_ROWS : NJODE_GENERIC_TILE_ROWS;
   if (tile_rows != want) NJODE_FAIL(NJODE_EINVAL, "%s: schedule was built for tile_rows=%d, kernels need %d", fn, tile_rows, want);
-  const int units = njode_tile_units(desc, N);
-  if (n_tiles != (N + units - 1) / units) NJODE_FAIL(NJODE_EINVAL, "%s: n_tiles does not match N (njode_num_tiles)", fn);
+  if (n_tiles != njode_tile_plan(desc, N).n_tiles) NJODE_FAIL(NJODE_EINVAL, "%s: n_tiles does not match N (njode_num_tiles)", fn);
   return NJODE_OK;
 }
 
@@ -271,7 +295,8 @@ static SweepArgs make_args(const NjodeDesc* desc, const float* params, const flo
   a.params = params; a.params_t = params_t; a.times = times; a.values = values;
   a.kenc = kenc; a.perm = perm; a.tile_kmax = tile_kmax; a.tile_slot_off = tile_slot_off; a.knots = knots;
   a.N = N; a.n_tiles = n_tiles; a.total_slots = total_slots; a.tile_rows = tile_rows;
-  a.tile_units = njode_tile_units(desc, N);
+  const TilePlan plan = njode_tile_plan(desc, N);
+  a.tile_units = plan.units; a.tile_units_small = plan.units_small; a.n_small_tiles = plan.n_small;
   return a;
 }
 

@@ -149,6 +149,19 @@ static inline size_t njode_align_up(size_t v, size_t a) { return (v + a - 1) / a
 // weight-gradient MMAs (contraction over the tile's rows) are the long pole of a step -- half- or quarter-filled
 // tiles shorten that pole and spread the work over more SMs.  Every entry point derives this from (desc, N).
 int32_t njode_tile_units(const NjodeDesc* d, int64_t N);
+// The tiling of N units (sorted by step count, longest first): the first n_small tiles hold units_small units each,
+// the others `units` (= njode_tile_units).  Small leading tiles keep the LONGEST units -- the critical path of a
+// sweep with few tiles per SM -- in tiles whose reverse step is cheap (4 instead of 16 K-slices per weight-gradient
+// batch, a quarter of the tile stores), while the bulk of the work stays in full tiles.
+struct TilePlan {
+  int32_t units, units_small;
+  int64_t n_small, n_tiles;
+  __host__ __device__ int32_t units_of(int64_t tile) const { return tile < n_small ? units_small : units; }
+  __host__ __device__ int64_t first_unit(int64_t tile) const {
+    return tile < n_small ? tile * units_small : n_small * units_small + (tile - n_small) * units;
+  }
+};
+TilePlan njode_tile_plan(const NjodeDesc* d, int64_t N);
 
 struct SweepArgs {
   NjodeDesc desc;
@@ -164,7 +177,9 @@ struct SweepArgs {
   const float* knots;
   int64_t N, n_tiles, total_slots;
   int32_t tile_rows;
-  int32_t tile_units;        // units per tile (rows >= tile_units of every tile are padding)
+  int32_t tile_units;        // units per tile (rows >= tile_units of every tile are padding) ...
+  int32_t tile_units_small;  // ... except in the first n_small_tiles tiles (njode_tile_plan)
+  int64_t n_small_tiles;
   // forward outputs
   float* preds;
   float* preds_before;

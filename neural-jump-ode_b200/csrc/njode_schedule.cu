@@ -57,15 +57,15 @@ __global__ void k_count_steps(const float* __restrict__ times, const int64_t* __
   if ((threadIdx.x & 31) == 0 && total) atomicAdd(&header[NJODE_HDR_TOTAL_STEPS], total);
 }
 
-// sorted unit list -> tiles of `tile_rows` rows with `units` units each (the other rows hold no unit: -1)
-__global__ void k_spread_perm(const int32_t* __restrict__ sorted, int64_t N, int64_t Npad, int tile_rows, int units,
+// sorted unit list -> tiles of `tile_rows` rows holding plan.units_of(tile) units each (the other rows hold no unit: -1)
+__global__ void k_spread_perm(const int32_t* __restrict__ sorted, int64_t N, int64_t Npad, int tile_rows, TilePlan plan,
                               int32_t* __restrict__ perm) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Npad) return;
   const int64_t tile = idx / tile_rows;
   const int r = (int)(idx - tile * tile_rows);
-  const int64_t j = tile * units + r;
-  perm[idx] = (r < units && j < N) ? sorted[j] : -1;
+  const int64_t j = plan.first_unit(tile) + r;
+  perm[idx] = (r < plan.units_of(tile) && j < N) ? sorted[j] : -1;
 }
 
 __global__ void k_tile_kmax(const int32_t* __restrict__ kenc, const int32_t* __restrict__ perm,
@@ -161,9 +161,9 @@ extern "C" int njode_schedule_build(const NjodeDesc* desc, const float* times, c
   if (workspace_bytes < njode_schedule_workspace_bytes(B, N, tile_rows))
     NJODE_FAIL(NJODE_EWORKSPACE, "njode_schedule_build: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  const int units = njode_tile_units(desc, N);
-  if (units > tile_rows) NJODE_FAIL(NJODE_EINVAL, "njode_schedule_build: tile_rows does not match this descriptor (njode_tile_rows)");
-  const int64_t n_tiles = (N + units - 1) / units;
+  const TilePlan plan = njode_tile_plan(desc, N);
+  if (plan.units > tile_rows) NJODE_FAIL(NJODE_EINVAL, "njode_schedule_build: tile_rows does not match this descriptor (njode_tile_rows)");
+  const int64_t n_tiles = plan.n_tiles;
   const int64_t Npad = n_tiles * tile_rows;
   NJODE_CUDA_OK(cudaMemsetAsync(header, 0, NJODE_HDR_WORDS * sizeof(int64_t), st));
   if (N == 0) return NJODE_OK;
@@ -182,7 +182,7 @@ extern "C" int njode_schedule_build(const NjodeDesc* desc, const float* times, c
   NJODE_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, sorted, (int)N, 0,
                                                 NJODE_BIN_BITS, st));
   njode_count_launch(2);
-  k_spread_perm<<<(unsigned)((Npad + 255) / 256), 256, 0, st>>>(sorted, N, Npad, tile_rows, units, perm);
+  k_spread_perm<<<(unsigned)((Npad + 255) / 256), 256, 0, st>>>(sorted, N, Npad, tile_rows, plan, perm);
   NJODE_LAUNCH_OK("k_spread_perm");
   k_tile_kmax<<<(unsigned)((n_tiles + 127) / 128), 128, 0, st>>>(kenc, perm, n_tiles, tile_rows, tile_kmax);
   NJODE_LAUNCH_OK("k_tile_kmax");

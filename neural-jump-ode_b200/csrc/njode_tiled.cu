@@ -433,7 +433,6 @@ __device__ __forceinline__ void bwd_issuer(const SweepArgs& a, uint8_t* smem_raw
   const int worker = blockIdx.x / S, n_workers = gridDim.x / S;
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&ctl.tmem_base);
   const uint64_t wbase0 = umma::desc_k(umma::smem_u32(m.wt)), tbase0 = umma::desc_mn(umma::smem_u32(m.tiles), TILE_F * 4);
-  const int nks = a.tile_units / 8;               // K-slices of the row contraction: the tile's units only
   TR_DECL(2);
   TR_SMEM(reinterpret_cast<long long*>((reinterpret_cast<uintptr_t>(m.ctl + 1) + 15) & ~(uintptr_t)15) + NJODE_TRACE_SMEM_REC);
   bool ok = true;
@@ -447,6 +446,7 @@ __device__ __forceinline__ void bwd_issuer(const SweepArgs& a, uint8_t* smem_raw
   // compiler from hoisting ~200 loop-invariant 64-bit descriptors into (spilled) registers
   uint64_t wbase, tbase;
   auto fresh = [&]() { wbase = wbase0; tbase = tbase0; asm volatile("" : "+l"(wbase), "+l"(tbase)); };
+  int nks = 0;                                    // K-slices of the row contraction: the current tile's units only
   auto issue_readout = [&]() {
     wait_ops();
     fresh();
@@ -470,6 +470,7 @@ __device__ __forceinline__ void bwd_issuer(const SweepArgs& a, uint8_t* smem_raw
     const int64_t tile = snake_tile(round, worker, n_workers);
     if (tile >= a.n_tiles) continue;
     const int kmax = a.tile_kmax[tile];
+    nks = (tile < a.n_small_tiles ? a.tile_units_small : a.tile_units) / 8;
     issue_readout();
     for (int k = kmax - 1; k >= 0; --k) {
       TR(64);
@@ -559,8 +560,8 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
   const uint32_t quad_base = tmem + ((uint32_t)(q * 32) << 16);     // this warp's lane quadrant, column 0
   const uint32_t lane_base = quad_base + (uint32_t)col0;            // ... at this thread's column slice
   const uint32_t tiles_s = umma::smem_u32(tiles);
-  // rows >= tile_units of every tile are padding: the row contraction stops before them, so they skip the tile stores
-  const bool has_unit_row = row < a.tile_units;
+  // rows beyond a tile's units are padding: the row contraction stops before them, so they skip the tile stores
+  bool has_unit_row = true;
   if (c == 0) {  // zero the persistent weight-gradient accumulators
     uint32_t zero[8];
 #pragma unroll
@@ -632,6 +633,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
     const int64_t tile = snake_tile(round, worker, n_workers);
     if (tile >= a.n_tiles) continue;
     const int kmax = a.tile_kmax[tile];
+    has_unit_row = row < (tile < a.n_small_tiles ? a.tile_units_small : a.tile_units);
     const int u = a.perm[tile * R + row];
     const int ke = u >= 0 ? a.kenc[u] : 0;
     // this thread's slice of the tile's checkpoint / knot slots (32-bit offsets per step from here on)
@@ -693,6 +695,14 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
     float tn = ld_na(kn + kmax * R);
     float tc_next = kmax > 0 ? ld_na(kn + (kmax - 1) * R) : tn;
     bool pending = false;                             // weight-gradient MMAs of the previous step still to be merged
+    if (kmax > 0) {
+      ld8_cg(ck + (kmax - 1) * (2 * R * H), hrow);
+      ld8_cg(ck + (kmax - 1) * (2 * R * H) + R * H, z);
+      if (kmax > 1) {
+        prefetch_l2(ck + (kmax - 2) * (2 * R * H));
+        prefetch_l2(ck + (kmax - 2) * (2 * R * H) + R * H);
+      }
+    }
     for (int k = kmax - 1; k >= 0; --k) {
       TR(1);
       const float tc = tc_next;
@@ -707,12 +717,10 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
       // This step's checkpoints and the next knot.  Issued AFTER the hand-over on purpose: scoreboards are shared,
       // so anything that waits on an older load (delta above) or fences memory (the hand-over) would also wait for
       // these ~1000-cycle HBM loads.  They are consumed after the weight-gradient wait below.
-      ld8_cg(ck + k * (2 * R * H), hrow);
-      ld8_cg(ck + k * (2 * R * H) + R * H, z);
       tc_next = ld_na(kn + (k > 0 ? k - 1 : 0) * R);
-      if (k > 0) {   // and pull the NEXT step's checkpoints into L2 (no destination register, no scoreboard)
-        prefetch_l2(ck + (k - 1) * (2 * R * H));
-        prefetch_l2(ck + (k - 1) * (2 * R * H) + R * H);
+      if (k > 1) {   // pull the checkpoints of the step after the next into L2 (no destination register, no scoreboard)
+        prefetch_l2(ck + (k - 2) * (2 * R * H));
+        prefetch_l2(ck + (k - 2) * (2 * R * H) + R * H);
       }
       // the MN tiles are free once the previous step's weight-gradient MMAs are done
       if (pending) {
@@ -724,9 +732,13 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
       }
       TR(5);
       scale8(sc_kind, hrow);
+      TR(13);
       put(hrow, false, 0, 0, T_AM_HI, T_AM_LO);
+      TR(14);
       put(d, false, 0, 0, T_D1M_HI, T_D1M_LO);
+      TR(15);
       put(z, false, 0, 0, T_ZM_HI, T_ZM_LO);
+      TR(16);
       {
         // aux columns (1, s(x).., t, dt); no dynamic indexing (a local-memory array costs an L2 round trip here)
         static_assert(MAX_DX == 2, "aux column layout assumes d_x <= 2");
@@ -745,10 +757,14 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
       hand_over();                                                           // -> d s(h) = d0 * W0 ; weight gradients
       pending = true;
       TR(10);
+      // the NEXT step's checkpoints, as soon as their registers are free: an L2 hit is ~1000 cycles away and nothing
+      // on the way to their first use (the tile stores after the weight-gradient wait) may have to wait for them
+      if (k > 0) ld8_cg(ck + (k - 1) * (2 * R * H) + R * H, z);
       wait_chain();
       TR(11);
       umma::tmem_ld8(lane_base + B_ACCD, acc);
       scale_grad_acc8(sc_kind, acc, hrow, g);
+      if (k > 0) ld8_cg(ck + (k - 1) * (2 * R * H), hrow);
       TR(12);
     }
     if (pending) {
