@@ -165,6 +165,18 @@ int njode_forward_batch(const NjodeDesc* desc, const float* params, const float*
                         void* arena, size_t arena_bytes, int32_t want_ckpt, float* ckpt, int64_t ckpt_floats,
                         void* scratch, size_t scratch_bytes, int64_t* header_host,
                         float* preds, float* preds_before, void* stream);
+/* The same in two halves, for callers with host work of their own to do while the schedule is being built on the
+ * device: _begin launches the schedule build and the header copy and returns at once (it needs neither the
+ * parameters nor the output buffers); _finish synchronises `stream`, checks the capacities and launches knots +
+ * forward sweep.  njode_forward_batch = _begin then _finish with the same buffers. */
+int njode_forward_batch_begin(const NjodeDesc* desc, const float* times, const int64_t* obs_offsets,
+                              int64_t B, int64_t N, void* arena, size_t arena_bytes,
+                              void* scratch, size_t scratch_bytes, int64_t* header_host, void* stream);
+int njode_forward_batch_finish(const NjodeDesc* desc, const float* params, const float* times, const float* values,
+                               const int64_t* obs_offsets, int64_t B, int64_t N,
+                               void* arena, size_t arena_bytes, int32_t want_ckpt, float* ckpt, int64_t ckpt_floats,
+                               void* scratch, size_t scratch_bytes, int64_t* header_host,
+                               float* preds, float* preds_before, void* stream);
 
 /* ---- loss: value and gradient w.r.t. preds / preds_before in one pass --------------------------
  * loss_out: device float[1].  grad_* may be NULL (value only).  traj_scale = 1/B_global so that

@@ -391,11 +391,27 @@ extern "C" size_t njode_batch_scratch_bytes(const NjodeDesc* desc, int64_t B, in
   return njode_align_up(njode_schedule_workspace_bytes(B, N, tile_rows), 256) + njode_align_up(njode_forward_workspace_bytes(desc), 256);
 }
 
-extern "C" int njode_forward_batch(const NjodeDesc* desc, const float* params, const float* times, const float* values,
-                                   const int64_t* obs_offsets, int64_t B, int64_t N,
-                                   void* arena, size_t arena_bytes, int32_t want_ckpt, float* ckpt, int64_t ckpt_floats,
-                                   void* scratch, size_t scratch_bytes, int64_t* header_host,
-                                   float* preds, float* preds_before, void* stream) {
+// arena pointers of a batch (fixed part; knots follow)
+struct ArenaView {
+  int32_t *kenc, *perm, *tile_kmax;
+  int64_t *tile_slot_off, *header;
+  float* knots;
+};
+static ArenaView arena_view(void* arena, const int64_t* lay) {
+  char* base = (char*)arena;
+  ArenaView v;
+  v.kenc = (int32_t*)(base + lay[NJODE_ARENA_KENC]);
+  v.perm = (int32_t*)(base + lay[NJODE_ARENA_PERM]);
+  v.tile_kmax = (int32_t*)(base + lay[NJODE_ARENA_TILE_KMAX]);
+  v.tile_slot_off = (int64_t*)(base + lay[NJODE_ARENA_TILE_SLOT_OFF]);
+  v.header = (int64_t*)(base + lay[NJODE_ARENA_HEADER]);
+  v.knots = (float*)(base + lay[NJODE_ARENA_KNOTS]);
+  return v;
+}
+
+extern "C" int njode_forward_batch_begin(const NjodeDesc* desc, const float* times, const int64_t* obs_offsets,
+                                         int64_t B, int64_t N, void* arena, size_t arena_bytes,
+                                         void* scratch, size_t scratch_bytes, int64_t* header_host, void* stream) {
   const int tile_rows = njode_tile_rows(desc);
   if (tile_rows < 1) return NJODE_EINVAL;                      // (njode_tile_rows set the error text)
   if (!arena || !scratch || !header_host) NJODE_FAIL(NJODE_EINVAL, "njode_forward_batch: null arena / scratch / header_host");
@@ -403,31 +419,51 @@ extern "C" int njode_forward_batch(const NjodeDesc* desc, const float* params, c
   const size_t fixed = njode_batch_arena_bytes(desc, B, N, 0, lay);
   if (arena_bytes < fixed) NJODE_FAIL(NJODE_EWORKSPACE, "njode_forward_batch: arena smaller than its size-independent part (njode_batch_arena_bytes(..., 0))");
   if (scratch_bytes < njode_batch_scratch_bytes(desc, B, N)) NJODE_FAIL(NJODE_EWORKSPACE, "njode_forward_batch: scratch too small");
-  cudaStream_t st = (cudaStream_t)stream;
-  char* base = (char*)arena;
-  int32_t* kenc = (int32_t*)(base + lay[NJODE_ARENA_KENC]);
-  int32_t* perm = (int32_t*)(base + lay[NJODE_ARENA_PERM]);
-  int32_t* tile_kmax = (int32_t*)(base + lay[NJODE_ARENA_TILE_KMAX]);
-  int64_t* tile_slot_off = (int64_t*)(base + lay[NJODE_ARENA_TILE_SLOT_OFF]);
-  int64_t* header = (int64_t*)(base + lay[NJODE_ARENA_HEADER]);
-  float* knots = (float*)(base + lay[NJODE_ARENA_KNOTS]);
+  const ArenaView v = arena_view(arena, lay);
   const size_t sched_ws = njode_align_up(njode_schedule_workspace_bytes(B, N, tile_rows), 256);
-  int rc = njode_schedule_build(desc, times, obs_offsets, B, N, tile_rows, kenc, perm, tile_kmax, tile_slot_off, header,
+  int rc = njode_schedule_build(desc, times, obs_offsets, B, N, tile_rows, v.kenc, v.perm, v.tile_kmax, v.tile_slot_off, v.header,
                                 scratch, sched_ws, stream);
   if (rc) return rc;
-  NJODE_CUDA_OK(cudaMemcpyAsync(header_host, header, NJODE_HDR_WORDS * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  NJODE_CUDA_OK(cudaStreamSynchronize(st));
+  NJODE_CUDA_OK(cudaMemcpyAsync(header_host, v.header, NJODE_HDR_WORDS * sizeof(int64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return NJODE_OK;
+}
+
+extern "C" int njode_forward_batch_finish(const NjodeDesc* desc, const float* params, const float* times, const float* values,
+                                          const int64_t* obs_offsets, int64_t B, int64_t N,
+                                          void* arena, size_t arena_bytes, int32_t want_ckpt, float* ckpt, int64_t ckpt_floats,
+                                          void* scratch, size_t scratch_bytes, int64_t* header_host,
+                                          float* preds, float* preds_before, void* stream) {
+  const int tile_rows = njode_tile_rows(desc);
+  if (tile_rows < 1) return NJODE_EINVAL;
+  if (!arena || !scratch || !header_host) NJODE_FAIL(NJODE_EINVAL, "njode_forward_batch: null arena / scratch / header_host");
+  if (scratch_bytes < njode_batch_scratch_bytes(desc, B, N)) NJODE_FAIL(NJODE_EWORKSPACE, "njode_forward_batch: scratch too small");
+  int64_t lay[NJODE_ARENA_WORDS];
+  njode_batch_arena_bytes(desc, B, N, 0, lay);
+  const ArenaView v = arena_view(arena, lay);
+  NJODE_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));          // the schedule header is on the host now
   const int64_t total_slots = header_host[NJODE_HDR_TOTAL_SLOTS];
   const int64_t n_tiles = njode_num_tiles(desc, N);
   const int S = desc->shared_network ? 1 : desc->num_moments;
   const int64_t need_ckpt = want_ckpt ? (int64_t)S * total_slots * tile_rows * njode_ckpt_row_floats(desc) : 0;
   if (arena_bytes < njode_batch_arena_bytes(desc, B, N, total_slots, nullptr) || (want_ckpt && (ckpt_floats < need_ckpt || (!ckpt && need_ckpt > 0))))
     NJODE_FAIL(NJODE_ECAPACITY, "njode_forward_batch: this batch has %lld checkpoint slots; arena / ckpt are too small for it", (long long)total_slots);
-  rc = njode_schedule_knots(times, kenc, perm, tile_kmax, tile_slot_off, N, n_tiles, tile_rows, desc, knots, stream);
+  int rc = njode_schedule_knots(times, v.kenc, v.perm, v.tile_kmax, v.tile_slot_off, N, n_tiles, tile_rows, desc, v.knots, stream);
   if (rc) return rc;
-  return njode_forward(desc, params, times, values, obs_offsets, B, N, kenc, perm, tile_kmax, tile_slot_off, knots, n_tiles,
+  const size_t sched_ws = njode_align_up(njode_schedule_workspace_bytes(B, N, tile_rows), 256);
+  return njode_forward(desc, params, times, values, obs_offsets, B, N, v.kenc, v.perm, v.tile_kmax, v.tile_slot_off, v.knots, n_tiles,
                        total_slots, tile_rows, preds, preds_before, want_ckpt ? ckpt : nullptr,
                        (char*)scratch + sched_ws, scratch_bytes - sched_ws, stream);
+}
+
+extern "C" int njode_forward_batch(const NjodeDesc* desc, const float* params, const float* times, const float* values,
+                                   const int64_t* obs_offsets, int64_t B, int64_t N,
+                                   void* arena, size_t arena_bytes, int32_t want_ckpt, float* ckpt, int64_t ckpt_floats,
+                                   void* scratch, size_t scratch_bytes, int64_t* header_host,
+                                   float* preds, float* preds_before, void* stream) {
+  int rc = njode_forward_batch_begin(desc, times, obs_offsets, B, N, arena, arena_bytes, scratch, scratch_bytes, header_host, stream);
+  if (rc) return rc;
+  return njode_forward_batch_finish(desc, params, times, values, obs_offsets, B, N, arena, arena_bytes, want_ckpt, ckpt, ckpt_floats,
+                                    scratch, scratch_bytes, header_host, preds, preds_before, stream);
 }
 
 extern "C" int njode_backward(const NjodeDesc* desc, const float* params, const float* times, const float* values,

@@ -62,6 +62,8 @@ SIGNATURES = {
     "njode_batch_arena_bytes": (_SZ, [_DESC, _I64, _I64, _I64, _P]),
     "njode_batch_scratch_bytes": (_SZ, [_DESC, _I64, _I64]),
     "njode_forward_batch": (C.c_int, [_DESC, _P, _P, _P, _P, _I64, _I64, _P, _SZ, _I32, _P, _I64, _P, _SZ, _P, _P, _P, _P]),
+    "njode_forward_batch_begin": (C.c_int, [_DESC, _P, _P, _I64, _I64, _P, _SZ, _P, _SZ, _P, _P]),
+    "njode_forward_batch_finish": (C.c_int, [_DESC, _P, _P, _P, _P, _I64, _I64, _P, _SZ, _I32, _P, _I64, _P, _SZ, _P, _P, _P, _P]),
     "njode_loss_workspace_bytes": (_SZ, [_I64]),
     "njode_loss": (C.c_int, [_LDESC, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _F, _P, _P, _P, _P, _SZ, _P]),
     "njode_backward_workspace_bytes": (_SZ, [_DESC, _I64]),
@@ -75,7 +77,7 @@ SIGNATURES = {
 }
 
 # kernels launched by each ABI call (bench.py's gpu_launches claim): name -> count
-KERNELS_PER_CALL = {"njode_schedule_build": 5, "njode_schedule_knots": 1, "njode_forward": 2, "njode_forward_batch": 8, "njode_loss": 2,
+KERNELS_PER_CALL = {"njode_schedule_build": 5, "njode_schedule_knots": 1, "njode_forward": 2, "njode_forward_batch": 8, "njode_forward_batch_begin": 5, "njode_forward_batch_finish": 3, "njode_loss": 2,
                     "njode_backward": 3, "njode_adam_step": 1}
 launch_count = 0
 

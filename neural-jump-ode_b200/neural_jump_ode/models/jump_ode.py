@@ -110,25 +110,25 @@ class OutputNN(nn.Module):
 # autograd glue: forward sweep / reverse sweep
 # ------------------------------------------------------------------------------------------------
 
+class _BatchPlan:
+    """What the sweep needs to know about a batch before it runs (see NeuralJumpODE._begin_batch)."""
+    __slots__ = ("tile_rows", "n_tiles", "row_floats", "key", "sched", "slots", "arena", "layout", "scratch", "scratch_bytes", "host")
+
+
 class _SweepFunction(torch.autograd.Function):
     """preds, preds_before = sweep(batch; params).  Forward = ``njode_forward`` on a batch whose schedule is cached,
-    ``njode_forward_batch`` (schedule + knots + sweep in one call) on a new one; per-step hidden-state checkpoints
-    are written when a gradient will be needed.  Backward = ``njode_backward``."""
+    ``njode_forward_batch_begin`` / ``_finish`` (schedule + knots + sweep, no Python between the schedule's host sync
+    and the sweep) on a new one; per-step hidden-state checkpoints are written when a gradient will be needed.
+    Backward = ``njode_backward``."""
 
     @staticmethod
-    def forward(ctx, model, desc, batch: PackedBatch, want_grad: bool, *params):
+    def forward(ctx, model, desc, batch: PackedBatch, want_grad: bool, plan, *params):
         lib = nat.load()
         dev = batch.device
         N, B = batch.N, batch.B
         d_y, M = desc.d_y, desc.num_moments
         S = 1 if desc.shared_network else M
-        tile_rows = lib.njode_tile_rows(desc)
-        n_tiles = lib.njode_num_tiles(desc, N)
-        row_floats = lib.njode_ckpt_row_floats(desc)
-        if tile_rows < 1 or n_tiles < 0 or row_floats < 0:
-            raise RuntimeError("NeuralJumpODE: " + lib.njode_last_error().decode(errors="replace"))
-        key = batch.schedule_key(desc, tile_rows, n_tiles)
-        sched = batch._schedules.get(key)
+        tile_rows, n_tiles, row_floats, key, sched = plan.tile_rows, plan.n_tiles, plan.row_floats, plan.key, plan.sched
         with nat.on_device(dev):
             stream = nat.current_stream(dev)
             flat = model._flat_view(params)
@@ -146,29 +146,32 @@ class _SweepFunction(torch.autograd.Function):
                                             nat.ptr(preds), nat.ptr(before), nat.ptr(ckpt), nat.ptr(ws), ws_bytes, stream),
                           "njode_forward")
             else:
-                # new batch: everything is sized from a guess of its checkpoint slot count (exact when a batch of
-                # this shape was seen before) so that no Python runs between the schedule's host sync and the sweep
-                slots = model._guess_slots(N, B, n_tiles)
-                scratch_bytes = lib.njode_batch_scratch_bytes(desc, B, N)
-                scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
-                host = pinned_header(dev)
-                layout = (nat.C.c_int64 * nat.ARENA_WORDS)()
-                for attempt in (0, 1):
-                    arena_bytes = lib.njode_batch_arena_bytes(desc, B, N, slots, layout)
-                    arena = torch.empty(arena_bytes, dtype=torch.uint8, device=dev)
+                # new batch: its schedule is being built on the device since _begin_batch (njode_forward_batch_begin);
+                # arena and checkpoints are sized from a guess of its slot count (exact when a batch of this shape
+                # was seen before) so that no Python runs between the schedule's host sync and the sweep
+                slots, arena, layout, scratch, scratch_bytes, host = plan.slots, plan.arena, plan.layout, plan.scratch, plan.scratch_bytes, plan.host
+                ckpt_floats = S * slots * tile_rows * row_floats if want_grad else 0
+                ckpt = torch.empty(max(ckpt_floats, 1), dtype=torch.float32, device=dev) if want_grad else None
+                rc = lib.njode_forward_batch_finish(desc, nat.ptr(flat), nat.ptr(batch.times), nat.ptr(batch.values),
+                                                    nat.ptr(batch.offsets), B, N, nat.ptr(arena), arena.numel(),
+                                                    1 if want_grad else 0, nat.ptr(ckpt), ckpt_floats,
+                                                    nat.ptr(scratch), scratch_bytes, host.data_ptr(),
+                                                    nat.ptr(preds), nat.ptr(before), stream)
+                if rc == nat.ECAPACITY:
+                    # the guess was too small; the schedule is known now: size exactly and run the one-call form
+                    slots = int(host[nat.HDR_TOTAL_SLOTS])
+                    arena = ckpt = None
+                    arena = torch.empty(lib.njode_batch_arena_bytes(desc, B, N, slots, layout), dtype=torch.uint8, device=dev)
                     ckpt_floats = S * slots * tile_rows * row_floats if want_grad else 0
                     ckpt = torch.empty(max(ckpt_floats, 1), dtype=torch.float32, device=dev) if want_grad else None
                     rc = lib.njode_forward_batch(desc, nat.ptr(flat), nat.ptr(batch.times), nat.ptr(batch.values),
-                                                 nat.ptr(batch.offsets), B, N, nat.ptr(arena), arena_bytes,
+                                                 nat.ptr(batch.offsets), B, N, nat.ptr(arena), arena.numel(),
                                                  1 if want_grad else 0, nat.ptr(ckpt), ckpt_floats,
                                                  nat.ptr(scratch), scratch_bytes, host.data_ptr(),
                                                  nat.ptr(preds), nat.ptr(before), stream)
-                    if rc == nat.ECAPACITY and attempt == 0:
-                        arena = ckpt = None
-                        slots = int(host[nat.HDR_TOTAL_SLOTS])     # the schedule is known now: size exactly, run again
-                        continue
                     nat.check(rc, "njode_forward_batch")
-                    break
+                else:
+                    nat.check(rc, "njode_forward_batch_finish")
                 sched = Schedule(arena, layout, N, tile_rows, n_tiles, host.tolist())
                 model._note_slots(N, B, n_tiles, sched.total_slots)
                 batch._schedules[key] = sched
@@ -211,7 +214,7 @@ class _SweepFunction(torch.autograd.Function):
         # Stacks of moments >= 2 get an all-zero gradient from nj_ode_loss (jump_ode.py:328-378); the
         # reference reports zero tensors for them too (torch.stack backward), so nothing is special-cased.
         grads = [g.view(shp) for g, shp in zip(grad_flat.split([shp.numel() for shp in ctx.shapes]), ctx.shapes)]
-        return (None, None, None, None, *grads)
+        return (None, None, None, None, None, *grads)
 
 
 class _LossFunction(torch.autograd.Function):
@@ -343,6 +346,34 @@ class NeuralJumpODE(nn.Module):
             break
         return torch.cat([p.detach().reshape(-1) for p in params]).float()
 
+    def _begin_batch(self, desc, batch: PackedBatch):
+        """Tiling of the batch for this model; if its schedule is not cached yet, launch the schedule build right away
+        (``njode_forward_batch_begin``) so that it runs on the device while the host prepares the sweep."""
+        lib = nat.load()
+        plan = _BatchPlan()
+        N, B = batch.N, batch.B
+        plan.tile_rows = lib.njode_tile_rows(desc)
+        plan.n_tiles = lib.njode_num_tiles(desc, N)
+        plan.row_floats = lib.njode_ckpt_row_floats(desc)
+        if plan.tile_rows < 1 or plan.n_tiles < 0 or plan.row_floats < 0:
+            raise RuntimeError("NeuralJumpODE: " + lib.njode_last_error().decode(errors="replace"))
+        plan.key = batch.schedule_key(desc, plan.tile_rows, plan.n_tiles)
+        plan.sched = batch._schedules.get(plan.key)
+        if plan.sched is None:
+            dev = batch.device
+            with nat.on_device(dev):
+                plan.slots = self._guess_slots(N, B, plan.n_tiles)
+                plan.layout = (nat.C.c_int64 * nat.ARENA_WORDS)()
+                plan.arena = torch.empty(lib.njode_batch_arena_bytes(desc, B, N, plan.slots, plan.layout), dtype=torch.uint8, device=dev)
+                plan.scratch_bytes = lib.njode_batch_scratch_bytes(desc, B, N)
+                plan.scratch = torch.empty(plan.scratch_bytes, dtype=torch.uint8, device=dev)
+                plan.host = pinned_header(dev)
+                nat.check(lib.njode_forward_batch_begin(desc, nat.ptr(batch.times), nat.ptr(batch.offsets), B, N,
+                                                        nat.ptr(plan.arena), plan.arena.numel(), nat.ptr(plan.scratch),
+                                                        plan.scratch_bytes, plan.host.data_ptr(), nat.current_stream(dev)),
+                          "njode_forward_batch_begin")
+        return plan
+
     # -- checkpoint-slot guesses for batches whose schedule is not known yet (njode_forward_batch) -------
     def _guess_slots(self, N, B, n_tiles) -> int:
         exact = self._slots_memo.get((N, B))
@@ -418,8 +449,9 @@ class NeuralJumpODE(nn.Module):
         if batch.values.shape[1] != self.input_dim:
             raise ValueError(f"values have d_x={batch.values.shape[1]}, model expects {self.input_dim}")
         desc = self.descriptor()
+        plan = self._begin_batch(desc, batch)
         want_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        return _SweepFunction.apply(self, desc, batch, want_grad, *params)
+        return _SweepFunction.apply(self, desc, batch, want_grad, plan, *params)
 
     def forward(self, batch_times, batch_values=None):
         """batch_times / batch_values: lists of (n_i,) / (n_i, d_x) tensors (reference jump_ode.py:218-233),
