@@ -57,27 +57,24 @@ __global__ void k_count_steps(const float* __restrict__ times, const int64_t* __
   if ((threadIdx.x & 31) == 0 && total) atomicAdd(&header[NJODE_HDR_TOTAL_STEPS], total);
 }
 
-// sorted unit list -> tiles of `tile_rows` rows holding plan.units_of(tile) units each (the other rows hold no unit: -1)
-__global__ void k_spread_perm(const int32_t* __restrict__ sorted, int64_t N, int64_t Npad, int tile_rows, TilePlan plan,
-                              int32_t* __restrict__ perm) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Npad) return;
-  const int64_t tile = idx / tile_rows;
-  const int r = (int)(idx - tile * tile_rows);
+// sorted unit list -> tiles of `tile_rows` rows holding plan.units_of(tile) units each (the other rows hold no unit: -1),
+// and the largest step count of each tile.  One block per tile, one thread per row (tile_rows = 32 or 128).
+__global__ void k_spread_perm(const int32_t* __restrict__ sorted, const int32_t* __restrict__ kenc, int64_t N, int tile_rows,
+                              TilePlan plan, int32_t* __restrict__ perm, int32_t* __restrict__ tile_kmax) {
+  __shared__ int warp_max[32];
+  const int64_t tile = blockIdx.x;
+  const int r = threadIdx.x;
   const int64_t j = plan.first_unit(tile) + r;
-  perm[idx] = (r < plan.units_of(tile) && j < N) ? sorted[j] : -1;
-}
-
-__global__ void k_tile_kmax(const int32_t* __restrict__ kenc, const int32_t* __restrict__ perm,
-                            int64_t n_tiles, int tile_rows, int32_t* __restrict__ tile_kmax) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_tiles) return;
-  int km = 0;
-  for (int r = 0; r < tile_rows; ++r) {
-    const int u = perm[t * tile_rows + r];
-    if (u >= 0) km = max(km, kenc[u] >> 1);
+  const int u = (r < plan.units_of(tile) && j < N) ? sorted[j] : -1;
+  perm[tile * tile_rows + r] = u;
+  int km = u >= 0 ? (kenc[u] >> 1) : 0;
+  for (int o = 16; o > 0; o >>= 1) km = max(km, __shfl_xor_sync(0xffffffffu, km, o));
+  if ((r & 31) == 0) warp_max[r >> 5] = km;
+  __syncthreads();
+  if (r == 0) {
+    for (int w = 1; w < (tile_rows + 31) / 32; ++w) km = max(km, warp_max[w]);
+    tile_kmax[tile] = km;
   }
-  tile_kmax[t] = km;
 }
 
 // single block: exclusive scan of (kmax+1) over tiles -> checkpoint slot offsets; header totals
@@ -164,7 +161,6 @@ extern "C" int njode_schedule_build(const NjodeDesc* desc, const float* times, c
   const TilePlan plan = njode_tile_plan(desc, N);
   if (plan.units > tile_rows) NJODE_FAIL(NJODE_EINVAL, "njode_schedule_build: tile_rows does not match this descriptor (njode_tile_rows)");
   const int64_t n_tiles = plan.n_tiles;
-  const int64_t Npad = n_tiles * tile_rows;
   NJODE_CUDA_OK(cudaMemsetAsync(header, 0, NJODE_HDR_WORDS * sizeof(int64_t), st));
   if (N == 0) return NJODE_OK;
   const size_t seg = njode_align_up((size_t)N * sizeof(int32_t), 256);
@@ -182,10 +178,9 @@ extern "C" int njode_schedule_build(const NjodeDesc* desc, const float* times, c
   NJODE_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, sorted, (int)N, 0,
                                                 NJODE_BIN_BITS, st));
   njode_count_launch(2);
-  k_spread_perm<<<(unsigned)((Npad + 255) / 256), 256, 0, st>>>(sorted, N, Npad, tile_rows, plan, perm);
+  if (tile_rows > 1024 || tile_rows % 32 != 0) NJODE_FAIL(NJODE_EINVAL, "njode_schedule_build: tile_rows must be a multiple of 32, at most 1024");
+  k_spread_perm<<<(unsigned)n_tiles, tile_rows, 0, st>>>(sorted, kenc, N, tile_rows, plan, perm, tile_kmax);
   NJODE_LAUNCH_OK("k_spread_perm");
-  k_tile_kmax<<<(unsigned)((n_tiles + 127) / 128), 128, 0, st>>>(kenc, perm, n_tiles, tile_rows, tile_kmax);
-  NJODE_LAUNCH_OK("k_tile_kmax");
   k_tile_scan<<<1, 1024, 0, st>>>(tile_kmax, n_tiles, tile_slot_off, (long long*)header);
   NJODE_LAUNCH_OK("k_tile_scan");
   return NJODE_OK;

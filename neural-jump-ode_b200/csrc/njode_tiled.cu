@@ -283,9 +283,11 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
   for (int64_t round = 0; round * n_workers < a.n_tiles; ++round) {
     const int64_t tile = snake_tile(round, worker, n_workers);
     if (tile >= a.n_tiles) continue;
-    const int64_t slot0 = a.tile_slot_off[tile];
     const int kmax = a.tile_kmax[tile];
     const int u = a.perm[tile * R + row];
+    // this thread's slice of the tile's checkpoint / knot slots (32-bit offsets per step from here on)
+    float* const ck = ckpt ? ckpt + a.tile_slot_off[tile] * (2 * R * H) : nullptr;
+    const float* const kn = a.knots + a.tile_slot_off[tile] * R + row;
     const int ke = u >= 0 ? a.kenc[u] : 0;
     const int K = ke >> 1;
     float x[MAX_DX], xs[MAX_DX];
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
     ld8(sp.b_jump1 + col0, cb);
 #pragma unroll
     for (int j = 0; j < 8; ++j) h[j] = act_fwd<ACT>(acc[j] + cb[j]);
-    if (ckpt) st8_stream(ckpt + (slot0 + 0) * (2 * R * H), h);
+    if (ck) st8_stream(ck, h);
 
     // readout: y = out(h)                                           jump_ode.py:170 / :177, :205-212
     auto readout = [&](float* __restrict__ dst, int64_t obs, bool write) {
@@ -340,14 +342,14 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
     // Euler steps with x held constant                              jump_ode.py:188-203, :122-140
     // knots are loaded one step ahead: a load consumed in the step that issues it is an exposed global-memory
     // latency on this latency-bound chain (it was the top stall site of the forward kernel, 17 % of its samples)
-    float tn = ld_na(a.knots + (slot0 + 0) * R + row);
-    float tn_ahead = kmax > 0 ? ld_na(a.knots + (slot0 + 1) * R + row) : tn;
+    float tn = ld_na(kn);
+    float tn_ahead = kmax > 0 ? ld_na(kn + R) : tn;
     for (int k = 0; k < kmax; ++k) {
       const float tc = tn;
       tn = tn_ahead;
       // (lands in its own register and is moved into tn_ahead at the END of the step: assigned here, the compiler's
       // register-rotation move followed the load directly and waited out the whole global-memory latency every step)
-      const float tn_loaded = ld_na(a.knots + (slot0 + (k + 2 <= kmax ? k + 2 : kmax)) * R + row);
+      const float tn_loaded = ld_na(kn + (k + 2 <= kmax ? k + 2 : kmax) * R);
       const float delta = __fsub_rn(tn, tc);
       TR(32 + 7);
 #pragma unroll
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
       ld8(sp.ext_ode0[dx + 1] + col0, cw);
 #pragma unroll
       for (int j = 0; j < 8; ++j) z[j] = act_fwd<ACT>(fmaf(cw[j], delta, z[j]));
-      if (ckpt) st8_stream(ckpt + ((slot0 + k) * 2 + 1) * (R * H), z);
+      if (ck) st8_stream(ck + (k * 2 + 1) * (R * H), z);
       gemm(z, FW_ODE1, acc);
       TR(32 + 8);
       if (k < K) {
@@ -378,7 +380,7 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) h[j] = fmaf(delta, acc[j] + cb[j], h[j]);
       }
-      if (ckpt) st8_stream(ckpt + (slot0 + k + 1) * (2 * R * H), h);
+      if (ck) st8_stream(ck + (k + 1) * (2 * R * H), h);
       asm volatile("mov.f32 %0, %1;" : "=f"(tn_ahead) : "f"(tn_loaded));
     }
     readout(a.preds_before, (int64_t)u + 1, u >= 0 && (ke & 1));

@@ -77,7 +77,7 @@ SIGNATURES = {
 }
 
 # kernels launched by each ABI call (bench.py's gpu_launches claim): name -> count
-KERNELS_PER_CALL = {"njode_schedule_build": 5, "njode_schedule_knots": 1, "njode_forward": 2, "njode_forward_batch": 8, "njode_forward_batch_begin": 5, "njode_forward_batch_finish": 3, "njode_loss": 2,
+KERNELS_PER_CALL = {"njode_schedule_build": 4, "njode_schedule_knots": 1, "njode_forward": 2, "njode_forward_batch": 7, "njode_forward_batch_begin": 4, "njode_forward_batch_finish": 3, "njode_loss": 2,
                     "njode_backward": 3, "njode_adam_step": 1}
 launch_count = 0
 
