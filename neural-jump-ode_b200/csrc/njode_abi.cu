@@ -168,10 +168,12 @@ TilePlan njode_tile_plan(const NjodeDesc* d, int64_t N) {
     const int S = d->shared_network ? 1 : d->num_moments;
     const int64_t sms_per_stack = sm_count_abi() / S > 0 ? sm_count_abi() / S : 1;
     const int64_t full_tiles = (N + p.units - 1) / p.units;
-    // up to ~8 full tiles per SM the longest tile is a large part of a sweep's time (default workload: 2.2 full
-    // tiles per SM, longest tile 78 steps against an average of 12 per CTA): one quarter tile per SM for the
-    // longest units.  Beyond that the sweeps are throughput-bound and the extra tile-steps only cost.
-    static const int tail = [] { const char* e = getenv("NJODE_TAIL_TILES"); return e ? atoi(e) : 1; }();   // (A/B knob)
+    // Up to ~8 full tiles per SM the longest tile is a large part of a sweep's time (default workload: 2.2 full
+    // tiles per SM, longest tile 78 steps against an average of 12 per CTA), which suggests one quarter tile per SM
+    // for the longest units.  Measured: 0.3292 -> 0.3279 ms per step (a quarter tile's reverse step is 4000 cycles,
+    // not the ~2900 its MMA and store counts suggest: all of its rows live in warps of one scheduler) for +43 % of
+    // checkpoint bytes (padding rows are stored too).  Off unless NJODE_TAIL_TILES=1.
+    static const int tail = [] { const char* e = getenv("NJODE_TAIL_TILES"); return e ? atoi(e) : 0; }();
     if (tail && full_tiles <= 8 * sms_per_stack) {
       p.units_small = NJODE_TILED_TILE_ROWS / 4;
       p.n_small = sms_per_stack;

@@ -7,6 +7,8 @@ by ~2e-6):
     loss                                             : 5e-6 relative
     per-observation Euler step counts, preds_before at each first observation == 0 : exact
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -333,6 +335,44 @@ def test_one_call_batch_path_equals_cached_schedule_path(hidden, shared):
         c.schedule(desc)
         p2, b2 = model.forward_packed(c)
         assert torch.equal(p1, p2) and torch.equal(b1, b2)
+
+
+_TAIL_SCRIPT = r"""
+import sys, torch, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2])
+from test_gpu_parity import _random_batch, _grads_of
+from neural_jump_ode import NeuralJumpODE, PackedBatch
+torch.manual_seed(8)
+model = NeuralJumpODE(1, 32, 1, dt_ode_step=0.01, num_moments=2).to("cuda")
+batch = PackedBatch.from_lists(*_random_batch(2500, seed=12), device="cuda")
+p, b, loss, grads = _grads_of(model, batch, dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0]))
+sched = next(iter(batch._schedules.values()))
+torch.save(dict(p=p.cpu(), b=b.cpu(), loss=loss, grads=[g.cpu() for g in grads], n_tiles=sched.n_tiles,
+                rows=(sched.perm.view(-1, sched.tile_rows) >= 0).sum(1).cpu()), sys.argv[3])
+"""
+
+
+def test_tail_tile_plan_is_the_same_function(tmp_path):
+    """NJODE_TAIL_TILES=1 (read once per process) packs the longest units into quarter tiles, one per SM, and the rest
+    into full tiles (njode_tile_plan): a different tiling of the same batch -- same predictions bit for bit
+    (rows are independent), same loss and gradients to tolerance."""
+    import subprocess, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    pkg = os.path.join(os.path.dirname(here), "neural-jump-ode_b200")
+    outs = []
+    for tail in ("0", "1"):
+        out = str(tmp_path / f"tail{tail}.pt")
+        env = dict(os.environ, NJODE_TAIL_TILES=tail)
+        subprocess.run([sys.executable, "-c", _TAIL_SCRIPT, here, pkg, out], check=True, env=env, timeout=300)
+        outs.append(torch.load(out))
+    full, tail = outs
+    assert tail["n_tiles"] > full["n_tiles"]
+    assert int((tail["rows"] == 32).sum()) >= 64 and int((tail["rows"] == 128).sum()) >= 1     # quarter tiles, then full ones
+    assert int((full["rows"] == 32).sum()) == 0
+    assert torch.equal(full["p"], tail["p"]) and torch.equal(full["b"], tail["b"])
+    assert abs(full["loss"] - tail["loss"]) <= TOL_LOSS * abs(full["loss"])
+    for g1, g2 in zip(full["grads"], tail["grads"]):
+        assert rel_err(g2, g1) <= TOL
 
 
 def test_flatten_parameters_keeps_the_module_intact():

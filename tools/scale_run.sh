@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: tools/scale_run.sh N  -- the bench workloads on N GPUs of this box (weak scaling), JSON lines under gpurun_out/
+# usage: tools/scale_run.sh N ["ou heston64k ..."]  -- the bench workloads on N GPUs of this box (weak scaling), JSON lines under gpurun_out/
 N=$1
 run() { # name, args...
   local name=$1; shift
@@ -14,7 +14,12 @@ except Exception as e:
     print("${name} N=${N} ERR", e)
 PY
 }
-run ou --steps 20 --warmup 5
-run heston64k --workload heston_sep_b262144 --batch 65536 --steps 5 --warmup 3
-run mixed_h64 --workload mixed_h64_ragged --batch 32768 --steps 3 --warmup 3
-run h128 --workload heston_h128_l3 --batch 2048 --steps 3 --warmup 3
+WHICH=${2:-"ou heston64k mixed_h64 h128"}
+for w in $WHICH; do
+  case $w in
+    ou) run ou --steps 20 --warmup 5 ;;
+    heston64k) run heston64k --workload heston_sep_b262144 --batch 65536 --steps 5 --warmup 3 ;;
+    mixed_h64) run mixed_h64 --workload mixed_h64_ragged --batch 32768 --steps 3 --warmup 3 ;;
+    h128) run h128 --workload heston_h128_l3 --batch 2048 --steps 3 --warmup 3 ;;
+  esac
+done
