@@ -236,11 +236,13 @@ __global__ void k_transpose_params(ParamTable T, const float* __restrict__ p, fl
 
 // grad[i] = sum over the workers of stack s (fixed order) of their partial; partials are input-major
 // (transposed = 1, generic / row-tiled flavours) or PyTorch layout (transposed = 0).
-// Block = 32 elements x 8 worker groups: thread (e, g) adds the partials of workers g, g+8, ... of the element's
-// stack, the 8 group sums are combined through shared memory in a fixed order: deterministic for a given schedule.
-__global__ void __launch_bounds__(256) k_reduce_partials(ParamTable T, const float* __restrict__ partials, int n_workers,
-                                                         int transposed, float* __restrict__ grad, int64_t total) {
-  __shared__ float red[8][33];
+// Block = 32 elements x 32 worker groups: thread (e, g) adds the partials of workers g, g+32, ... of the element's
+// stack (independent loads: the 8-group version was a chain of ~18 dependent L2 round trips, 9 us), the 32 group sums
+// are combined through shared memory in a fixed order: deterministic for a given schedule.
+#define RED_GROUPS 32
+__global__ void __launch_bounds__(32 * RED_GROUPS) k_reduce_partials(ParamTable T, const float* __restrict__ partials, int n_workers,
+                                                                   int transposed, float* __restrict__ grad, int64_t total) {
+  __shared__ float red[RED_GROUPS][33];
   const int e_local = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int64_t i = (int64_t)blockIdx.x * 32 + e_local;
   float acc = 0.0f;
@@ -250,13 +252,15 @@ __global__ void __launch_bounds__(256) k_reduce_partials(ParamTable T, const flo
     s = i / T.stack_floats;
     e = (int)(i - s * T.stack_floats);
     const int per_stack = (n_workers - (int)s + T.S - 1) / T.S;       // workers of this stack: s, s + S, ...
-    for (int j = g; j < per_stack; j += 8) acc += partials[(int64_t)((int)s + j * T.S) * T.stack_floats + e];
+    for (int j = g; j < per_stack; j += RED_GROUPS) acc += partials[(int64_t)((int)s + j * T.S) * T.stack_floats + e];
   }
   red[g][e_local] = acc;
   __syncthreads();
   if (g != 0 || i >= total) return;
-  const float sum = ((red[0][e_local] + red[1][e_local]) + (red[2][e_local] + red[3][e_local])) +
-                    ((red[4][e_local] + red[5][e_local]) + (red[6][e_local] + red[7][e_local]));
+  float sum = 0.0f;
+#pragma unroll
+  for (int k = 0; k < RED_GROUPS; k += 4)
+    sum += (red[k][e_local] + red[k + 1][e_local]) + (red[k + 2][e_local] + red[k + 3][e_local]);
   int64_t dst = e;
   if (transposed) {
     int net, l;
@@ -503,7 +507,7 @@ extern "C" int njode_backward(const NjodeDesc* desc, const float* params, const 
   rc = impl == NJODE_IMPL_TILED ? njode_tiled_backward(a, st)
      : impl == NJODE_IMPL_ROWTILE ? njode_rowtile_backward(a, st) : njode_generic_backward(a, st);
   if (rc) return rc;
-  k_reduce_partials<<<(unsigned)((total + 31) / 32), 256, 0, st>>>(T, partials, a.n_workers,
+  k_reduce_partials<<<(unsigned)((total + 31) / 32), 32 * RED_GROUPS, 0, st>>>(T, partials, a.n_workers,
                                                                     impl == NJODE_IMPL_TILED ? 0 : 1, grad_params, total);
   NJODE_LAUNCH_OK("k_reduce_partials");
   return NJODE_OK;

@@ -12,12 +12,17 @@
 #include "njode_common.cuh"
 
 #define LOSS_TB 128
+#define LOSS_TRAJ_PER_BLOCK (LOSS_TB / 32)
 
+// One WARP per trajectory: lane l takes observations l, l + 32, ... (a thread per trajectory walked its ~10-100
+// observations serially, one dependent load chain each: 11 us for 4096 trajectories on 32 SMs); the lanes' sums are
+// combined by a fixed xor-shuffle tree, the block's 4 trajectories and then the blocks in double: deterministic.
 __global__ void __launch_bounds__(LOSS_TB)
 k_loss(NjodeLossDesc ld, const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ Yb,
        const int64_t* __restrict__ off, int64_t B, int d, int M, float traj_scale,
        float* __restrict__ gY, float* __restrict__ gYb, double* __restrict__ block_part) {
-  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t b = (int64_t)blockIdx.x * LOSS_TRAJ_PER_BLOCK + w;
   float traj_loss = 0.0f;
   if (b < B) {
     const int64_t lo = off[b], hi = off[b + 1];
@@ -27,7 +32,7 @@ k_loss(NjodeLossDesc ld, const float* __restrict__ X, const float* __restrict__ 
     const float g1 = ld.w1 * traj_scale * inv_n;
     const bool direct = ld.variance_method == NJODE_VAR_DIRECT;
     float sum0 = 0.0f, sum1 = 0.0f;
-    for (int64_t o = lo; o < hi; ++o) {
+    for (int64_t o = lo + lane; o < hi; o += 32) {
       const bool keep = !(ld.ignore_first_continuity && o == lo);
       const float* x = X + o * d;
       const float* y = Y + o * d * M;
@@ -38,10 +43,10 @@ k_loss(NjodeLossDesc ld, const float* __restrict__ X, const float* __restrict__ 
         a += e * e;
         c += eb * eb;
         if (M > 1) {
-          const float w = y[k * M + 1], wb = yb[k * M + 1];
+          const float w1 = y[k * M + 1], wb = yb[k * M + 1];
           const float z = direct ? e * e : x[k] * x[k];
           const float zb = direct ? eb * eb : x[k] * x[k];
-          const float v = direct ? w * w : w, vb = direct ? wb * wb : wb;
+          const float v = direct ? w1 * w1 : w1, vb = direct ? wb * wb : wb;
           va += (z - v) * (z - v);
           vc += (zb - vb) * (zb - vb);
         }
@@ -66,30 +71,34 @@ k_loss(NjodeLossDesc ld, const float* __restrict__ X, const float* __restrict__ 
           gy[k * M] = -2.0f * e * da;
           gyb[k * M] = -2.0f * eb * dc;
           if (M > 1) {
-            const float w = y[k * M + 1], wb = yb[k * M + 1];
+            const float w1 = y[k * M + 1], wb = yb[k * M + 1];
             const float z = direct ? e * e : x[k] * x[k];
             const float zb = direct ? eb * eb : x[k] * x[k];
-            const float v = direct ? w * w : w, vb = direct ? wb * wb : wb;
+            const float v = direct ? w1 * w1 : w1, vb = direct ? wb * wb : wb;
             // d (z-v)^2 / d w = -2 (z-v) * dv/dw ;  dv/dw = 2w (direct) or 1
-            gy[k * M + 1] = -2.0f * (z - v) * (direct ? 2.0f * w : 1.0f) * dva;
+            gy[k * M + 1] = -2.0f * (z - v) * (direct ? 2.0f * w1 : 1.0f) * dva;
             gyb[k * M + 1] = -2.0f * (zb - vb) * (direct ? 2.0f * wb : 1.0f) * dvc;
             for (int m = 2; m < M; ++m) { gy[k * M + m] = 0.0f; gyb[k * M + m] = 0.0f; }
           }
         }
       }
     }
+    for (int o = 16; o > 0; o >>= 1) {
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, o);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, o);
+    }
     traj_loss = ld.w0 * (sum0 * inv_n);
     if (M > 1) traj_loss += ld.w1 * (sum1 * inv_n);
   }
   // deterministic block sum in double
-  __shared__ double sh[LOSS_TB];
-  sh[threadIdx.x] = (double)traj_loss;
+  __shared__ double sh[LOSS_TRAJ_PER_BLOCK];
+  if (lane == 0) sh[w] = (double)traj_loss;
   __syncthreads();
-  for (int s = LOSS_TB / 2; s > 0; s >>= 1) {
-    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
-    __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < LOSS_TRAJ_PER_BLOCK; ++i) s += sh[i];
+    block_part[blockIdx.x] = s;
   }
-  if (threadIdx.x == 0) block_part[blockIdx.x] = sh[0];
 }
 
 __global__ void k_loss_final(const double* __restrict__ block_part, int64_t nblocks, float traj_scale,
@@ -107,7 +116,7 @@ __global__ void k_loss_final(const double* __restrict__ block_part, int64_t nblo
 }
 
 extern "C" size_t njode_loss_workspace_bytes(int64_t B) {
-  return (size_t)((B + LOSS_TB - 1) / LOSS_TB + 1) * sizeof(double);
+  return (size_t)((B + LOSS_TRAJ_PER_BLOCK - 1) / LOSS_TRAJ_PER_BLOCK + 1) * sizeof(double);
 }
 
 extern "C" int njode_loss(const NjodeLossDesc* ld, const float* values, const float* preds,
@@ -124,7 +133,7 @@ extern "C" int njode_loss(const NjodeLossDesc* ld, const float* values, const fl
     NJODE_FAIL(NJODE_EINVAL, "njode_loss: grad_preds and grad_preds_before must both be given or both be NULL");
   if (workspace_bytes < njode_loss_workspace_bytes(B)) NJODE_FAIL(NJODE_EWORKSPACE, "njode_loss: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t nblocks = (B + LOSS_TB - 1) / LOSS_TB;
+  const int64_t nblocks = (B + LOSS_TRAJ_PER_BLOCK - 1) / LOSS_TRAJ_PER_BLOCK;
   k_loss<<<(unsigned)nblocks, LOSS_TB, 0, st>>>(*ld, values, preds, preds_before, obs_offsets, B, d, M, traj_scale,
                                                 grad_preds, grad_preds_before, (double*)workspace);
   NJODE_LAUNCH_OK("k_loss");
