@@ -110,6 +110,42 @@ class OutputNN(nn.Module):
 # autograd glue: forward sweep / reverse sweep
 # ------------------------------------------------------------------------------------------------
 
+class _SweepState:
+    """What a reverse sweep needs, shared by the sweep's autograd node and -- through ``preds._njode_state`` -- by
+    ``nj_ode_loss``, which may run the reverse sweep EARLY (see ``_LossFunction``)."""
+    __slots__ = ("desc", "batch", "sched", "dp_group", "shapes", "flat", "ckpt", "versions", "params",
+                 "eager_ok", "early_grad", "early_key")
+
+    def reverse_sweep(self, g_preds, g_before):
+        """njode_backward (+ the data-parallel all-reduce): the flat parameter gradient for these output gradients."""
+        if self.ckpt is None:
+            raise RuntimeError("NeuralJumpODE: backward requested but the forward sweep ran without checkpoints")
+        if sum(p._version for p in self.params) != self.versions:
+            raise RuntimeError("NeuralJumpODE: a parameter was modified in place between the forward sweep and its "
+                               "backward (the reverse sweep reads the parameters where they live)")
+        lib = nat.load()
+        desc, batch, sched = self.desc, self.batch, self.sched
+        dev = batch.device
+        with nat.on_device(dev):
+            stream = nat.current_stream(dev)
+            g_preds = g_preds.contiguous().float()
+            g_before = g_before.contiguous().float()
+            grad_flat = torch.empty_like(self.flat)
+            ws_bytes = lib.njode_backward_workspace_bytes(desc, sched.n_tiles)
+            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+            nat.check(lib.njode_backward(desc, nat.ptr(self.flat), nat.ptr(batch.times), nat.ptr(batch.values),
+                                         nat.ptr(batch.offsets), batch.B, batch.N, *sched.ptrs,
+                                         sched.n_tiles, sched.total_slots, sched.tile_rows,
+                                         nat.ptr(g_preds), nat.ptr(g_before), nat.ptr(self.ckpt), nat.ptr(grad_flat),
+                                         nat.ptr(ws), ws_bytes, stream), "njode_backward")
+        if self.dp_group is not None:
+            # data parallel: the reverse sweep left this rank's share of the gradient (the loss is scaled by
+            # 1/B_global) in ONE flat buffer -- sum it over the ranks in place, no gather / scatter copies
+            import torch.distributed as dist
+            dist.all_reduce(grad_flat, op=dist.ReduceOp.SUM, group=None if self.dp_group is True else self.dp_group)
+        return grad_flat
+
+
 class _BatchPlan:
     """What the sweep needs to know about a batch before it runs (see NeuralJumpODE._begin_batch)."""
     __slots__ = ("tile_rows", "n_tiles", "row_floats", "key", "sched", "slots", "arena", "layout", "scratch", "scratch_bytes", "host")
@@ -175,54 +211,52 @@ class _SweepFunction(torch.autograd.Function):
                 sched = Schedule(arena, layout, N, tile_rows, n_tiles, host.tolist())
                 model._note_slots(N, B, n_tiles, sched.total_slots)
                 batch._schedules[key] = sched
-        ctx.desc, ctx.batch, ctx.sched = desc, batch, sched
-        ctx.dp_group = model._dp_group
-        ctx.shapes = [p.shape for p in params]
-        ctx.flat, ctx.ckpt = flat, ckpt
-        ctx.versions = sum(p._version for p in params)
-        ctx.params = params
+        st = _SweepState()
+        st.desc, st.batch, st.sched = desc, batch, sched
+        st.dp_group = model._dp_group
+        st.shapes = [p.shape for p in params]
+        st.flat, st.ckpt = flat, ckpt
+        st.versions = sum(p._version for p in params)
+        st.params = params
+        st.eager_ok = bool(model.eager_backward) and want_grad
+        st.early_grad = st.early_key = None
+        ctx.state = st
+        model._last_state = st
         return preds, before
 
     @staticmethod
     def backward(ctx, g_preds, g_before):
-        if ctx.ckpt is None:
-            raise RuntimeError("NeuralJumpODE: backward requested but the forward sweep ran without checkpoints")
-        if sum(p._version for p in ctx.params) != ctx.versions:
-            raise RuntimeError("NeuralJumpODE: a parameter was modified in place between the forward sweep and its "
-                               "backward (the reverse sweep reads the parameters where they live)")
-        lib = nat.load()
-        desc, batch, sched = ctx.desc, ctx.batch, ctx.sched
-        dev = batch.device
-        with nat.on_device(dev):
-            stream = nat.current_stream(dev)
-            g_preds = g_preds.contiguous().float()
-            g_before = g_before.contiguous().float()
-            grad_flat = torch.empty_like(ctx.flat)
-            ws_bytes = lib.njode_backward_workspace_bytes(desc, sched.n_tiles)
-            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
-            nat.check(lib.njode_backward(desc, nat.ptr(ctx.flat), nat.ptr(batch.times), nat.ptr(batch.values),
-                                         nat.ptr(batch.offsets), batch.B, batch.N, *sched.ptrs,
-                                         sched.n_tiles, sched.total_slots, sched.tile_rows,
-                                         nat.ptr(g_preds), nat.ptr(g_before), nat.ptr(ctx.ckpt), nat.ptr(grad_flat),
-                                         nat.ptr(ws), ws_bytes, stream), "njode_backward")
-        ctx.ckpt = None     # checkpoints are the big buffer: release them as soon as they are consumed
-        if ctx.dp_group is not None:
-            # data parallel: the reverse sweep left this rank's share of the gradient (the loss is scaled by
-            # 1/B_global) in ONE flat buffer -- sum it over the ranks in place, no gather / scatter copies
-            import torch.distributed as dist
-            dist.all_reduce(grad_flat, op=dist.ReduceOp.SUM, group=None if ctx.dp_group is True else ctx.dp_group)
+        st = ctx.state
+        early = st.early_grad
+        if early is not None and st.early_key is not None and st.early_key[0] == (g_preds.data_ptr(), g_before.data_ptr()):
+            # nj_ode_loss already ran the reverse sweep on its un-scaled gradients, and what arrives here is exactly
+            # those gradients times the loss's upstream gradient (same buffers): scale the result by it
+            if sum(p._version for p in st.params) != st.versions:
+                raise RuntimeError("NeuralJumpODE: a parameter was modified in place between the forward sweep and its "
+                                   "backward (the reverse sweep reads the parameters where they live)")
+            grad_flat = early * st.early_key[1]
+        else:
+            grad_flat = st.reverse_sweep(g_preds, g_before)
+        st.ckpt = st.early_grad = st.early_key = None     # checkpoints are the big buffer: release them once consumed
         # Stacks of moments >= 2 get an all-zero gradient from nj_ode_loss (jump_ode.py:328-378); the
         # reference reports zero tensors for them too (torch.stack backward), so nothing is special-cased.
-        grads = [g.view(shp) for g, shp in zip(grad_flat.split([shp.numel() for shp in ctx.shapes]), ctx.shapes)]
+        grads = [g.view(shp) for g, shp in zip(grad_flat.split([shp.numel() for shp in st.shapes]), st.shapes)]
         return (None, None, None, None, None, *grads)
 
 
 class _LossFunction(torch.autograd.Function):
     """nj_ode_loss value; d loss / d preds and d loss / d preds_before are closed-form and produced by
-    the same kernel pass (``njode_loss``)."""
+    the same kernel pass (``njode_loss``).
+
+    When ``preds`` / ``preds_before`` come straight from the model, the reverse sweep is launched HERE, on those
+    un-scaled gradients, instead of ~100 us later when the autograd engine reaches the sweep's node (thread hand-off,
+    two Python nodes): the GPU no longer idles between the loss and the reverse sweep.  The sweep's backward node
+    then only scales the finished parameter gradient by the loss's upstream gradient -- if what reaches it is not
+    exactly this loss's gradient buffers (a second loss on the same predictions, a hook) it runs the reverse sweep
+    itself as before.  ``model.eager_backward = False`` turns this off."""
 
     @staticmethod
-    def forward(ctx, ldesc, batch: PackedBatch, traj_scale: float, want_grad: bool, preds, before):
+    def forward(ctx, ldesc, batch: PackedBatch, traj_scale: float, want_grad: bool, state, preds, before):
         lib = nat.load()
         dev = preds.device
         N, d, M = preds.shape
@@ -239,7 +273,11 @@ class _LossFunction(torch.autograd.Function):
                                      nat.ptr(loss), nat.ptr(g[0]) if want_grad else None,
                                      nat.ptr(g[1]) if want_grad else None, nat.ptr(ws), ws_bytes, stream),
                       "njode_loss")
-        ctx.g = g
+            if state is not None and want_grad and state.eager_ok and state.ckpt is not None and state.early_grad is None:
+                state.early_grad = state.reverse_sweep(g[0], g[1])
+            else:
+                state = None
+        ctx.g, ctx.state = g, state
         return loss
 
     @staticmethod
@@ -247,7 +285,10 @@ class _LossFunction(torch.autograd.Function):
         if ctx.g is None:
             raise RuntimeError("nj_ode_loss: backward requested but gradients were not computed")
         scaled = ctx.g * g                      # one launch for both gradients
-        return None, None, None, None, scaled[0], scaled[1]
+        gp, gb = scaled[0], scaled[1]
+        if ctx.state is not None:
+            ctx.state.early_key = ((gp.data_ptr(), gb.data_ptr()), g, scaled)    # (scaled kept alive: its address is the key)
+        return None, None, None, None, None, gp, gb
 
 
 # ------------------------------------------------------------------------------------------------
@@ -295,6 +336,8 @@ class NeuralJumpODE(nn.Module):
         self.kernel_impl = "auto"                 # 'auto' | 'generic' | 'rowtile' | 'tiled' (testing / profiling knob)
         self._dp_group = None                     # see enable_data_parallel
         self.auto_flatten = True                  # see flatten_parameters
+        self.eager_backward = True                # see _LossFunction
+        self._last_state = None
         self._slots_memo, self._slots_per_tile = {}, 0.0
 
     def enable_data_parallel(self, group=True):
@@ -451,7 +494,11 @@ class NeuralJumpODE(nn.Module):
         desc = self.descriptor()
         plan = self._begin_batch(desc, batch)
         want_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        return _SweepFunction.apply(self, desc, batch, want_grad, plan, *params)
+        preds, before = _SweepFunction.apply(self, desc, batch, want_grad, plan, *params)
+        if want_grad:
+            preds._njode_state = before._njode_state = self._last_state     # lets nj_ode_loss start the reverse sweep early
+        self._last_state = None
+        return preds, before
 
     def forward(self, batch_times, batch_values=None):
         """batch_times / batch_values: lists of (n_i,) / (n_i, d_x) tensors (reference jump_ode.py:218-233),
@@ -538,4 +585,7 @@ def nj_ode_loss(batch_times, batch_values, preds, preds_before,
     ld.w0, ld.w1 = _moment_weights(moment_weights, M)
     scale = 1.0 / batch.B if traj_scale is None else float(traj_scale)
     want_grad = torch.is_grad_enabled() and (p.requires_grad or pb.requires_grad)
-    return _LossFunction.apply(ld, batch, scale, want_grad, p, pb)
+    state = getattr(p, "_njode_state", None)
+    if state is not None and (getattr(pb, "_njode_state", None) is not state or state.batch is not batch):
+        state = None
+    return _LossFunction.apply(ld, batch, scale, want_grad, state, p, pb)

@@ -375,6 +375,51 @@ def test_tail_tile_plan_is_the_same_function(tmp_path):
         assert rel_err(g2, g1) <= TOL
 
 
+def test_early_reverse_sweep_is_the_same_gradient():
+    """nj_ode_loss launches the reverse sweep itself when the predictions come straight from the model (the sweep's
+    backward node then only scales the result): same bits as the late path for loss.backward(), the upstream gradient
+    is honoured, and anything else reaching the node (a second loss on the same predictions) falls back to the late path."""
+    from neural_jump_ode import NeuralJumpODE, nj_ode_loss, PackedBatch
+    torch.manual_seed(9)
+    model = NeuralJumpODE(1, 32, 1, dt_ode_step=0.01, num_moments=2).to(DEV)
+    lk = dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0])
+    lk2 = dict(ignore_first_continuity=False, moment_weights=[2.0, 1.0])
+    bt, bv = _random_batch(300, seed=21)
+    batch = PackedBatch.from_lists(bt, bv, device=DEV)
+
+    def run(eager, how):
+        model.eager_backward = eager
+        model.zero_grad(set_to_none=True)
+        if how == "lists":
+            btc, bvc = [t.to(DEV) for t in bt], [v.to(DEV) for v in bv]
+            p, b = model(btc, bvc)
+            nj_ode_loss(btc, bvc, p, b, **lk).backward()
+        else:
+            p, b = model.forward_packed(batch)
+            if how == "plain":
+                nj_ode_loss(batch, None, p, b, **lk).backward()
+            elif how == "times3":
+                (3.0 * nj_ode_loss(batch, None, p, b, **lk)).backward()
+            elif how == "two_losses":
+                (nj_ode_loss(batch, None, p, b, **lk) + nj_ode_loss(batch, None, p, b, **lk2)).backward()
+            elif how == "never":
+                nj_ode_loss(batch, None, p, b, **lk)            # early sweep runs, backward never asked for
+                return None
+        return [q.grad.clone() for q in model.flat_parameters()]
+
+    late = run(False, "plain")
+    for how in ("plain", "lists"):
+        for g1, g2 in zip(run(True, how), late):
+            assert torch.equal(g1, g2), how
+    for g1, g2 in zip(run(True, "times3"), late):
+        assert rel_err(g1, 3.0 * g2) <= 1e-6
+    for g1, g2 in zip(run(True, "two_losses"), run(False, "two_losses")):
+        assert torch.equal(g1, g2)
+    run(True, "never")
+    for g1, g2 in zip(run(True, "plain"), late):
+        assert torch.equal(g1, g2)
+
+
 def test_flatten_parameters_keeps_the_module_intact():
     """The sweeps read the parameters from one flat buffer (model.flatten_parameters, automatic): Parameter objects,
     state_dict, torch optimizers and .to() keep working, and the flat view follows in-place updates."""
