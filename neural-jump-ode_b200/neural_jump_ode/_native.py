@@ -76,16 +76,6 @@ SIGNATURES = {
     "njode_kernel_launches": (_I64, [_I32]),
 }
 
-# kernels launched by each ABI call (bench.py's gpu_launches claim): name -> count
-KERNELS_PER_CALL = {"njode_schedule_build": 4, "njode_schedule_knots": 1, "njode_forward": 2, "njode_forward_batch": 7, "njode_forward_batch_begin": 4, "njode_forward_batch_finish": 3, "njode_loss": 2,
-                    "njode_backward": 3, "njode_adam_step": 1}
-launch_count = 0
-
-
-def count(name):
-    global launch_count
-    launch_count += KERNELS_PER_CALL[name]
-
 _lib = None
 
 
@@ -116,8 +106,6 @@ def load():
 
 
 def check(rc, what):
-    global launch_count
-    launch_count += KERNELS_PER_CALL.get(what, 0)
     if rc != 0:
         msg = load().njode_last_error().decode(errors="replace")
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
