@@ -60,6 +60,17 @@ __device__ __forceinline__ void stage(float* __restrict__ dst, const float* __re
   for (; i < count; i += NTH) dst[i] = src[i];
 }
 
+// 16 bytes from SHARED memory (explicit: through these pointers the compiler emitted generic LD.E.128)
+__device__ __forceinline__ float4 lds128(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+  return v;
+}
+
+__device__ __forceinline__ void sts128(float* p, float4 v) {
+  asm volatile("st.shared.v4.f32 [%4], {%0,%1,%2,%3};" :: "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+}
+
 // acc[i][j] = sum_k in_T[k][4*ty + i] * W[k * ldw + tx + 32*j]   for columns < N   (all 256 threads)
 template <int NB>
 __device__ __forceinline__ void gemm(const float* __restrict__ in_T, int K, const float* __restrict__ W, int ldw, int N,
@@ -74,7 +85,7 @@ __device__ __forceinline__ void gemm(const float* __restrict__ in_T, int K, cons
   if (full) {
 #pragma unroll 4
     for (int k = 0; k < K; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(a_ptr + k * LDA);
+      const float4 a = lds128(a_ptr + k * LDA);
       const float* w = W + k * ldw + tx;
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
@@ -87,7 +98,7 @@ __device__ __forceinline__ void gemm(const float* __restrict__ in_T, int K, cons
     }
   } else {
     for (int k = 0; k < K; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(a_ptr + k * LDA);
+      const float4 a = lds128(a_ptr + k * LDA);
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
         const int n = tx + 32 * j;
@@ -108,7 +119,7 @@ __device__ __forceinline__ void put_tile(float* __restrict__ buf, const Tile<NB>
 #pragma unroll
   for (int j = 0; j < NB; ++j) {
     const int n = tx + 32 * j;
-    if (n < N) *reinterpret_cast<float4*>(buf + n * LDA + 4 * ty) = make_float4(t.v[0][j], t.v[1][j], t.v[2][j], t.v[3][j]);
+    if (n < N) sts128(buf + n * LDA + 4 * ty, make_float4(t.v[0][j], t.v[1][j], t.v[2][j], t.v[3][j]));
   }
 }
 template <int NB>
@@ -118,7 +129,7 @@ __device__ __forceinline__ void get_tile(const float* __restrict__ buf, Tile<NB>
   for (int j = 0; j < NB; ++j) {
     const int n = tx + 32 * j;
     float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (n < N) q = *reinterpret_cast<const float4*>(buf + n * LDA + 4 * ty);
+    if (n < N) q = lds128(buf + n * LDA + 4 * ty);
     t.v[0][j] = q.x; t.v[1][j] = q.y; t.v[2][j] = q.z; t.v[3][j] = q.w;
   }
 }
@@ -210,9 +221,9 @@ __device__ __forceinline__ void layer_wgrad(const ParamTable& T, int net, int l,
     for (int c = 0; c < RT; c += 4) {
       float4 dv[4], iv[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) dv[i] = *reinterpret_cast<const float4*>(dj[i] + c);
+      for (int i = 0; i < 4; ++i) dv[i] = lds128(dj[i] + c);
 #pragma unroll
-      for (int m = 0; m < 4; ++m) iv[m] = *reinterpret_cast<const float4*>(ik[m] + c);
+      for (int m = 0; m < 4; ++m) iv[m] = lds128(ik[m] + c);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -242,7 +253,7 @@ __device__ __forceinline__ void layer_wgrad(const ParamTable& T, int net, int l,
     const float* dr = d_T + j * LDA;
     float s = 0.0f;
 #pragma unroll
-    for (int c = 0; c < RT; c += 4) { const float4 q = *reinterpret_cast<const float4*>(dr + c); s += (q.x + q.y) + (q.z + q.w); }
+    for (int c = 0; c < RT; c += 4) { const float4 q = lds128(dr + c); s += (q.x + q.y) + (q.z + q.w); }
     atomicAdd(&gb[j], s);
   }
 }
