@@ -34,6 +34,7 @@ for it in range(n + 10):
     torch.cuda.synchronize()
     clock("sched_ws_bytes", lambda: lib.njode_schedule_workspace_bytes(B, N, tile_rows))
     clock("schedule_build", lambda: lib.njode_schedule_build(desc, nat.ptr(batch.times), nat.ptr(batch.offsets), B, N, tile_rows, at(0), at(1), at(2), at(3), at(4), nat.ptr(ws), ws_b, st))
+    t0 = time.perf_counter(); torch.cuda.synchronize(); acc["schedule_build drain (device time left after the launch returns)"] = acc.get("schedule_build drain (device time left after the launch returns)", 0.0) + time.perf_counter() - t0
     clock("schedule_knots", lambda: lib.njode_schedule_knots(nat.ptr(batch.times), at(0), at(1), at(2), at(3), N, n_tiles, tile_rows, desc, at(5), st))
     clock("forward", lambda: lib.njode_forward(desc, nat.ptr(flat), nat.ptr(batch.times), nat.ptr(batch.values), nat.ptr(batch.offsets), B, N, at(0), at(1), at(2), at(3), at(5), n_tiles, s.total_slots, tile_rows, nat.ptr(out[0]), nat.ptr(out[1]), nat.ptr(ck), nat.ptr(fws), fws_b, st))
     torch.cuda.synchronize()
