@@ -94,6 +94,42 @@ def test_abi_param_count_and_validation():
     assert b"n_hidden_layers" in lib.njode_last_error()
 
 
+def test_abi_tiling_and_arena_layout():
+    """Host-only arithmetic of the ABI: tiles per batch (njode_num_tiles: quarter / half / full tiles for the tcgen05
+    flavour, 32-row tiles otherwise) and the arena layout of njode_forward_batch (256-byte aligned, knots last, only
+    the knots depend on the slot count).  No kernel is launched."""
+    import ctypes as C
+    from neural_jump_ode import NeuralJumpODE, _native as nat
+    lib = nat.load()
+    tiled = NeuralJumpODE(1, 32, 1, dt_ode_step=0.01, num_moments=2, shared_network=True).descriptor()
+    rowt = NeuralJumpODE(1, 64, 1, dt_ode_step=0.01, num_moments=2).descriptor()
+    assert lib.njode_tile_rows(tiled) == 128 and lib.njode_tile_rows(rowt) == 32
+    assert lib.njode_ckpt_row_floats(tiled) == 64 and lib.njode_ckpt_row_floats(rowt) == 128
+    sms = 148                                            # what the library assumes when it cannot ask a device
+    for N in (0, 1, 31, 32, 33, 1000, 4 * 128 * sms // 4, 40960, 10 ** 6):
+        full = (N + 127) // 128
+        units = 32 if 4 * full <= sms else 64 if full <= sms else 128
+        assert lib.njode_num_tiles(tiled, N) == (N + units - 1) // units, N
+        assert lib.njode_num_tiles(rowt, N) == (N + 31) // 32, N
+    assert lib.njode_num_tiles(tiled, -1) == -1
+    for desc in (tiled, rowt):
+        rows = lib.njode_tile_rows(desc)
+        for N, B in ((1, 1), (40960, 4096), (10 ** 6, 10 ** 5)):
+            lay0, lay1 = (C.c_int64 * nat.ARENA_WORDS)(), (C.c_int64 * nat.ARENA_WORDS)()
+            fixed = lib.njode_batch_arena_bytes(desc, B, N, 0, lay0)
+            slots = 12345
+            total = lib.njode_batch_arena_bytes(desc, B, N, slots, lay1)
+            assert list(lay0) == list(lay1)              # nothing but the size depends on the slot count
+            offs = [lay1[w] for w in (nat.ARENA_KENC, nat.ARENA_PERM, nat.ARENA_TILE_KMAX, nat.ARENA_TILE_SLOT_OFF,
+                                      nat.ARENA_HEADER, nat.ARENA_KNOTS)]
+            assert offs[0] == 0 and offs == sorted(offs) and all(o % 256 == 0 for o in offs)
+            n_tiles = lib.njode_num_tiles(desc, N)
+            assert offs[1] - offs[0] >= 4 * N and offs[2] - offs[1] >= 4 * n_tiles * rows
+            assert offs[4] - offs[3] >= 8 * (n_tiles + 1) and offs[5] - offs[4] >= 8 * nat.HDR_WORDS
+            assert fixed <= total and total - offs[5] >= 4 * slots * rows and total % 256 == 0
+            assert lib.njode_batch_scratch_bytes(desc, B, N) >= lib.njode_schedule_workspace_bytes(B, N, rows)
+
+
 def test_packed_batch_host_logic():
     from neural_jump_ode import PackedBatch
     bt = [torch.tensor([0.0, 0.5, 1.0]), torch.tensor([0.0, 0.3])]
