@@ -130,6 +130,22 @@ def test_abi_tiling_and_arena_layout():
             assert lib.njode_batch_scratch_bytes(desc, B, N) >= lib.njode_schedule_workspace_bytes(B, N, rows)
 
 
+def test_slot_guess_bookkeeping():
+    """The checkpoint-slot guess for a batch whose schedule is not known yet: exact for a batch shape seen before,
+    else the largest slots-per-tile ratio seen (+3 %), and 0 (= size exactly after the schedule is built) at first."""
+    from neural_jump_ode import NeuralJumpODE
+    m = NeuralJumpODE(1, 32, 1, dt_ode_step=0.01)
+    assert m._guess_slots(1000, 100, 8) == 0
+    m._note_slots(1000, 100, 8, 90)
+    assert m._guess_slots(1000, 100, 8) == 90                       # same shape: exact
+    assert m._guess_slots(2000, 200, 16) == int(90 / 8 * 16 * 1.03) + 2
+    m._note_slots(500, 50, 4, 80)                                   # a batch with longer gaps raises the ratio
+    assert m._guess_slots(2000, 200, 16) == int(20.0 * 16 * 1.03) + 2
+    for i in range(300):                                            # the exact-shape memo is bounded
+        m._note_slots(10000 + i, 7, 3, 5)
+    assert len(m._slots_memo) <= 257
+
+
 def test_packed_batch_host_logic():
     from neural_jump_ode import PackedBatch
     bt = [torch.tensor([0.0, 0.5, 1.0]), torch.tensor([0.0, 0.3])]
