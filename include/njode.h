@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define NJODE_ABI_VERSION 1
+#define NJODE_ABI_VERSION 2
 
 enum {
   NJODE_OK = 0,
@@ -65,8 +65,9 @@ enum { NJODE_ACT_RELU = 0, NJODE_ACT_TANH = 1, NJODE_ACT_SIGMOID = 2, NJODE_ACT_
 enum { NJODE_SCALE_IDENTITY = 0, NJODE_SCALE_TANH = 1, NJODE_SCALE_SIGMOID = 2 };
 /* jump_ode.py:333 / :346 */
 enum { NJODE_VAR_DIRECT = 0, NJODE_VAR_SECOND_MOMENT = 1 };
-/* kernel flavour: AUTO picks TILED when the shape is supported, else GENERIC */
-enum { NJODE_IMPL_AUTO = 0, NJODE_IMPL_GENERIC = 1, NJODE_IMPL_TILED = 2, NJODE_IMPL_ROWTILE = 3 };
+/* kernel flavour: AUTO picks TILED (tcgen05, hidden 32 / 1 layer), then WIDE (tcgen05, hidden 64 / 128, <= 3 layers),
+ * then ROWTILE (FP32 FMA), then GENERIC */
+enum { NJODE_IMPL_AUTO = 0, NJODE_IMPL_GENERIC = 1, NJODE_IMPL_TILED = 2, NJODE_IMPL_ROWTILE = 3, NJODE_IMPL_WIDE = 4 };
 
 typedef struct NjodeDesc {
   int32_t d_x;              /* input_dim */
@@ -93,7 +94,7 @@ typedef struct NjodeLossDesc {
 
 /* schedule header written by njode_schedule_build (device int64[8]) */
 enum { NJODE_HDR_TOTAL_STEPS = 0,   /* sum over trajectories of Euler steps ("trajectory-ODE-steps") */
-       NJODE_HDR_TOTAL_SLOTS = 1,   /* checkpoint slots: sum over tiles of (kmax_tile + 1) */
+       NJODE_HDR_TOTAL_SLOTS = 1,   /* checkpoint slots: sum over tiles of (kmax_tile + 1 + flavour extras) */
        NJODE_HDR_NUM_TILES = 2,
        NJODE_HDR_KMAX = 3,
        NJODE_HDR_WORDS = 8 };
@@ -108,6 +109,8 @@ int32_t njode_num_stacks(const NjodeDesc* desc);
 
 /* rows per tile of the kernel flavour that (desc) selects; the schedule is built for it */
 int32_t njode_tile_rows(const NjodeDesc* desc);
+/* the flavour (NJODE_IMPL_*, never AUTO) that runs for this descriptor; -1 on a bad / unsupported descriptor */
+int32_t njode_selected_impl(const NjodeDesc* desc);
 
 /* ---- step schedule (jump_ode.py:188-203, float32 accumulation reproduced bit for bit) ---------
  * build: kenc[o] = (K_o << 1) | has_next_o ; perm = units sorted by K descending, padded with -1
@@ -129,7 +132,8 @@ int njode_schedule_knots(const float* times, const int32_t* kenc, const int32_t*
  * ckpt: float32 [S][total_slots][tile_rows * Hc] per-slot checkpoints (Hc = njode_ckpt_row_floats): the hidden
  *       state before every Euler step and after the last one, plus -- tiled / row-tiled flavours -- the ODE
  *       net's hidden-layer outputs of that step; opaque to the caller, written by njode_forward and read by
- *       njode_backward.  Pass NULL for inference (no checkpoints written).
+ *       njode_backward (the WIDE flavour's reverse sweep also WRITES its half of the buffer: per-layer data
+ *       gradients for the weight-gradient GEMM).  Pass NULL for inference (no checkpoints written).
  * workspace: njode_forward_workspace_bytes (re-laid-out weights). */
 int64_t njode_ckpt_row_floats(const NjodeDesc* desc);
 /* Number of tiles the schedule of N observation units has (tiles hold tile_rows rows, of which a flavour- and
@@ -198,7 +202,7 @@ int njode_backward(const NjodeDesc* desc, const float* params, const float* time
                    const int32_t* kenc, const int32_t* perm, const int32_t* tile_kmax,
                    const int64_t* tile_slot_off, const float* knots,
                    int64_t n_tiles, int64_t total_slots, int32_t tile_rows,
-                   const float* grad_preds, const float* grad_preds_before, const float* ckpt,
+                   const float* grad_preds, const float* grad_preds_before, float* ckpt,
                    float* grad_params, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- Adam on the flat parameter buffer (torch.optim.Adam semantics, weight_decay as L2-in-grad) --
@@ -209,14 +213,16 @@ int njode_adam_step(float* params, const float* grads, float* exp_avg, float* ex
 
 
 /* ---- measurement hooks (bench.py) ---------------------------------------------------------------
- * njode_set_kernel_timing: the next njode_forward (which=1) / njode_backward (which=2) call records the
- * two caller-owned cudaEvent_t around its main sweep kernel only (on the call's stream).  One-shot;
+ * njode_set_kernel_timing: the next njode_forward (which=1) / njode_backward (which=2; which=3: the WIDE flavour's
+ * weight-gradient GEMM) call records the two caller-owned cudaEvent_t around that kernel only (on the call's stream).  One-shot;
  * pass NULLs to clear.  njode_ffma_peak: runs an FFMA-only kernel on the current device and returns the
  * measured dense FP32 FMA throughput in TFLOP/s (the roofline denominator of the FP32 path; it is not
  * in MEASURED_PEAKS.json).  Synchronises the device. */
 int njode_set_kernel_timing(int32_t which, void* ev_start, void* ev_stop);
-/* sticky device-side diagnostic word of the tiled kernels (0 = healthy; bit 0 / bit 1: a forward / reverse
- * sweep CTA gave up waiting on an MMA-completion barrier).  Synchronises the device. */
+/* sticky device-side diagnostic word of the tcgen05 kernels (0 = healthy; bit 0 / 1: a TILED forward / reverse
+ * sweep CTA gave up waiting on an mbarrier; bit 2 / 3 / 4: WIDE forward / reverse / weight-gradient).  A kernel that
+ * gives up TRAPS after setting its bit, so every later CUDA call on the context fails: a protocol failure can never
+ * yield silently wrong numbers.  Synchronises the device. */
 int njode_device_status(uint32_t* status_host);
 /* Number of CUDA kernels this library has launched in this process (every launch site counts itself);
  * reset != 0 returns the count and sets it to zero.  Measurement aid for bench.py's `gpu_launches`. */

@@ -6,6 +6,10 @@
 #include <string.h>
 
 #include "njode_common.cuh"
+#include "njode_wide.cuh"
+
+int njode_wide_sweep_status(unsigned* out_host);
+int njode_wide_wgrad_status(unsigned* out_host);
 
 static thread_local char g_err[512] = "";
 
@@ -20,9 +24,9 @@ extern "C" const char* njode_last_error(void) { return g_err; }
 
 // ---- measurement hooks -------------------------------------------------------------------------
 #include <atomic>
-static std::atomic<void*> g_ev[3][2];
+static std::atomic<void*> g_ev[4][2];
 extern "C" int njode_set_kernel_timing(int32_t which, void* ev_start, void* ev_stop) {
-  if (which < 1 || which > 2) NJODE_FAIL(NJODE_EINVAL, "njode_set_kernel_timing: which must be 1 (forward) or 2 (backward)");
+  if (which < 1 || which > 3) NJODE_FAIL(NJODE_EINVAL, "njode_set_kernel_timing: which must be 1 (forward), 2 (backward) or 3 (weight-gradient GEMM)");
   g_ev[which][0].store(ev_start);
   g_ev[which][1].store(ev_stop);
   return NJODE_OK;
@@ -91,9 +95,11 @@ extern "C" int64_t njode_kernel_launches(int32_t reset) {
 
 extern "C" int njode_device_status(uint32_t* status_host) {
   if (!status_host) NJODE_FAIL(NJODE_EINVAL, "njode_device_status: null output");
-  unsigned v = 0;
-  const int rc = njode_tiled_status(&v);
-  *status_host = v;
+  unsigned v = 0, w1 = 0, w2 = 0;
+  int rc = njode_tiled_status(&v);
+  if (!rc) rc = njode_wide_sweep_status(&w1);
+  if (!rc) rc = njode_wide_wgrad_status(&w2);
+  *status_host = v | w1 | w2;
   return rc;
 }
 
@@ -112,8 +118,9 @@ extern "C" int64_t njode_param_count(const NjodeDesc* d) {
   return per < 0 ? -1 : per * njode_num_stacks(d);
 }
 
-// which flavour runs for this descriptor: 0 = error, else NJODE_IMPL_GENERIC / _TILED / _ROWTILE.
-// AUTO prefers the tcgen05 tiled kernels (hidden 32, one layer), then the row-tiled FP32 kernels, then generic.
+// which flavour runs for this descriptor: 0 = error, else NJODE_IMPL_GENERIC / _TILED / _ROWTILE / _WIDE.
+// AUTO prefers the tcgen05 kernels (tiled: hidden 32, one layer; wide: hidden 64 / 128, <= 3 layers), then the
+// row-tiled FP32 kernels, then generic.
 static int pick_impl(const NjodeDesc* d, const char** why) {
   if (!njode_desc_ok(d, why)) return 0;
   if (d->impl == NJODE_IMPL_TILED) {
@@ -124,7 +131,12 @@ static int pick_impl(const NjodeDesc* d, const char** why) {
     if (!njode_rowtile_supported(d)) { *why = "impl=ROWTILE requested but this shape is not supported by the row-tiled kernels"; return 0; }
     return NJODE_IMPL_ROWTILE;
   }
+  if (d->impl == NJODE_IMPL_WIDE) {
+    if (!njode_wide_supported(d)) { *why = "impl=WIDE requested but this shape is not supported by the wide tcgen05 kernels"; return 0; }
+    return NJODE_IMPL_WIDE;
+  }
   if (d->impl == NJODE_IMPL_AUTO && njode_tiled_supported(d)) return NJODE_IMPL_TILED;
+  if (d->impl == NJODE_IMPL_AUTO && njode_wide_supported(d)) return NJODE_IMPL_WIDE;
   if (d->impl == NJODE_IMPL_AUTO && njode_rowtile_supported(d)) return NJODE_IMPL_ROWTILE;
   if (d->impl != NJODE_IMPL_AUTO && d->impl != NJODE_IMPL_GENERIC) { *why = "unknown impl code"; return 0; }
   if (!njode_generic_supported(d, why)) return 0;
@@ -135,7 +147,19 @@ extern "C" int32_t njode_tile_rows(const NjodeDesc* d) {
   const char* why = nullptr;
   const int impl = pick_impl(d, &why);
   if (!impl) { njode_set_error("njode_tile_rows: %s", why); return -1; }
-  return impl == NJODE_IMPL_TILED ? NJODE_TILED_TILE_ROWS : NJODE_GENERIC_TILE_ROWS;
+  return (impl == NJODE_IMPL_TILED || impl == NJODE_IMPL_WIDE) ? NJODE_TILED_TILE_ROWS : NJODE_GENERIC_TILE_ROWS;
+}
+
+extern "C" int32_t njode_selected_impl(const NjodeDesc* d) {
+  const char* why = nullptr;
+  const int impl = pick_impl(d, &why);
+  if (!impl) { njode_set_error("njode_selected_impl: %s", why); return -1; }
+  return impl;
+}
+
+int32_t njode_slot_extra(const NjodeDesc* d) {
+  const char* why = nullptr;
+  return pick_impl(d, &why) == NJODE_IMPL_WIDE ? NJODE_WIDE_XSLOTS : 0;
 }
 
 static int sm_count_abi() {
@@ -147,6 +171,7 @@ static int sm_count_abi() {
 int32_t njode_tile_units(const NjodeDesc* d, int64_t N) {
   const char* why = nullptr;
   const int impl = pick_impl(d, &why);
+  if (impl == NJODE_IMPL_WIDE) return NJODE_TILED_TILE_ROWS;     // always full tiles: the weight stream is per tile-step
   if (impl != NJODE_IMPL_TILED) return NJODE_GENERIC_TILE_ROWS;
   const int S = d->shared_network ? 1 : d->num_moments;
   const int64_t full_tiles = (N + NJODE_TILED_TILE_ROWS - 1) / NJODE_TILED_TILE_ROWS;
@@ -200,6 +225,8 @@ extern "C" int64_t njode_ckpt_row_floats(const NjodeDesc* d) {
   if (impl == NJODE_IMPL_TILED) return 2 * d->hidden;
   // the row-tiled kernels keep every hidden-layer output of the ODE net (no re-computation in the reverse sweep)
   if (impl == NJODE_IMPL_ROWTILE) return (int64_t)(1 + d->n_hidden_layers) * d->hidden;
+  // wide: (L + 1) activation planes + (L + 1) data-gradient planes + 8 aux floats per row and slot (njode_wide.cuh)
+  if (impl == NJODE_IMPL_WIDE) return (int64_t)2 * (1 + d->n_hidden_layers) * d->hidden + 8;
   return d->hidden;
 }
 
@@ -284,7 +311,7 @@ static int check_common(const char* fn, const NjodeDesc* desc, const float* para
   if (!*impl) NJODE_FAIL(NJODE_EINVAL, "%s: %s", fn, why);
   if (!params || (N > 0 && (!times || !values))) NJODE_FAIL(NJODE_EINVAL, "%s: null input pointer", fn);
   if (B < 0 || N < 0) NJODE_FAIL(NJODE_EINVAL, "%s: negative size", fn);
-  const int want = *impl == NJODE_IMPL_TILED ? NJODE_TILED_TILE_ROWS : NJODE_GENERIC_TILE_ROWS;
+  const int want = (*impl == NJODE_IMPL_TILED || *impl == NJODE_IMPL_WIDE) ? NJODE_TILED_TILE_ROWS : NJODE_GENERIC_TILE_ROWS;
   if (tile_rows != want) NJODE_FAIL(NJODE_EINVAL, "%s: schedule was built for tile_rows=%d, kernels need %d", fn, tile_rows, want);
   if (n_tiles != njode_tile_plan(desc, N).n_tiles) NJODE_FAIL(NJODE_EINVAL, "%s: n_tiles does not match N (njode_num_tiles)", fn);
   return NJODE_OK;
@@ -310,13 +337,22 @@ static size_t params_bytes(const NjodeDesc* d) {
   return njode_align_up((size_t)njode_param_count(d) * sizeof(float), 256);
 }
 
+// wide flavour: the workspace holds the split / swizzled weight images instead of the transposed parameters
+static size_t relayout_bytes(const NjodeDesc* desc) {
+  const char* why = nullptr;
+  if (pick_impl(desc, &why) == NJODE_IMPL_WIDE) return njode_wide_image_bytes(desc) + 1024;
+  return params_bytes(desc);
+}
+static float* image_ptr(void* workspace) { return (float*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023); }
+
 extern "C" size_t njode_forward_workspace_bytes(const NjodeDesc* desc) {
   if (njode_param_count(desc) < 0) return 0;
-  return params_bytes(desc);
+  return relayout_bytes(desc);
 }
 
 static int workers_for(const NjodeDesc* desc, int impl, int64_t n_tiles) {
   if (impl == NJODE_IMPL_TILED) return njode_tiled_workers(desc, n_tiles);
+  if (impl == NJODE_IMPL_WIDE) return njode_wide_workers(desc, n_tiles);
   if (impl == NJODE_IMPL_ROWTILE) return njode_rowtile_workers(desc, n_tiles);
   return njode_generic_workers(desc, n_tiles);
 }
@@ -327,7 +363,7 @@ extern "C" size_t njode_backward_workspace_bytes(const NjodeDesc* desc, int64_t 
   if (!impl) { njode_set_error("njode_backward_workspace_bytes: %s", why); return 0; }
   const ParamTable T = njode_make_table(desc);
   const int nw = workers_for(desc, impl, n_tiles);
-  return params_bytes(desc) + njode_align_up((size_t)nw * T.stack_floats * sizeof(float), 256);
+  return njode_align_up(relayout_bytes(desc), 256) + njode_align_up((size_t)nw * T.stack_floats * sizeof(float), 256);
 }
 
 static int relayout(const NjodeDesc* desc, const float* params, float* params_t, cudaStream_t st) {
@@ -355,7 +391,7 @@ extern "C" int njode_forward(const NjodeDesc* desc, const float* params, const f
   cudaStream_t st = (cudaStream_t)stream;
   if (N == 0) return NJODE_OK;
   float* params_t = (float*)workspace;
-  if (impl != NJODE_IMPL_TILED) {          // the tcgen05 kernels build their own (split, swizzled) weight tiles
+  if (impl != NJODE_IMPL_TILED && impl != NJODE_IMPL_WIDE) {   // the tcgen05 kernels build their own (split, swizzled) weight tiles
     rc = relayout(desc, params, params_t, st);
     if (rc) return rc;
   }
@@ -366,6 +402,7 @@ extern "C" int njode_forward(const NjodeDesc* desc, const float* params, const f
   // preds_before of each trajectory's first observation stays 0 (jump_ode.py:161)
   NJODE_CUDA_OK(cudaMemsetAsync(preds_before, 0, (size_t)N * desc->d_y * desc->num_moments * sizeof(float), st));
   if (impl == NJODE_IMPL_TILED) return njode_tiled_forward(a, st);
+  if (impl == NJODE_IMPL_WIDE) return njode_wide_forward(a, image_ptr(workspace), st);
   if (impl == NJODE_IMPL_ROWTILE) return njode_rowtile_forward(a, st);
   return njode_generic_forward(a, st);
 }
@@ -477,7 +514,7 @@ extern "C" int njode_backward(const NjodeDesc* desc, const float* params, const 
                               const int32_t* kenc, const int32_t* perm, const int32_t* tile_kmax,
                               const int64_t* tile_slot_off, const float* knots,
                               int64_t n_tiles, int64_t total_slots, int32_t tile_rows,
-                              const float* grad_preds, const float* grad_preds_before, const float* ckpt,
+                              const float* grad_preds, const float* grad_preds_before, float* ckpt,
                               float* grad_params, void* workspace, size_t workspace_bytes, void* stream) {
   int impl = 0;
   int rc = check_common("njode_backward", desc, params, times, values, B, N, n_tiles, tile_rows, &impl);
@@ -493,22 +530,24 @@ extern "C" int njode_backward(const NjodeDesc* desc, const float* params, const 
   if (workspace_bytes < njode_backward_workspace_bytes(desc, n_tiles))
     NJODE_FAIL(NJODE_EWORKSPACE, "njode_backward: workspace too small");
   float* params_t = (float*)workspace;
-  float* partials = (float*)((char*)workspace + params_bytes(desc));
-  if (impl != NJODE_IMPL_TILED) {
+  float* partials = (float*)((char*)workspace + njode_align_up(relayout_bytes(desc), 256));
+  if (impl != NJODE_IMPL_TILED && impl != NJODE_IMPL_WIDE) {
     rc = relayout(desc, params, params_t, st);
     if (rc) return rc;
   }
   SweepArgs a = make_args(desc, params, params_t, times, values, kenc, perm, tile_kmax, tile_slot_off, knots, N, n_tiles,
                           total_slots, tile_rows);
-  a.grad_preds = grad_preds; a.grad_preds_before = grad_preds_before; a.ckpt = const_cast<float*>(ckpt);
+  a.grad_preds = grad_preds; a.grad_preds_before = grad_preds_before; a.ckpt = ckpt;
   a.partials = partials;
   a.n_workers = workers_for(desc, impl, n_tiles);
   NJODE_CUDA_OK(cudaMemsetAsync(partials, 0, (size_t)a.n_workers * T.stack_floats * sizeof(float), st));
   rc = impl == NJODE_IMPL_TILED ? njode_tiled_backward(a, st)
+     : impl == NJODE_IMPL_WIDE ? njode_wide_backward(a, image_ptr(workspace), st)
      : impl == NJODE_IMPL_ROWTILE ? njode_rowtile_backward(a, st) : njode_generic_backward(a, st);
   if (rc) return rc;
+  const int pytorch_layout = (impl == NJODE_IMPL_TILED || impl == NJODE_IMPL_WIDE) ? 1 : 0;
   k_reduce_partials<<<(unsigned)((total + 31) / 32), 32 * RED_GROUPS, 0, st>>>(T, partials, a.n_workers,
-                                                                    impl == NJODE_IMPL_TILED ? 0 : 1, grad_params, total);
+                                                                    pytorch_layout ? 0 : 1, grad_params, total);
   NJODE_LAUNCH_OK("k_reduce_partials");
   return NJODE_OK;
 }

@@ -163,6 +163,10 @@ struct TilePlan {
 };
 TilePlan njode_tile_plan(const NjodeDesc* d, int64_t N);
 
+// checkpoint slots a tile owns beyond its kmax + 1 step slots (the wide flavour keeps the jump / readout
+// activations of a tile in three extra slots, see njode_wide.cuh)
+int32_t njode_slot_extra(const NjodeDesc* d);
+
 struct SweepArgs {
   NjodeDesc desc;
   ParamTable T;

@@ -77,8 +77,8 @@ __global__ void k_spread_perm(const int32_t* __restrict__ sorted, const int32_t*
   }
 }
 
-// single block: exclusive scan of (kmax+1) over tiles -> checkpoint slot offsets; header totals
-__global__ void k_tile_scan(const int32_t* __restrict__ tile_kmax, int64_t n_tiles,
+// single block: exclusive scan of (kmax + 1 + slots_extra) over tiles -> checkpoint slot offsets; header totals
+__global__ void k_tile_scan(const int32_t* __restrict__ tile_kmax, int64_t n_tiles, int slots_extra,
                             int64_t* __restrict__ slot_off, long long* __restrict__ header) {
   __shared__ long long part[1024];
   __shared__ int kmx[1024];
@@ -87,7 +87,7 @@ __global__ void k_tile_scan(const int32_t* __restrict__ tile_kmax, int64_t n_til
   const int64_t lo = min((int64_t)tid * chunk, n_tiles), hi = min(lo + chunk, n_tiles);
   long long s = 0;
   int km = 0;
-  for (int64_t t = lo; t < hi; ++t) { s += tile_kmax[t] + 1; km = max(km, tile_kmax[t]); }
+  for (int64_t t = lo; t < hi; ++t) { s += tile_kmax[t] + 1 + slots_extra; km = max(km, tile_kmax[t]); }
   part[tid] = s;
   kmx[tid] = km;
   __syncthreads();
@@ -102,7 +102,7 @@ __global__ void k_tile_scan(const int32_t* __restrict__ tile_kmax, int64_t n_til
   }
   __syncthreads();
   long long acc = part[tid];
-  for (int64_t t = lo; t < hi; ++t) { slot_off[t] = acc; acc += tile_kmax[t] + 1; }
+  for (int64_t t = lo; t < hi; ++t) { slot_off[t] = acc; acc += tile_kmax[t] + 1 + slots_extra; }
 }
 
 // one thread per (tile,row): the float32 knots t_0..t_kmax of that row
@@ -181,7 +181,7 @@ extern "C" int njode_schedule_build(const NjodeDesc* desc, const float* times, c
   if (tile_rows > 1024 || tile_rows % 32 != 0) NJODE_FAIL(NJODE_EINVAL, "njode_schedule_build: tile_rows must be a multiple of 32, at most 1024");
   k_spread_perm<<<(unsigned)n_tiles, tile_rows, 0, st>>>(sorted, kenc, N, tile_rows, plan, perm, tile_kmax);
   NJODE_LAUNCH_OK("k_spread_perm");
-  k_tile_scan<<<1, 1024, 0, st>>>(tile_kmax, n_tiles, tile_slot_off, (long long*)header);
+  k_tile_scan<<<1, 1024, 0, st>>>(tile_kmax, n_tiles, njode_slot_extra(desc), tile_slot_off, (long long*)header);
   NJODE_LAUNCH_OK("k_tile_scan");
   return NJODE_OK;
 }

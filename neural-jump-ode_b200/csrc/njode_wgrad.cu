@@ -1,0 +1,405 @@
+// njode_wgrad.cu -- every weight gradient of the wide flavour (hidden_dim 64 / 128) as ONE split-K tensor-core GEMM.
+//
+// After the two chain sweeps (njode_wide.cu) the checkpoint buffer holds, for every Linear layer application of the
+// batch, the layer's input activations (half A) and d loss / d(pre-activation) (half D) as planes of 128 rows.  A
+// weight gradient is a contraction over rows:   dW[out][in] = sum_rows D[row][out] * A[row][in]
+// i.e. a GEMM whose K index is the row, for ~(kmax + 3) x (L + 1) plane pairs per tile.  Both operands are data, so
+// both go through shared memory as MN-major tf32 tiles (SWIZZLE_128B_BASE32B, 128-byte rows of 32 features):
+//     A operand = D plane  [rows][out]  (M = H),   B operand = [A plane | aux columns]  [rows][in + 16]  (N = H + 16)
+// The aux columns (1, s(x).., t, dt | 1, dY.. | 1, x..; written per slot by the reverse sweep) make the bias, the
+// x / t / dt columns of the first ODE layer, the readout weights and the first jump layer fall out of the same MMAs.
+// FP32 accuracy: 3xTF32 (P_lo*Q_hi + P_hi*Q_lo + P_hi*Q_hi).  The tensor core's accumulate is not round-to-nearest
+// (round 1: ~3000 MMAs into one accumulator drifted a gradient by 6e-5), so each plane pair (48 MMAs at H=128) goes
+// into a FRESH TMEM accumulator (double buffered) that the CUDA cores merge into TMEM-resident running sums with
+// IEEE adds; running sums are flushed per category into this CTA's partial buffer (reduced in a fixed order by
+// k_reduce_partials: deterministic for a given schedule, no atomics).
+// Pipeline: 16 loader warps pull 32-row stages (LDG.256, two stages ahead in registers), split into hi / lo and
+// write the swizzled tiles (3-stage ring, full / empty mbarriers); one issuer warp runs 12 MMAs per stage.
+// The kernel is bound by the shared-memory port: 8.5 KB of operand reads per M128 N144 K8 MMA = 68 cycles at
+// 128 B/cycle -- the tensor floor for this shape is 72 -- plus the tile writes.
+#include "njode_wide.cuh"
+
+namespace {
+using namespace wide;
+
+__device__ unsigned g_status = 0;
+
+constexpr int NT3 = NT_W + 128;        // 16 loader / merge warps + one warpgroup whose first warp issues the MMAs (setmaxnreg: 104 / 56 registers)
+constexpr int NSTAGE3 = 3;
+constexpr int SROWS = 32;              // rows (K) per stage
+constexpr int BLK = SROWS * 128;       // bytes of one 32-feature block of a stage tile
+constexpr uint32_t FRESH0 = 0, FRESH1 = 160, RUN = 320, TMEM3 = 512;
+
+enum { CAT_ODE = 0, CAT_OUT, CAT_READOUT, CAT_JUMP, CAT_JUMP0 };
+
+template <int HW>
+struct G3 {
+  static constexpr int NB = HW / 32;                       // 32-feature blocks per operand
+  static constexpr int P_HI = 0, P_LO = NB * BLK, Q_HI = 2 * NB * BLK, X_HI = Q_HI + NB * BLK,
+                       Q_LO = X_HI + BLK, X_LO = Q_LO + NB * BLK, STAGE = X_LO + BLK;
+  static constexpr int NACC = HW + 16;                     // accumulator columns (in-features + aux block)
+  static constexpr int CPT = NACC / 4;                     // columns per merge thread (4 column groups)
+  static constexpr int NLOAD = HW / 8;                     // loader warps (one 8-column chunk each)
+};
+
+struct Ctl3 {
+  uint64_t full[NSTAGE3], empty[NSTAGE3], fresh_done[2], merged[2];
+  uint32_t tmem_base, pad;
+};
+
+__device__ __forceinline__ int n_cats(int L) { return 3 * L + 3; }
+__device__ __forceinline__ void cat_decode(int L, int c, int& kind, int& l) {
+  if (c <= L) { kind = CAT_ODE; l = c; }
+  else if (c <= 2 * L) { kind = CAT_OUT; l = c - (L + 1); }
+  else if (c == 2 * L + 1) { kind = CAT_READOUT; l = L; }
+  else if (c <= 3 * L + 1) { kind = CAT_JUMP; l = c - (2 * L + 1); }
+  else { kind = CAT_JUMP0; l = 0; }
+}
+__device__ __forceinline__ int cat_instances(int kind, int kmax) {
+  return kind == CAT_ODE ? kmax : (kind == CAT_OUT || kind == CAT_READOUT) ? 2 : 1;
+}
+
+// walks (category, tile of this CTA, instance, 32-row stage) in the order every role uses
+struct Cursor {
+  int c, kind, l, inst, qs, n_inst, kmax;
+  int64_t r, so;
+  bool valid;
+};
+__device__ __forceinline__ void cursor_seek(Cursor& cu, const SweepArgs& a, int wi, int n_w) {
+  const int L = a.T.L;
+  while (cu.c < n_cats(L)) {
+    const int64_t tile = wi + cu.r * n_w;
+    if (tile < a.n_tiles) {
+      cat_decode(L, cu.c, cu.kind, cu.l);
+      cu.kmax = a.tile_kmax[tile];
+      cu.n_inst = cat_instances(cu.kind, cu.kmax);
+      if (cu.n_inst > 0) { cu.so = a.tile_slot_off[tile]; cu.inst = 0; cu.qs = 0; cu.valid = true; return; }
+      ++cu.r;
+    } else {
+      ++cu.c;
+      cu.r = 0;
+    }
+  }
+  cu.valid = false;
+}
+__device__ __forceinline__ void cursor_init(Cursor& cu, const SweepArgs& a, int wi, int n_w) {
+  cu.c = 0; cu.r = 0; cu.inst = cu.qs = 0; cu.valid = false;
+  cursor_seek(cu, a, wi, n_w);
+}
+// returns true when the step crossed an instance boundary
+__device__ __forceinline__ void cursor_next(Cursor& cu, const SweepArgs& a, int wi, int n_w) {
+  if (++cu.qs < R / SROWS) return;
+  cu.qs = 0;
+  if (++cu.inst < cu.n_inst) return;
+  ++cu.r;
+  cursor_seek(cu, a, wi, n_w);
+}
+// slots (relative to the tile's first) of the P plane, Q plane and aux rows of the cursor's instance
+__device__ __forceinline__ void cursor_planes(const Cursor& cu, int L, int& p_slot, int& p_plane, bool& p_from_d,
+                                              int& q_slot, int& q_plane, bool& has_q, int& x_slot) {
+  const int X = cu.kmax + 1 + cu.inst, X3 = cu.kmax + 3;
+  p_from_d = true; has_q = true;
+  switch (cu.kind) {
+    case CAT_ODE: p_slot = q_slot = x_slot = cu.inst; p_plane = q_plane = cu.l; break;
+    case CAT_OUT:
+      p_slot = x_slot = X; p_plane = cu.l;
+      if (cu.l == 0) { q_slot = cu.inst == 0 ? 0 : cu.kmax; q_plane = 0; } else { q_slot = X; q_plane = cu.l; }
+      break;
+    case CAT_READOUT: p_slot = x_slot = X; p_plane = L; p_from_d = false; has_q = false; q_slot = q_plane = 0; break;
+    case CAT_JUMP: p_slot = q_slot = x_slot = X3; p_plane = cu.l; q_plane = cu.l - 1; break;
+    default: p_slot = x_slot = X3; p_plane = 0; has_q = false; q_slot = q_plane = 0; break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int HW>
+__device__ __forceinline__ void wg_issuer(const SweepArgs& a, uint8_t* ring, Ctl3& ctl) {
+  using G = G3<HW>;
+  const int S = a.T.S;
+  const int wi = blockIdx.x / S, n_w = gridDim.x / S;
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&ctl.tmem_base);
+  const uint32_t ring_s = umma::smem_u32(ring);
+  constexpr uint32_t idesc_q = umma::idesc_tf32(HW, G::NACC, 1, 1), idesc_x = umma::idesc_tf32(HW, 16, 1, 1);
+  Cursor cu;
+  cursor_init(cu, a, wi, n_w);
+  uint32_t sc = 0, ic = 0;
+  while (cu.valid) {
+    const bool has_q = !(cu.kind == CAT_READOUT || cu.kind == CAT_JUMP0);
+    const uint32_t b = ic & 1u, use = ic >> 1;
+    if (use > 0) wait_or_die(&ctl.merged[b], (use - 1) & 1u, &g_status, 16u);     // the accumulator's previous content is merged
+    const uint32_t acc = tmem + (b ? FRESH1 : FRESH0);
+#pragma unroll 1
+    for (int qs = 0; qs < R / SROWS; ++qs, ++sc) {
+      const uint32_t stage = sc % NSTAGE3, sround = sc / NSTAGE3;
+      wait_or_die(&ctl.full[stage], sround & 1u, &g_status, 16u);
+      umma::fence_after_sync();
+      if (umma::elect_one()) {
+        const uint32_t sb = ring_s + stage * G::STAGE;
+        const uint64_t p_hi = umma::desc_mn(sb + G::P_HI, BLK), p_lo = umma::desc_mn(sb + G::P_LO, BLK);
+        const uint64_t q_hi = umma::desc_mn(sb + (has_q ? G::Q_HI : G::X_HI), BLK), q_lo = umma::desc_mn(sb + (has_q ? G::Q_LO : G::X_LO), BLK);
+        const uint32_t idesc = has_q ? idesc_q : idesc_x;
+#pragma unroll
+        for (int ks = 0; ks < SROWS / 8; ++ks) umma::mma_ss(acc, p_lo + 64 * ks, q_hi + 64 * ks, idesc, (qs > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < SROWS / 8; ++ks) umma::mma_ss(acc, p_hi + 64 * ks, q_lo + 64 * ks, idesc, 1u);
+#pragma unroll
+        for (int ks = 0; ks < SROWS / 8; ++ks) umma::mma_ss(acc, p_hi + 64 * ks, q_hi + 64 * ks, idesc, 1u);
+        umma::commit(&ctl.empty[stage]);
+        if (qs == R / SROWS - 1) umma::commit(&ctl.fresh_done[b]);
+      }
+      __syncwarp();
+      cursor_next(cu, a, wi, n_w);
+    }
+    ++ic;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int HW>
+__device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* ring, Ctl3& ctl) {
+  using G = G3<HW>;
+  const ParamTable& T = a.T;
+  const int L = T.L, S = T.S, dx = T.d_x, O = T.O;
+  const int s = blockIdx.x % S, wi = blockIdx.x / S, n_w = gridDim.x / S;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3, cg = warp >> 2;
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&ctl.tmem_base);
+  const uint32_t my_t = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * G::CPT);     // this thread's accumulator cells
+  const uint32_t ring_s = umma::smem_u32(ring);
+  const int64_t PL = Cfg<HW>::PL, slotf = (int64_t)(L + 1) * PL;
+  const int64_t half = (int64_t)S * a.total_slots * slotf;
+  const float* const baseA = a.ckpt + (int64_t)s * a.total_slots * slotf;
+  const float* const baseD = baseA + half;
+  const float* const baseX = a.ckpt + 2 * half + (int64_t)s * a.total_slots * (R * 8);
+  float* const part = a.partials + (int64_t)blockIdx.x * T.stack_floats;
+  const bool loader = warp < G::NLOAD;
+  const int sc_kind = a.desc.input_scaling;
+
+  // accumulator row of this thread: M = 128 -> lane = row; M = 64 -> row i lives in lane (i % 16) + 32 * (i / 16)
+  const bool has_row = HW == 128 ? true : lane < 16;
+  const int irow = HW == 128 ? q * 32 + lane : q * 16 + lane;
+
+  auto zero_run = [&]() {
+    uint32_t z[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int t = 0; t < G::CPT; t += 4)
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(my_t + RUN + t), "r"(z[0]), "r"(z[1]), "r"(z[2]), "r"(z[3]) : "memory");
+    umma::wait_st();
+  };
+  auto ld4 = [&](uint32_t addr, float (&v)[4]) {
+    uint32_t u0, u1, u2, u3;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3) : "r"(addr));
+    v[0] = __uint_as_float(u0); v[1] = __uint_as_float(u1); v[2] = __uint_as_float(u2); v[3] = __uint_as_float(u3);
+  };
+  auto st4 = [&](uint32_t addr, const float (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+                 :: "r"(addr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])) : "memory");
+  };
+  // running += fresh[b]  (IEEE adds), then release the fresh accumulator
+  auto merge = [&](uint32_t ic) {
+    const uint32_t b = ic & 1u;
+    wait_or_die(&ctl.fresh_done[b], (ic >> 1) & 1u, &g_status, 16u);
+    umma::fence_after_sync();
+    const uint32_t fr = my_t + (b ? FRESH1 : FRESH0);
+#pragma unroll
+    for (int t = 0; t < G::CPT; t += 4) {
+      float f[4], r4[4];
+      ld4(fr + t, f);
+      ld4(my_t + RUN + t, r4);
+      umma::wait_ld();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r4[i] += f[i];
+      st4(my_t + RUN + t, r4);
+    }
+    umma::wait_st();
+    umma::fence_before_sync();
+    __syncwarp();
+    if (lane == 0) umma::mbar_arrive(&ctl.merged[b]);
+  };
+  float dbo[MAX_O];                      // readout bias gradient: sum over rows of dY (aux loader warp, lane = row % 32)
+#pragma unroll
+  for (int o = 0; o < MAX_O; ++o) dbo[o] = 0.0f;
+  // running sums of category (kind, l) -> this CTA's partial buffer (PyTorch layout), then clear them
+  auto flush = [&](int kind, int l) {
+    if (has_row) {
+      const int net = kind == CAT_ODE ? NET_ODE : (kind == CAT_OUT || kind == CAT_READOUT) ? NET_OUT : NET_JUMP;
+      const int ld = T.n_vec[net][l] + T.n_ext[net][l];
+#pragma unroll
+      for (int t = 0; t < G::CPT; t += 4) {
+        float v[4];
+        ld4(my_t + RUN + t, v);
+        umma::wait_ld();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int n = cg * G::CPT + t + i;
+          if (kind == CAT_READOUT) {
+            if (n >= 1 && n <= O) part[T.w_off[NET_OUT][L] + (n - 1) * HW + irow] = v[i];
+          } else if (kind == CAT_JUMP0) {
+            if (n == 0) part[T.b_off[NET_JUMP][0] + irow] = v[i];
+            else if (n <= dx) part[T.w_off[NET_JUMP][0] + irow * dx + (n - 1)] = v[i];
+          } else if (n < HW) {
+            part[T.w_off[net][l] + irow * ld + n] = v[i];
+          } else if (n == HW) {
+            part[T.b_off[net][l] + irow] = v[i];
+          } else if (kind == CAT_ODE && l == 0 && n - HW - 1 < dx + 2) {
+            part[T.w_off[net][l] + irow * ld + HW + (n - HW - 1)] = v[i];
+          }
+        }
+      }
+    } else {
+      umma::wait_ld();
+    }
+    if (kind == CAT_READOUT && warp == 0) {
+#pragma unroll
+      for (int o = 0; o < MAX_O; ++o) {
+        float v = dbo[o];
+        for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+        if (lane == 0 && o < O) part[T.b_off[NET_OUT][L] + o] = v;
+      }
+    }
+    zero_run();
+  };
+
+  // everything the MMAs may read must be finite: clear the ring (aux columns 8..15 stay zero for good) and TMEM
+  for (int i = threadIdx.x; i < NSTAGE3 * G::STAGE / 16; i += NT_W) reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  {
+    uint32_t z[4] = {0u, 0u, 0u, 0u};
+    for (uint32_t c = 0; c < (uint32_t)G::CPT; c += 4) {
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(my_t + FRESH0 + c), "r"(z[0]), "r"(z[1]), "r"(z[2]), "r"(z[3]) : "memory");
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(my_t + FRESH1 + c), "r"(z[0]), "r"(z[1]), "r"(z[2]), "r"(z[3]) : "memory");
+    }
+    zero_run();
+  }
+  umma::fence_async_smem();
+  umma::named_bar_sync(1, NT_W);
+
+  // ---- stage loads, two stages ahead in registers ----
+  Cursor cur, pre;
+  cursor_init(cur, a, wi, n_w);
+  pre = cur;
+  float pb[2][8], qb[2][8], xb[2][8];
+  auto issue_loads = [&](const Cursor& cu, float (&p)[8], float (&qv)[8], float (&x)[8]) {
+    if (!cu.valid) return;
+    int ps, pp, qsl, qp, xs;
+    bool pd, hq;
+    cursor_planes(cu, L, ps, pp, pd, qsl, qp, hq, xs);
+    const int rowg = cu.qs * SROWS + lane;
+    if (loader) {
+      ld8g((pd ? baseD : baseA) + ((cu.so + ps) * (L + 1) + pp) * PL + ((int64_t)warp * R + rowg) * 8, p);
+      if (hq) ld8g(baseA + ((cu.so + qsl) * (L + 1) + qp) * PL + ((int64_t)warp * R + rowg) * 8, qv);
+    }
+    if (warp == 0) ld8g(baseX + ((cu.so + xs) * R + rowg) * 8, x);
+  };
+  issue_loads(pre, pb[0], qb[0], xb[0]);
+  cursor_next(pre, a, wi, n_w);
+  issue_loads(pre, pb[1], qb[1], xb[1]);
+  if (pre.valid) cursor_next(pre, a, wi, n_w);
+
+  uint32_t sc = 0, ic = 0;
+  bool pending = false;                  // instance ic - 1 not merged yet
+  while (cur.valid) {
+    const int kind = cur.kind, l = cur.l, c_now = cur.c;
+    const bool has_q = !(kind == CAT_READOUT || kind == CAT_JUMP0);
+    const bool scale_q = kind == CAT_ODE && l == 0 && sc_kind != NJODE_SCALE_IDENTITY;
+#pragma unroll
+    for (int qs = 0; qs < R / SROWS; ++qs, ++sc) {
+      const uint32_t stage = sc % NSTAGE3, sround = sc / NSTAGE3;
+      float (&p)[8] = pb[qs & 1];
+      float (&qv)[8] = qb[qs & 1];
+      float (&x)[8] = xb[qs & 1];
+      wait_or_die(&ctl.empty[stage], (sround & 1u) ^ 1u, &g_status, 16u);
+      const uint32_t sb = ring_s + stage * G::STAGE;
+      uint32_t hi[8], lo[8];
+      if (loader) {
+        const uint32_t boff = (uint32_t)(warp >> 2) * BLK;
+        umma::split8(p, hi, lo);
+        umma::chunk_to_mn_tile(sb + G::P_HI + boff, lane, warp & 3, hi);
+        umma::chunk_to_mn_tile(sb + G::P_LO + boff, lane, warp & 3, lo);
+        if (has_q) {
+          if (scale_q) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) qv[i] = scale_fwd_rt(sc_kind, qv[i]);
+          }
+          umma::split8(qv, hi, lo);
+          umma::chunk_to_mn_tile(sb + G::Q_HI + boff, lane, warp & 3, hi);
+          umma::chunk_to_mn_tile(sb + G::Q_LO + boff, lane, warp & 3, lo);
+        }
+      }
+      if (warp == 0) {
+        umma::split8(x, hi, lo);
+        umma::chunk_to_mn_tile(sb + G::X_HI, lane, 0, hi);
+        umma::chunk_to_mn_tile(sb + G::X_LO, lane, 0, lo);
+        if (kind == CAT_READOUT) {
+#pragma unroll
+          for (int o = 0; o < MAX_O; ++o) dbo[o] += x[1 + o];
+        }
+      }
+      umma::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&ctl.full[stage]);
+      // refill this register stage with the loads of the stage after the next
+      issue_loads(pre, p, qv, x);
+      if (pre.valid) cursor_next(pre, a, wi, n_w);
+      cursor_next(cur, a, wi, n_w);
+    }
+    if (pending) merge(ic - 1);
+    pending = true;
+    ++ic;
+    if (!cur.valid || cur.c != c_now) {    // category finished: fold the last accumulator in and flush
+      merge(ic - 1);
+      pending = false;
+      flush(kind, l);
+    }
+  }
+}
+
+template <int HW>
+__global__ void __launch_bounds__(NT3, 1) k_wide_wgrad(SweepArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  using G = G3<HW>;
+  uint8_t* ring = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  Ctl3& ctl = *reinterpret_cast<Ctl3*>(ring + (size_t)NSTAGE3 * G::STAGE);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE3; ++i) { umma::mbar_init(&ctl.full[i], NWARP_W); umma::mbar_init(&ctl.empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(&ctl.fresh_done[i], 1); umma::mbar_init(&ctl.merged[i], NWARP_W); }
+    umma::fence_mbar_init();
+  }
+  if (warp == 0) umma::tmem_alloc(&ctl.tmem_base, TMEM3);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  if (warp < NWARP_W) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    wg_worker<HW>(a, ring, ctl);
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == NWARP_W) wg_issuer<HW>(a, ring, ctl);
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_free(*reinterpret_cast<volatile uint32_t*>(&ctl.tmem_base), TMEM3);
+}
+
+template <int HW>
+int launch_wgrad(const SweepArgs& a, cudaStream_t st) {
+  const size_t smem = 1024 + (size_t)NSTAGE3 * G3<HW>::STAGE + sizeof(Ctl3) + 16;
+  NJODE_CUDA_OK(cudaFuncSetAttribute(k_wide_wgrad<HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  njode_timing_begin(3, st);
+  k_wide_wgrad<HW><<<a.n_workers, NT3, smem, st>>>(a);
+  njode_timing_end(3, st);
+  NJODE_LAUNCH_OK("k_wide_wgrad");
+  return NJODE_OK;
+}
+
+}  // namespace
+
+int njode_wide_wgrad(const SweepArgs& a, cudaStream_t st) {
+  if (a.n_tiles == 0) return NJODE_OK;
+  return a.desc.hidden == 128 ? launch_wgrad<128>(a, st) : launch_wgrad<64>(a, st);
+}
+
+int njode_wide_wgrad_status(unsigned* out_host) {
+  NJODE_CUDA_OK(cudaMemcpyFromSymbol(out_host, g_status, sizeof(unsigned)));
+  return NJODE_OK;
+}

@@ -1,0 +1,796 @@
+// njode_wide.cu -- tcgen05 / TMEM chain sweeps for hidden_dim in {64, 128}, 1..3 hidden layers
+// (BASELINE configs 4 and 5: Heston H=128 / L=3 / tanh and the mixed H=64 batch).
+//
+// A CTA owns a tile of 128 observation units of one network stack; row r of the tile is TMEM lane r.  Every
+// Linear of the path is a "chain" GEMM  D[128 x H] = A[128 x H] * W^T  with FP32 accuracy from the 3xTF32 split:
+//     A   the activation (forward) / data gradient (reverse), written by the row workers straight into TMEM as
+//         tf32 hi / lo parts (tcgen05.st) -- activations never pass through shared memory;
+//     W   does NOT fit in shared memory (H=128, L=3: 4 ODE matrices x 128 KB of hi/lo parts), so it is STREAMED:
+//         a producer warp walks the same GEMM program as the MMA issuer and pulls pre-split, pre-swizzled stages
+//         of 2 x H x 32 floats from a weight image in L2 with cp.async.bulk (TMA engine) into a 6-stage ring,
+//         full / empty mbarriers on either side (tcgen05.commit frees a stage);
+//     D   accumulates in TMEM, double buffered, and is read back with tcgen05.ld for the fused epilogue.
+// Epilogue and MMA of consecutive layers overlap: the 16 worker warps (warp w: lane quadrant w % 4, column
+// group w / 4) produce the next A operand in sub-steps of 8 columns per thread; after each sub-step the issuer
+// may run the 4 k-steps (one per column group) x 3 passes that only need those columns.  The K order of a
+// weight image is permuted accordingly, so that a ring stage is exactly the weights of one sub-step.
+// The reverse sweep is the same machine run backwards on transposed images: it propagates d loss / d(pre-
+// activation) through every layer and writes those "d planes" next to the forward sweep's activation planes;
+// all weight gradients are contractions of (d plane, activation plane) pairs over rows and run afterwards as one
+// split-K tensor-core GEMM (njode_wgrad.cu) -- at H = 128 neither shared memory nor TMEM has room to do them here.
+#include "njode_wide.cuh"
+
+namespace {
+using namespace wide;
+
+__device__ unsigned g_status = 0;
+
+constexpr int NT = NT_W + 128;         // 16 worker warps + one warpgroup holding the MMA issuer warp and the weight producer warp
+// Register budget: the CTA launches with 640 x 96 registers and setmaxnreg moves registers inside that pool:
+// 512 x 104 (workers: a 32-float state slice per thread at H = 128) + 128 x 56 = 60416 <= 61440.
+
+template <int HW>
+struct __align__(16) SmallW {
+  float b_jump[NJODE_WIDE_LMAX + 1][HW], b_ode[NJODE_WIDE_LMAX + 1][HW], b_out[NJODE_WIDE_LMAX][HW];
+  float ext_ode0[MAX_DX + 2][HW];      // [e][j]: columns H.. of the ODE first layer (x.., t_cur, dt)
+  float w_jump0[MAX_DX][HW];           // [e][j]
+  float w_out[MAX_O][HW];              // [o][j] readout layer (forward: W; reverse: the same)
+  float b_outL[MAX_O];
+  float red[4][R][MAX_O];              // readout partial sums of the 4 column groups
+};
+
+struct Ctl {
+  uint64_t full[8], empty[8], ops[4], accd[2];
+  uint32_t tmem_base, pad;
+};
+
+template <int HW>
+struct Smem {
+  uint8_t* ring;
+  SmallW<HW>* sw;
+  Ctl* ctl;
+  static constexpr size_t bytes() { return 1024 + (size_t)Cfg<HW>::NSTAGE * Cfg<HW>::STAGE_BYTES + sizeof(SmallW<HW>) + sizeof(Ctl) + 16; }
+  __device__ __forceinline__ explicit Smem(uint8_t* raw) {
+    uint8_t* base = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    ring = base;
+    sw = reinterpret_cast<SmallW<HW>*>(base + (size_t)Cfg<HW>::NSTAGE * Cfg<HW>::STAGE_BYTES);
+    ctl = reinterpret_cast<Ctl*>(reinterpret_cast<uint8_t*>(sw) + sizeof(SmallW<HW>));
+  }
+};
+
+__device__ __forceinline__ int64_t pred_index(const ParamTable& T, int64_t obs, int s, int o) {
+  return T.S == 1 ? obs * T.d_y * T.M + o : (obs * T.d_y + o) * T.M + s;
+}
+__device__ __forceinline__ int64_t snake_tile(int64_t round, int worker, int n_workers) {
+  return round * n_workers + ((round & 1) ? n_workers - 1 - worker : worker);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight images: for every stack and chain matrix, NSUB stages of [hi | lo] x [H rows n][32 k], K-major with the
+// 128-byte swizzle.  Stage j holds, for column group g = 0..3, the 8 input features g*CG + 8j .. +8 (local k = 8g + i):
+// exactly the columns of the A operand that sub-step j of the producing epilogue completes.
+//   forward image:  B[n][k] = W[n][k]     (n = output feature)
+//   reverse image:  B[n][k] = W[k][n]     (n = input feature < H: d loss / d input = d * W)
+// ------------------------------------------------------------------------------------------------
+template <int HW>
+__global__ void k_wide_prep(ParamTable T, const float* __restrict__ params, float* __restrict__ img, int transpose) {
+  using C = Cfg<HW>;
+  const int L = T.L, NM = n_mats(L);
+  const int64_t total = (int64_t)T.S * NM * HW * HW;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int k = (int)(idx % HW);
+  const int n = (int)((idx / HW) % HW);
+  const int m = (int)((idx / ((int64_t)HW * HW)) % NM);
+  const int s = (int)(idx / ((int64_t)HW * HW * NM));
+  int net, l;
+  if (m < L) { net = NET_JUMP; l = m + 1; }
+  else if (m <= 2 * L) { net = NET_ODE; l = m - L; }
+  else { net = NET_OUT; l = m - 2 * L - 1; }
+  const int ld = T.n_vec[net][l] + T.n_ext[net][l];
+  const float* W = params + (int64_t)s * T.stack_floats + T.w_off[net][l];
+  const float v = transpose ? W[k * ld + n] : W[n * ld + k];
+  uint32_t hi, lo;
+  umma::split1(v, hi, lo);
+  const int g = k / C::CG, r = k % C::CG, j = r >> 3, i = r & 7, kk = g * 8 + i;
+  float* st = img + ((int64_t)(s * NM + m) * C::NSUB + j) * (C::STAGE_BYTES / 4);
+  st[umma::swz_k(n, kk)] = __uint_as_float(hi);
+  st[C::STAGE_HALF / 4 + umma::swz_k(n, kk)] = __uint_as_float(lo);
+}
+
+// ------------------------------------------------------------------------------------------------
+// roles shared by both sweeps
+// ------------------------------------------------------------------------------------------------
+// GEMMs of one tile, in program order: forward  J1..JL | O0..O(L-1) | kmax x (E0..EL) | O0..O(L-1)
+//                                      reverse  O(L-1)..O0 | kmax x (EL..E0) | O(L-1)..O0 | JL..J1
+template <int HW, bool BWD>
+__device__ __forceinline__ void producer(const SweepArgs& a, uint8_t* raw, const float* __restrict__ img) {
+  using C = Cfg<HW>;
+  Smem<HW> sm(raw);
+  Ctl& ctl = *sm.ctl;
+  const int S = a.T.S, L = a.T.L;
+  const int s = blockIdx.x % S, worker = blockIdx.x / S, n_workers = gridDim.x / S;
+  const uint8_t* simg = reinterpret_cast<const uint8_t*>(img) + (size_t)s * n_mats(L) * C::NSUB * C::STAGE_BYTES;
+  uint32_t sc = 0;
+  auto load = [&](int m) {
+    const uint8_t* src = simg + (size_t)m * C::NSUB * C::STAGE_BYTES;
+#pragma unroll 1
+    for (int j = 0; j < C::NSUB; ++j, ++sc) {
+      const uint32_t stage = sc % C::NSTAGE, round = sc / C::NSTAGE;
+      wait_or_die(&ctl.empty[stage], (round & 1u) ^ 1u, &g_status, BWD ? 8u : 4u);
+      mbar_expect_tx(&ctl.full[stage], C::STAGE_BYTES);
+      bulk_g2s(sm.ring + (size_t)stage * C::STAGE_BYTES, src + (size_t)j * C::STAGE_BYTES, C::STAGE_BYTES, &ctl.full[stage]);
+    }
+  };
+  for (int64_t round = 0; round * n_workers < a.n_tiles; ++round) {
+    const int64_t tile = snake_tile(round, worker, n_workers);
+    if (tile >= a.n_tiles) continue;
+    const int kmax = a.tile_kmax[tile];
+    if (!BWD) {
+      for (int l = 1; l <= L; ++l) load(mat_jump(L, l));
+      for (int l = 0; l < L; ++l) load(mat_out(L, l));
+      for (int k = 0; k < kmax; ++k)
+        for (int l = 0; l <= L; ++l) load(mat_ode(L, l));
+      for (int l = 0; l < L; ++l) load(mat_out(L, l));
+    } else {
+      for (int l = L - 1; l >= 0; --l) load(mat_out(L, l));
+      for (int k = 0; k < kmax; ++k)
+        for (int l = L; l >= 0; --l) load(mat_ode(L, l));
+      for (int l = L - 1; l >= 0; --l) load(mat_out(L, l));
+      for (int l = L; l >= 1; --l) load(mat_jump(L, l));
+    }
+  }
+}
+
+template <int HW, bool BWD>
+__device__ __forceinline__ void issuer(const SweepArgs& a, uint8_t* raw) {
+  using C = Cfg<HW>;
+  Smem<HW> sm(raw);
+  Ctl& ctl = *sm.ctl;
+  const int S = a.T.S, L = a.T.L;
+  const int worker = blockIdx.x / S, n_workers = gridDim.x / S;
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&ctl.tmem_base);
+  const uint32_t ring_s = umma::smem_u32(sm.ring);
+  constexpr uint32_t idesc = umma::idesc_tf32(128, HW, 0, 0);
+  constexpr unsigned bit = BWD ? 8u : 4u;
+  uint32_t sc = 0, gi = 0;
+  for (int64_t round = 0; round * n_workers < a.n_tiles; ++round) {
+    const int64_t tile = snake_tile(round, worker, n_workers);
+    if (tile >= a.n_tiles) continue;
+    const int n_gemm = 3 * L + a.tile_kmax[tile] * (L + 1);
+#pragma unroll 1
+    for (int e = 0; e < n_gemm; ++e, ++gi) {
+      const uint32_t acc = tmem + C::ACC0 + (gi & 1u) * HW;
+#pragma unroll 1
+      for (int j = 0; j < C::NSUB; ++j, ++sc) {
+        const uint32_t stage = sc % C::NSTAGE, sround = sc / C::NSTAGE;
+        wait_or_die(&ctl.ops[j], gi & 1u, &g_status, bit);            // the A columns of this sub-step are in TMEM
+        wait_or_die(&ctl.full[stage], sround & 1u, &g_status, bit);   // its weights are in the ring
+        umma::fence_after_sync();
+        if (umma::elect_one()) {
+          const uint64_t dbh = umma::desc_k(ring_s + stage * C::STAGE_BYTES);
+          const uint64_t dbl = umma::desc_k(ring_s + stage * C::STAGE_BYTES + C::STAGE_HALF);
+          const uint32_t a_hi = tmem + C::A_HI + 8 * j, a_lo = tmem + C::A_LO + 8 * j;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) umma::mma_ts(acc, a_lo + g * C::CG, dbh + 2 * g, idesc, (j > 0 || g > 0) ? 1u : 0u);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) umma::mma_ts(acc, a_hi + g * C::CG, dbl + 2 * g, idesc, 1u);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) umma::mma_ts(acc, a_hi + g * C::CG, dbh + 2 * g, idesc, 1u);
+          umma::commit(&ctl.empty[stage]);                            // stage free once these MMAs have read it
+          if (j == C::NSUB - 1) umma::commit(&ctl.accd[gi & 1u]);     // accumulator complete
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// per-thread view of the worker role
+template <int HW>
+struct WorkerCtx {
+  using C = Cfg<HW>;
+  Ctl& ctl;
+  SmallW<HW>& sw;
+  int lane, q, g, row, col0;
+  uint32_t lane_base;      // TMEM address of (this lane quadrant, column col0)
+  uint32_t gi;             // GEMM counter (same sequence as the issuer's)
+  unsigned bit;
+  __device__ __forceinline__ WorkerCtx(Smem<HW>& sm, unsigned bit_) : ctl(*sm.ctl), sw(*sm.sw), gi(0), bit(bit_) {
+    const int warp = threadIdx.x >> 5;
+    lane = threadIdx.x & 31;
+    q = warp & 3;
+    g = warp >> 2;
+    row = q * 32 + lane;
+    col0 = g * C::CG;
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&ctl.tmem_base);
+    lane_base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
+  }
+  // sub-chunk j of the next GEMM's A operand: split, store to TMEM, tell the issuer (one arrival per warp)
+  __device__ __forceinline__ void emit(int j, const float (&v)[8]) {
+    uint32_t hi[8], lo[8];
+    umma::split8(v, hi, lo);
+    umma::tmem_st8_raw(lane_base + C::A_HI + 8 * j, hi);
+    umma::tmem_st8_raw(lane_base + C::A_LO + 8 * j, lo);
+    umma::wait_st();
+    umma::fence_before_sync();
+    __syncwarp();
+    if (lane == 0) umma::mbar_arrive(&ctl.ops[j]);
+  }
+  // wait for the accumulator of GEMM gi (call once per GEMM, then acc_ld for each sub-chunk, then done())
+  __device__ __forceinline__ void wait_acc() {
+    wait_or_die(&ctl.accd[gi & 1u], (gi >> 1) & 1u, &g_status, bit);
+    umma::fence_after_sync();
+  }
+  __device__ __forceinline__ void acc_ld(int j, float (&v)[8]) { umma::tmem_ld8(lane_base + C::ACC0 + (gi & 1u) * HW + 8 * j, v); }
+  __device__ __forceinline__ void done() { ++gi; }
+};
+
+template <int HW>
+__device__ __forceinline__ void load_small(SmallW<HW>& sw, const ParamTable& T, const float* __restrict__ p) {
+  const int L = T.L;
+  for (int t = threadIdx.x; t < HW; t += NT_W) {
+    for (int l = 0; l <= L; ++l) {
+      sw.b_jump[l][t] = p[T.b_off[NET_JUMP][l] + t];
+      sw.b_ode[l][t] = p[T.b_off[NET_ODE][l] + t];
+      if (l < L) sw.b_out[l][t] = p[T.b_off[NET_OUT][l] + t];
+    }
+    const int ld0 = HW + T.d_x + 2;
+    for (int e = 0; e < T.d_x + 2; ++e) sw.ext_ode0[e][t] = p[T.w_off[NET_ODE][0] + t * ld0 + HW + e];
+    for (int e = 0; e < T.d_x; ++e) sw.w_jump0[e][t] = p[T.w_off[NET_JUMP][0] + t * T.d_x + e];
+    for (int o = 0; o < T.O; ++o) sw.w_out[o][t] = p[T.w_off[NET_OUT][L] + o * HW + t];
+    if (t < T.O) sw.b_outL[t] = p[T.b_off[NET_OUT][L] + t];
+  }
+}
+
+__device__ __forceinline__ void scale8(int sc, float (&v)[8]) {
+  if (sc == NJODE_SCALE_TANH) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = tanhf(v[i]);
+  } else if (sc == NJODE_SCALE_SIGMOID) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 1.0f / (1.0f + expf(-v[i]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward sweep: row workers
+// ------------------------------------------------------------------------------------------------
+template <int HW, int ACT>
+__device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
+  using C = Cfg<HW>;
+  constexpr int CG = C::CG, NSUB = C::NSUB;
+  Smem<HW> sm(raw);
+  WorkerCtx<HW> w(sm, 4u);
+  SmallW<HW>& sw = w.sw;
+  const ParamTable& T = a.T;
+  const int L = T.L, dx = T.d_x, O = T.O, sc_kind = a.desc.input_scaling;
+  const int s = blockIdx.x % T.S, worker = blockIdx.x / T.S, n_workers = gridDim.x / T.S;
+  const int row = w.row, col0 = w.col0, g = w.g;
+  const int64_t PL = C::PL, slotf = (int64_t)(L + 1) * PL;
+  float* const ckpt_s = a.ckpt ? a.ckpt + (int64_t)s * a.total_slots * slotf + ((col0 >> 3) * R + row) * 8 : nullptr;
+
+  for (int64_t round = 0; round * n_workers < a.n_tiles; ++round) {
+    const int64_t tile = snake_tile(round, worker, n_workers);
+    if (tile >= a.n_tiles) continue;
+    const int kmax = a.tile_kmax[tile];
+    const int u = a.perm[tile * R + row];
+    float* const ck = ckpt_s ? ckpt_s + a.tile_slot_off[tile] * slotf : nullptr;
+    // plane `pl` of slot `sl`, this thread's sub-chunk j
+    auto cp = [&](int sl, int pl, int j) { return ck + ((int64_t)sl * (L + 1) + pl) * PL + j * (R * 8); };
+    const float* const kn = a.knots + a.tile_slot_off[tile] * R + row;
+    const int ke = u >= 0 ? a.kenc[u] : 0;
+    const int K = ke >> 1;
+    const int X1 = kmax + 1, X2 = kmax + 2, X3 = kmax + 3;
+    float x[MAX_DX], xs[MAX_DX];
+#pragma unroll
+    for (int e = 0; e < MAX_DX; ++e) {
+      x[e] = (e < dx && u >= 0) ? a.values[(int64_t)u * dx + e] : 0.0f;
+      xs[e] = scale_fwd_rt(sc_kind, x[e]);
+    }
+    float h[CG];
+
+    // ---- h = jump(x)                                                  jump_ode.py:169 / :176 ----
+#pragma unroll
+    for (int j = 0; j < NSUB; ++j) {
+      float z[8], cw[8];
+      ld8s(sw.b_jump[0] + col0 + 8 * j, z);
+#pragma unroll
+      for (int e = 0; e < MAX_DX; ++e) if (e < dx) {
+        ld8s(sw.w_jump0[e] + col0 + 8 * j, cw);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[i] = fmaf(cw[i], x[e], z[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) z[i] = act_fwd<ACT>(z[i]);
+      if (ck) st8g(cp(X3, 0, j), z);
+      w.emit(j, z);
+    }
+    for (int l = 1; l <= L; ++l) {
+      w.wait_acc();
+#pragma unroll
+      for (int j = 0; j < NSUB; ++j) {
+        float z[8], cb[8];
+        w.acc_ld(j, z);
+        ld8s(sw.b_jump[l] + col0 + 8 * j, cb);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[i] = act_fwd<ACT>(z[i] + cb[i]);
+        if (l < L) {
+          if (ck) st8g(cp(X3, l, j), z);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) h[8 * j + i] = z[i];
+          if (ck) st8g(cp(0, 0, j), z);
+        }
+        w.emit(j, z);                   // next jump layer, or (l == L) the first out-net layer on h_0
+      }
+      w.done();
+    }
+
+    // ---- y = out(h): the A operand (h) has been emitted; L chain GEMMs, then the readout dot products ----
+    auto readout = [&](int X, float* __restrict__ dst, int64_t obs, bool write) {
+      float y[MAX_O];
+#pragma unroll
+      for (int o = 0; o < MAX_O; ++o) y[o] = 0.0f;
+      for (int l = 0; l < L; ++l) {
+        w.wait_acc();
+#pragma unroll
+        for (int j = 0; j < NSUB; ++j) {
+          float z[8], cb[8];
+          w.acc_ld(j, z);
+          ld8s(sw.b_out[l] + col0 + 8 * j, cb);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) z[i] = act_fwd<ACT>(z[i] + cb[i]);
+          if (ck) st8g(cp(X, l + 1, j), z);
+          if (l < L - 1) {
+            w.emit(j, z);
+          } else {
+#pragma unroll
+            for (int o = 0; o < MAX_O; ++o) if (o < O) {
+              ld8s(sw.w_out[o] + col0 + 8 * j, cb);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) y[o] = fmaf(z[i], cb[i], y[o]);
+            }
+          }
+        }
+        w.done();
+      }
+      *reinterpret_cast<float4*>(sw.red[g][row]) = make_float4(y[0], y[1], y[2], y[3]);
+      umma::named_bar_sync(1, NT_W);
+      if (g == 0 && write) {
+#pragma unroll
+        for (int o = 0; o < MAX_O; ++o) if (o < O)
+          dst[pred_index(T, obs, s, o)] = sw.b_outL[o] + ((sw.red[0][row][o] + sw.red[1][row][o]) + (sw.red[2][row][o] + sw.red[3][row][o]));
+      }
+    };
+    readout(X1, a.preds, u, u >= 0);
+
+    // A operand of the next GEMM from the state in registers: s(h) for an Euler step, h itself for the readout
+    auto emit_state = [&](bool scaled) {
+#pragma unroll
+      for (int j = 0; j < NSUB; ++j) {
+        float z[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[i] = h[8 * j + i];
+        if (scaled) scale8(sc_kind, z);
+        w.emit(j, z);
+      }
+    };
+    emit_state(kmax > 0);
+
+    // ---- Euler steps with x held constant                              jump_ode.py:188-203, :122-140 ----
+    float tn = ldg_na(kn);
+    float tn_ahead = kmax > 0 ? ldg_na(kn + R) : tn;
+    for (int k = 0; k < kmax; ++k) {
+      const float tc = tn;
+      tn = tn_ahead;
+      const float tn_loaded = ldg_na(kn + (k + 2 <= kmax ? k + 2 : kmax) * R);
+      const float delta = __fsub_rn(tn, tc);
+      // first layer: bias + the x / t_cur / dt columns on the CUDA cores      jump_ode.py:57-61
+      w.wait_acc();
+#pragma unroll
+      for (int j = 0; j < NSUB; ++j) {
+        float z[8], cw[8];
+        w.acc_ld(j, z);
+        ld8s(sw.b_ode[0] + col0 + 8 * j, cw);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[i] += cw[i];
+#pragma unroll
+        for (int e = 0; e < MAX_DX; ++e) if (e < dx) {
+          ld8s(sw.ext_ode0[e] + col0 + 8 * j, cw);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) z[i] = fmaf(cw[i], xs[e], z[i]);
+        }
+        ld8s(sw.ext_ode0[dx] + col0 + 8 * j, cw);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[i] = fmaf(cw[i], tc, z[i]);
+        ld8s(sw.ext_ode0[dx + 1] + col0 + 8 * j, cw);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[i] = act_fwd<ACT>(fmaf(cw[i], delta, z[i]));
+        if (ck) st8g(cp(k, 1, j), z);
+        w.emit(j, z);
+      }
+      w.done();
+      for (int l = 1; l < L; ++l) {
+        w.wait_acc();
+#pragma unroll
+        for (int j = 0; j < NSUB; ++j) {
+          float z[8], cb[8];
+          w.acc_ld(j, z);
+          ld8s(sw.b_ode[l] + col0 + 8 * j, cb);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) z[i] = act_fwd<ACT>(z[i] + cb[i]);
+          if (ck) st8g(cp(k, l + 1, j), z);
+          w.emit(j, z);
+        }
+        w.done();
+      }
+      // last layer (no activation) and the Euler update                      jump_ode.py:130-131 / :138-139
+      w.wait_acc();
+      const bool more = k + 1 < kmax;
+#pragma unroll
+      for (int j = 0; j < NSUB; ++j) {
+        float f[8], cb[8];
+        w.acc_ld(j, f);
+        ld8s(sw.b_ode[L] + col0 + 8 * j, cb);
+        if (k < K) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) h[8 * j + i] = fmaf(delta, f[i] + cb[i], h[8 * j + i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = h[8 * j + i];
+        if (ck) st8g(cp(k + 1, 0, j), f);
+        if (more) scale8(sc_kind, f);
+        w.emit(j, f);
+      }
+      w.done();
+      asm volatile("mov.f32 %0, %1;" : "=f"(tn_ahead) : "f"(tn_loaded));
+    }
+    readout(X2, a.preds_before, (int64_t)u + 1, u >= 0 && (ke & 1));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// reverse sweep: row workers.  Propagates d loss / d (pre-activation) through every layer, last to first, and
+// writes each of them as a "d plane" (half D of the checkpoint buffer) for the weight-gradient GEMM.
+// ------------------------------------------------------------------------------------------------
+template <int HW, int ACT>
+__device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
+  using C = Cfg<HW>;
+  constexpr int CG = C::CG, NSUB = C::NSUB;
+  Smem<HW> sm(raw);
+  WorkerCtx<HW> w(sm, 8u);
+  SmallW<HW>& sw = w.sw;
+  const ParamTable& T = a.T;
+  const int L = T.L, O = T.O, sc_kind = a.desc.input_scaling;
+  const int s = blockIdx.x % T.S, worker = blockIdx.x / T.S, n_workers = gridDim.x / T.S;
+  const int row = w.row, col0 = w.col0;
+  const int64_t PL = C::PL, slotf = (int64_t)(L + 1) * PL;
+  const int64_t half = (int64_t)T.S * a.total_slots * slotf;             // floats of half A
+  const int64_t toff = (int64_t)s * a.total_slots * slotf + ((col0 >> 3) * R + row) * 8;
+
+  for (int64_t round = 0; round * n_workers < a.n_tiles; ++round) {
+    const int64_t tile = snake_tile(round, worker, n_workers);
+    if (tile >= a.n_tiles) continue;
+    const int kmax = a.tile_kmax[tile];
+    const int u = a.perm[tile * R + row];
+    const int ke = u >= 0 ? a.kenc[u] : 0;
+    const float* const ca = a.ckpt + toff + a.tile_slot_off[tile] * slotf;       // activations (read)
+    float* const cd = a.ckpt + half + toff + a.tile_slot_off[tile] * slotf;      // d planes (written)
+    auto pa = [&](int sl, int pl, int j) { return ca + ((int64_t)sl * (L + 1) + pl) * PL + j * (R * 8); };
+    auto pd = [&](int sl, int pl, int j) { return cd + ((int64_t)sl * (L + 1) + pl) * PL + j * (R * 8); };
+    // aux rows of a slot (8 floats per row, written by the column-group-0 thread of the row): the extra B columns of
+    // the weight-gradient GEMM -- (1, s(x).., t, dt) for an Euler step, (1, dY..) for a readout, (1, x..) for the jump
+    float* const cx = a.ckpt + 2 * half + ((int64_t)s * a.total_slots + a.tile_slot_off[tile]) * (R * 8) + row * 8;
+    const float* const kn = a.knots + a.tile_slot_off[tile] * R + row;
+    const int X1 = kmax + 1, X2 = kmax + 2, X3 = kmax + 3;
+    float xr[MAX_DX], xs[MAX_DX];
+#pragma unroll
+    for (int e = 0; e < MAX_DX; ++e) {
+      xr[e] = (e < T.d_x && u >= 0) ? a.values[(int64_t)u * T.d_x + e] : 0.0f;
+      xs[e] = scale_fwd_rt(sc_kind, xr[e]);
+    }
+    float gr[CG];                      // d loss / d h (this thread's columns), running backwards in time
+#pragma unroll
+    for (int i = 0; i < CG; ++i) gr[i] = 0.0f;
+
+    // ---- readout backward at a hidden state: adds d loss / d h to gr ----
+    auto out_backward = [&](int X, const float* __restrict__ gsrc, int64_t obs, bool live) {
+      float dY[MAX_O];
+#pragma unroll
+      for (int o = 0; o < MAX_O; ++o) dY[o] = (live && o < O) ? gsrc[pred_index(T, obs, s, o)] : 0.0f;
+      if (w.g == 0) {
+        static_assert(MAX_O == 4, "aux row layout assumes <= 4 readout columns");
+        const float xv[8] = {1.0f, dY[0], dY[1], dY[2], dY[3], 0.0f, 0.0f, 0.0f};
+        st8g(cx + (int64_t)X * (R * 8), xv);
+      }
+      // d (pre-activation of out layer L-1) = (sum_o dY[o] * w_out[o][:]) * act'(z_L)
+#pragma unroll
+      for (int j = 0; j < NSUB; ++j) {
+        float z[8], d[8], cw[8];
+        ld8g(pa(X, L, j), z);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = 0.0f;
+#pragma unroll
+        for (int o = 0; o < MAX_O; ++o) if (o < O) {
+          ld8s(sw.w_out[o] + col0 + 8 * j, cw);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[i] = fmaf(dY[o], cw[i], d[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] *= act_grad_from_out<ACT>(z[i]);
+        st8g(pd(X, L - 1, j), d);
+        w.emit(j, d);                                            // -> d * W_out[L-1]
+      }
+      for (int l = L - 1; l >= 1; --l) {
+        float z[8];
+        ld8g(pa(X, l, 0), z);
+        w.wait_acc();
+#pragma unroll
+        for (int j = 0; j < NSUB; ++j) {
+          float acc[8], zn[8];
+          if (j + 1 < NSUB) ld8g(pa(X, l, j + 1), zn);
+          w.acc_ld(j, acc);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] *= act_grad_from_out<ACT>(z[i]);
+          st8g(pd(X, l - 1, j), acc);
+          w.emit(j, acc);                                        // -> d * W_out[l-1]
+          if (j + 1 < NSUB) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) z[i] = zn[i];
+          }
+        }
+        w.done();
+      }
+      w.wait_acc();                                              // d * W_out[0] = d loss / d h through this readout
+#pragma unroll
+      for (int j = 0; j < NSUB; ++j) {
+        float acc[8];
+        w.acc_ld(j, acc);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gr[8 * j + i] += acc[i];
+      }
+      w.done();
+    };
+
+    // ---- preds_before[u+1] = out(h_end) ----
+    out_backward(X2, a.grad_preds_before, (int64_t)u + 1, u >= 0 && (ke & 1));
+
+    // ---- Euler steps, last to first ----
+    float tn = kmax > 0 ? ldg_na(kn + kmax * R) : 0.0f;
+    float tc_next = kmax > 0 ? ldg_na(kn + (kmax - 1) * R) : 0.0f;
+    float delta_k = 0.0f;                                        // dt of the step being differentiated
+    if (kmax > 0) {
+      // d loss / d f of the last step: delta * g
+      const float delta = __fsub_rn(tn, tc_next);
+      delta_k = delta;
+#pragma unroll
+      for (int j = 0; j < NSUB; ++j) {
+        float d[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = delta * gr[8 * j + i];
+        st8g(pd(kmax - 1, L, j), d);
+        w.emit(j, d);                                            // -> d * W_ode[L]
+      }
+    }
+    for (int k = kmax - 1; k >= 0; --k) {
+      tn = tc_next;                                              // t_k
+      tc_next = ldg_na(kn + (k > 0 ? k - 1 : 0) * R);            // t_{k-1}
+      if (w.g == 0) {
+        static_assert(MAX_DX == 2, "aux row layout assumes d_x <= 2");
+        const bool two = T.d_x > 1;
+        const float xv[8] = {1.0f, xs[0], two ? xs[1] : tn, two ? tn : delta_k, two ? delta_k : 0.0f, 0.0f, 0.0f, 0.0f};
+        st8g(cx + (int64_t)k * (R * 8), xv);
+      }
+      for (int l = L; l >= 1; --l) {
+        float z[8];
+        ld8g(pa(k, l, 0), z);
+        if (l > 1) prefetch_l2(pa(k, l - 1, 0)); else if (sc_kind != NJODE_SCALE_IDENTITY) prefetch_l2(pa(k, 0, 0));
+        w.wait_acc();
+#pragma unroll
+        for (int j = 0; j < NSUB; ++j) {
+          float acc[8], zn[8];
+          if (j + 1 < NSUB) ld8g(pa(k, l, j + 1), zn);
+          w.acc_ld(j, acc);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] *= act_grad_from_out<ACT>(z[i]);      // d loss / d (pre-activation of layer l-1)
+          st8g(pd(k, l - 1, j), acc);
+          w.emit(j, acc);                                        // -> d * W_ode[l-1]
+          if (j + 1 < NSUB) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) z[i] = zn[i];
+          }
+        }
+        w.done();
+      }
+      // d * W_ode[0][:, :H] = d loss / d s(h_k); fused with the next step's first operand delta_{k-1} * g
+      const float delta_prev = __fsub_rn(tn, tc_next);           // (unused when k == 0)
+      w.wait_acc();
+#pragma unroll
+      for (int j = 0; j < NSUB; ++j) {
+        float acc[8];
+        w.acc_ld(j, acc);
+        if (sc_kind != NJODE_SCALE_IDENTITY) {
+          float hs[8];
+          ld8g(pa(k, 0, j), hs);
+          scale8(sc_kind, hs);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gr[8 * j + i] = fmaf(acc[i], scale_grad_rt(sc_kind, hs[i]), gr[8 * j + i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gr[8 * j + i] += acc[i];
+        }
+        if (k > 0) {
+          float d[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[i] = delta_prev * gr[8 * j + i];
+          st8g(pd(k - 1, L, j), d);
+          w.emit(j, d);
+        }
+      }
+      w.done();
+      delta_k = delta_prev;
+    }
+
+    // ---- preds[u] = out(h_0), then the jump net ----
+    out_backward(X1, a.grad_preds, u, u >= 0);
+    if (w.g == 0) {
+      const float xv[8] = {1.0f, xr[0], xr[1], 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};     // xr[1] = 0 when d_x = 1
+      st8g(cx + (int64_t)X3 * (R * 8), xv);
+    }
+    // d (pre-activation of jump layer L) = g * act'(h_0)
+#pragma unroll
+    for (int j = 0; j < NSUB; ++j) {
+      float z[8], d[8];
+      ld8g(pa(0, 0, j), z);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = gr[8 * j + i] * act_grad_from_out<ACT>(z[i]);
+      st8g(pd(X3, L, j), d);
+      w.emit(j, d);                                              // -> d * W_jump[L]
+    }
+    for (int l = L; l >= 1; --l) {
+      float z[8];
+      ld8g(pa(X3, l - 1, 0), z);
+      w.wait_acc();
+#pragma unroll
+      for (int j = 0; j < NSUB; ++j) {
+        float acc[8], zn[8];
+        if (j + 1 < NSUB) ld8g(pa(X3, l - 1, j + 1), zn);
+        w.acc_ld(j, acc);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] *= act_grad_from_out<ACT>(z[i]);        // d (pre-activation of jump layer l-1)
+        st8g(pd(X3, l - 1, j), acc);
+        if (l > 1) w.emit(j, acc);                               // -> d * W_jump[l-1]
+        if (j + 1 < NSUB) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) z[i] = zn[i];
+        }
+      }
+      w.done();
+    }
+  }
+}
+
+template <int HW, int ACT, bool BWD>
+__global__ void __launch_bounds__(NT, 1) k_wide_sweep(SweepArgs a, const float* __restrict__ img) {
+  extern __shared__ uint8_t smem_raw[];
+  using C = Cfg<HW>;
+  const int warp = threadIdx.x >> 5;
+  {
+    Smem<HW> sm(smem_raw);
+    Ctl& ctl = *sm.ctl;
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < C::NSTAGE; ++i) { umma::mbar_init(&ctl.full[i], 1); umma::mbar_init(&ctl.empty[i], 1); }
+      for (int i = 0; i < 4; ++i) umma::mbar_init(&ctl.ops[i], NWARP_W);
+      umma::mbar_init(&ctl.accd[0], 1);
+      umma::mbar_init(&ctl.accd[1], 1);
+      umma::fence_mbar_init();
+    }
+    if (warp == 0) umma::tmem_alloc(&ctl.tmem_base, C::TMEM_COLS);
+    if (warp < NWARP_W) load_small<HW>(*sm.sw, a.T, a.params + (int64_t)(blockIdx.x % a.T.S) * a.T.stack_floats);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+  }
+  if (warp < NWARP_W) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    if (BWD) bwd_worker<HW, ACT>(a, smem_raw); else fwd_worker<HW, ACT>(a, smem_raw);
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == NWARP_W) issuer<HW, BWD>(a, smem_raw);
+    else if (threadIdx.x == NT_W + 32) producer<HW, BWD>(a, smem_raw, img);
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    Smem<HW> sm(smem_raw);
+    umma::tmem_free(*reinterpret_cast<volatile uint32_t*>(&sm.ctl->tmem_base), C::TMEM_COLS);
+  }
+}
+
+template <int HW, int ACT>
+int launch_wide(const SweepArgs& a, const float* img, cudaStream_t st, bool backward) {
+  if (a.n_tiles == 0) return NJODE_OK;
+  const size_t smem = Smem<HW>::bytes();
+  if (backward) {
+    NJODE_CUDA_OK(cudaFuncSetAttribute(k_wide_sweep<HW, ACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    njode_timing_begin(2, st);
+    k_wide_sweep<HW, ACT, true><<<a.n_workers, NT, smem, st>>>(a, img);
+    njode_timing_end(2, st);
+    NJODE_LAUNCH_OK("k_wide_sweep<reverse>");
+  } else {
+    NJODE_CUDA_OK(cudaFuncSetAttribute(k_wide_sweep<HW, ACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    njode_timing_begin(1, st);
+    k_wide_sweep<HW, ACT, false><<<a.n_workers, NT, smem, st>>>(a, img);
+    njode_timing_end(1, st);
+    NJODE_LAUNCH_OK("k_wide_sweep<forward>");
+  }
+  return NJODE_OK;
+}
+
+template <int HW>
+int dispatch_wide(const SweepArgs& a, const float* img, cudaStream_t st, bool backward) {
+  switch (a.desc.activation) {
+    case NJODE_ACT_RELU: return launch_wide<HW, NJODE_ACT_RELU>(a, img, st, backward);
+    case NJODE_ACT_TANH: return launch_wide<HW, NJODE_ACT_TANH>(a, img, st, backward);
+    case NJODE_ACT_SIGMOID: return launch_wide<HW, NJODE_ACT_SIGMOID>(a, img, st, backward);
+    case NJODE_ACT_ELU: return launch_wide<HW, NJODE_ACT_ELU>(a, img, st, backward);
+    case NJODE_ACT_LEAKY_RELU: return launch_wide<HW, NJODE_ACT_LEAKY_RELU>(a, img, st, backward);
+    default: return launch_wide<HW, NJODE_ACT_SELU>(a, img, st, backward);
+  }
+}
+
+template <int HW>
+int prep_images(const SweepArgs& a, float* img, cudaStream_t st, int transpose) {
+  const int64_t total = (int64_t)a.T.S * n_mats(a.T.L) * HW * HW;
+  k_wide_prep<HW><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a.T, a.params, img, transpose);
+  NJODE_LAUNCH_OK("k_wide_prep");
+  return NJODE_OK;
+}
+
+}  // namespace
+
+int njode_wide_supported(const NjodeDesc* d) {
+  const int O = d->shared_network ? d->d_y * d->num_moments : d->d_y;
+  return (d->hidden == 64 || d->hidden == 128) && d->n_hidden_layers >= 1 && d->n_hidden_layers <= NJODE_WIDE_LMAX &&
+         d->d_x <= MAX_DX && O <= MAX_O;
+}
+
+size_t njode_wide_image_bytes(const NjodeDesc* d) {
+  const int S = d->shared_network ? 1 : d->num_moments;
+  return njode_align_up((size_t)S * n_mats(d->n_hidden_layers) * 2 * d->hidden * d->hidden * sizeof(float), 1024);
+}
+
+static int sm_count_wide() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+// one CTA per SM (it owns the shared memory and, at H = 128, all of TMEM); a multiple of S
+int njode_wide_workers(const NjodeDesc* d, int64_t n_tiles) {
+  const int S = d->shared_network ? 1 : d->num_moments;
+  int64_t per_stack = sm_count_wide() / S;
+  if (per_stack < 1) per_stack = 1;
+  if (per_stack > n_tiles) per_stack = n_tiles > 0 ? n_tiles : 1;
+  return (int)(per_stack * S);
+}
+
+int njode_wide_forward(const SweepArgs& a, float* images, cudaStream_t st) {
+  int rc = a.desc.hidden == 128 ? prep_images<128>(a, images, st, 0) : prep_images<64>(a, images, st, 0);
+  if (rc) return rc;
+  return a.desc.hidden == 128 ? dispatch_wide<128>(a, images, st, false) : dispatch_wide<64>(a, images, st, false);
+}
+
+int njode_wide_backward(const SweepArgs& a, float* images, cudaStream_t st) {
+  int rc = a.desc.hidden == 128 ? prep_images<128>(a, images, st, 1) : prep_images<64>(a, images, st, 1);
+  if (rc) return rc;
+  rc = a.desc.hidden == 128 ? dispatch_wide<128>(a, images, st, true) : dispatch_wide<64>(a, images, st, true);
+  if (rc) return rc;
+  return njode_wide_wgrad(a, st);
+}
+
+int njode_wide_sweep_status(unsigned* out_host) {
+  NJODE_CUDA_OK(cudaMemcpyFromSymbol(out_host, g_status, sizeof(unsigned)));
+  return NJODE_OK;
+}

@@ -1,0 +1,100 @@
+// njode_wide.cuh -- geometry and small device helpers shared by the "wide" tcgen05 kernels
+// (njode_wide.cu: forward / reverse chain sweeps, njode_wgrad.cu: weight-gradient GEMM) for
+// hidden_dim in {64, 128} and up to 3 hidden layers (BASELINE configs 4 and 5).
+//
+// Checkpoint geometry of this flavour.  A tile of 128 observation units owns (kmax + 1 + NJODE_WIDE_XSLOTS)
+// checkpoint slots; a slot is (L + 1) planes of [H/8 column chunks][128 rows][8 floats] (chunk-major: a warp
+// moving one chunk of 32 rows touches 1 KB contiguous).  The buffer holds two halves of equal size:
+//   half A (written by the forward sweep)              half D (written by the reverse sweep)
+//   slot k <= kmax : plane 0 = h before Euler step k   slot k < kmax: plane l = d loss / d (pre-activation
+//                    (after the last one for k = kmax)                of ODE layer l) of step k, l = 0..L
+//                    plane l = output of ODE layer l-1
+//   slot X1 = kmax+1 (readout at h_0), X2 = kmax+2 (readout at h_end):
+//                    plane l (1..L) = output of out-net       plane l (0..L-1) = d / d (pre-activation of
+//                    layer l-1                                out-net layer l)
+//   slot X3 = kmax+3 (jump net): plane l (0..L-1) = output    plane l (0..L) = d / d (pre-activation of jump
+//                    of jump layer l                          layer l)
+// The weight-gradient kernel contracts pairs (D plane, A plane) over rows; see njode_wgrad.cu.
+#pragma once
+#include "njode_common.cuh"
+#include "njode_umma.cuh"
+
+#define NJODE_WIDE_XSLOTS 3
+#define NJODE_WIDE_LMAX 3
+
+namespace wide {
+
+constexpr int R = 128;                 // rows (observation units) per tile
+constexpr int NWARP_W = 16;            // worker warps: warp w serves TMEM lane quadrant w % 4 and column group w / 4
+constexpr int NT_W = NWARP_W * 32;     // 512 row workers
+constexpr int MAX_DX = 2, MAX_O = 4;
+
+template <int HW>
+struct Cfg {
+  static constexpr int CG = HW / 4;                   // columns per column group (one group per worker warp of a quadrant)
+  static constexpr int NSUB = CG / 8;                 // sub-steps of 8 columns: the hand-over granularity of a layer
+  static constexpr int STAGE_HALF = HW * 128;         // bytes of the hi (or lo) part of a weight stage: HW rows x 32 k
+  static constexpr int STAGE_BYTES = 2 * STAGE_HALF;  // a stage = the 4 k-steps (one per column group) of one sub-step
+  static constexpr int NSTAGE = 6;
+  static constexpr uint32_t A_HI = 0, A_LO = HW, ACC0 = 2 * HW, TMEM_COLS = 4 * HW;
+  static constexpr int PL = R * HW;                   // floats per checkpoint plane
+};
+
+// matrices that run as chain GEMMs, in image order: jump layers 1..L, ODE layers 0..L, out-net layers 0..L-1
+__host__ __device__ __forceinline__ int mat_jump(int L, int l) { (void)L; return l - 1; }
+__host__ __device__ __forceinline__ int mat_ode(int L, int l) { return L + l; }
+__host__ __device__ __forceinline__ int mat_out(int L, int l) { return 2 * L + 1 + l; }
+__host__ __device__ __forceinline__ int n_mats(int L) { return 3 * L + 1; }
+
+// ---- memory helpers (explicit address spaces: through plain pointers the compiler falls back to generic LD/ST) ----
+__device__ __forceinline__ void ld8s(const float* __restrict__ src, float (&v)[8]) {     // 32-byte aligned, SHARED
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(src);
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a));
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(a));
+}
+__device__ __forceinline__ void ld8g(const float* __restrict__ src, float (&v)[8]) {     // one LDG.256, no L1 allocation
+  asm volatile("ld.global.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(src));
+}
+__device__ __forceinline__ void st8g(float* __restrict__ dst, const float (&v)[8]) {     // one STG.256
+  asm volatile("st.global.v8.f32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+               :: "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "l"(dst) : "memory");
+}
+__device__ __forceinline__ float ldg_na(const float* __restrict__ p) {
+  float v;
+  asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
+// ---- mbarrier / bulk-copy (TMA engine, 1-D) helpers ------------------------------------------------
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(umma::smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy executed by the TMA engine; completion is counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(umma::smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(umma::smem_u32(bar)) : "memory");
+}
+
+// sticky diagnostic word (njode_device_status): bit 2 / 3 / 4 = wide forward / reverse / weight-gradient kernel
+// gave up on an mbarrier.  The kernel then TRAPS: a protocol failure must never produce silently wrong numbers.
+// (each translation unit owns its status word: no relocatable device code in this build)
+__device__ __forceinline__ void wait_or_die(uint64_t* bar, uint32_t parity, unsigned* status, unsigned bit) {
+  if (!umma::mbar_wait(bar, parity)) {
+    atomicOr(status, bit);
+    __threadfence_system();
+    __trap();
+  }
+}
+
+}  // namespace wide
+
+// flavour entry points (njode_wide.cu / njode_wgrad.cu)
+int    njode_wide_supported(const NjodeDesc* d);
+size_t njode_wide_image_bytes(const NjodeDesc* d);                 // one direction (forward or transposed images)
+int    njode_wide_workers(const NjodeDesc* d, int64_t n_tiles);
+int    njode_wide_forward(const SweepArgs& a, float* images, cudaStream_t st);
+int    njode_wide_backward(const SweepArgs& a, float* images, cudaStream_t st);   // chain sweep, then weight gradients
+int    njode_wide_wgrad(const SweepArgs& a, cudaStream_t st);
+int    njode_wide_status(unsigned* out_host);

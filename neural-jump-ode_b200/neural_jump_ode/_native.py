@@ -13,13 +13,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get(
     "NJODE_B200_LIB", os.path.normpath(os.path.join(_HERE, "..", "lib", "libnjode_b200.so")))
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enums (include/njode.h)
 ACT = {"relu": 0, "tanh": 1, "sigmoid": 2, "elu": 3, "leaky_relu": 4, "selu": 5}
 SCALE = {"identity": 0, "none": 0, "tanh": 1, "sigmoid": 2}
 VAR = {"direct": 0, "second_moment": 1}
-IMPL = {"auto": 0, "generic": 1, "tiled": 2, "rowtile": 3}
+IMPL = {"auto": 0, "generic": 1, "tiled": 2, "rowtile": 3, "wide": 4}
+IMPL_NAME = {v: k for k, v in IMPL.items()}
 HDR_TOTAL_STEPS, HDR_TOTAL_SLOTS, HDR_NUM_TILES, HDR_KMAX, HDR_WORDS = 0, 1, 2, 3, 8
 ARENA_KENC, ARENA_PERM, ARENA_TILE_KMAX, ARENA_TILE_SLOT_OFF, ARENA_HEADER, ARENA_KNOTS, ARENA_WORDS = 0, 1, 2, 3, 4, 5, 8
 EINVAL, ECUDA, EWORKSPACE, ECAPACITY = -1, -2, -3, -4
@@ -51,6 +52,7 @@ SIGNATURES = {
     "njode_param_count": (_I64, [_DESC]),
     "njode_num_stacks": (_I32, [_DESC]),
     "njode_tile_rows": (_I32, [_DESC]),
+    "njode_selected_impl": (_I32, [_DESC]),
     "njode_schedule_workspace_bytes": (_SZ, [_I64, _I64, _I32]),
     "njode_schedule_build": (C.c_int, [_DESC, _P, _P, _I64, _I64, _I32, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "njode_schedule_knots": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I32, _DESC, _P, _P]),

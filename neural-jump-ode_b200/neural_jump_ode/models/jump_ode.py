@@ -333,7 +333,7 @@ class NeuralJumpODE(nn.Module):
         self.activation = activation
         self.input_scaling = input_scaling
         self.dropout_rate = dropout_rate
-        self.kernel_impl = "auto"                 # 'auto' | 'generic' | 'rowtile' | 'tiled' (testing / profiling knob)
+        self.kernel_impl = "auto"                 # 'auto' | 'generic' | 'rowtile' | 'tiled' | 'wide' (testing / profiling knob)
         self._dp_group = None                     # see enable_data_parallel
         self.auto_flatten = True                  # see flatten_parameters
         self.eager_backward = True                # see _LossFunction

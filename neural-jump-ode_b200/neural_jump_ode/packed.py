@@ -176,7 +176,8 @@ class PackedBatch:
 
     @staticmethod
     def schedule_key(desc, tile_rows, n_tiles):
-        return (bool(desc.has_dt), float(desc.dt), int(tile_rows), int(n_tiles))
+        # (the flavour is part of the key: tiled and wide share tile_rows but not the slots a tile owns)
+        return (bool(desc.has_dt), float(desc.dt), int(tile_rows), int(n_tiles), int(nat.load().njode_selected_impl(desc)))
 
     def step_counts(self, desc) -> torch.Tensor:
         """Per-observation Euler step counts (int32, device); the last observation of a trajectory has 0."""

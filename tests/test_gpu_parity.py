@@ -42,6 +42,8 @@ def _impl_ok(mk, impl):
     H, L = mk["hidden_dim"], mk.get("n_hidden_layers", 1)
     if impl == "rowtile":
         return H % 32 == 0 and 32 <= H <= 128 and L <= 3
+    if impl == "wide":
+        return H in (64, 128) and L <= 3 and mk["input_dim"] <= 2
     return True
 
 
@@ -56,7 +58,7 @@ def _run(model, bt, bv, loss_kwargs):
     return preds, before, loss
 
 
-@pytest.mark.parametrize("impl", ["generic", "rowtile", "auto"])
+@pytest.mark.parametrize("impl", ["generic", "rowtile", "wide", "auto"])
 @pytest.mark.parametrize("name", golden_names())
 def test_golden_parity(name, impl):
     """Same inputs and weights as the unmodified reference -> same preds, preds_before, loss, grads."""
@@ -137,7 +139,7 @@ def _random_batch(B, seed, n_steps=100, ragged=True, d_x=1):
     return bt, bv
 
 
-@pytest.mark.parametrize("impl", ["generic", "rowtile", "auto"])
+@pytest.mark.parametrize("impl", ["generic", "rowtile", "wide", "auto"])
 @pytest.mark.parametrize("case", range(len(CASES)))
 def test_oracle_parity_random(case, impl):
     """Seeded ragged batch of 96 trajectories against the float64 interval-flattened oracle."""
@@ -163,7 +165,7 @@ def test_oracle_parity_random(case, impl):
     assert np.array_equal(preds.batch.step_counts(desc).cpu().numpy(), ref["K"])
 
 
-@pytest.mark.parametrize("impl,hidden", [("auto", 32), ("rowtile", 64)])
+@pytest.mark.parametrize("impl,hidden", [("auto", 32), ("rowtile", 64), ("wide", 64)])
 def test_oracle_parity_many_tiles(impl, hidden):
     """More tiles than persistent CTAs (several rounds per CTA, partial last tile, deferred weight-gradient merges
     across tile boundaries): 2 500 ragged trajectories against the float64 oracle, plus run-to-run bitwise
@@ -568,7 +570,9 @@ def test_tiled_kernels_selected_and_healthy():
     m = NeuralJumpODE(1, 32, 1, dt_ode_step=0.01, num_moments=2).to(DEV)
     assert lib.njode_tile_rows(m.descriptor()) == 128
     m64 = NeuralJumpODE(1, 64, 1, dt_ode_step=0.01, num_moments=2)
-    assert lib.njode_tile_rows(m64.descriptor()) == 32
+    assert lib.njode_tile_rows(m64.descriptor()) == 128 and lib.njode_selected_impl(m64.descriptor()) == nat.IMPL["wide"]
+    m50 = NeuralJumpODE(1, 50, 1, dt_ode_step=0.01, num_moments=2)
+    assert lib.njode_tile_rows(m50.descriptor()) == 32
     bt, bv = _random_batch(300, seed=21)
     preds, before, loss = _run(m, bt, bv, dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0]))
     assert torch.isfinite(loss)

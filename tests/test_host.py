@@ -102,17 +102,23 @@ def test_abi_tiling_and_arena_layout():
     from neural_jump_ode import NeuralJumpODE, _native as nat
     lib = nat.load()
     tiled = NeuralJumpODE(1, 32, 1, dt_ode_step=0.01, num_moments=2, shared_network=True).descriptor()
-    rowt = NeuralJumpODE(1, 64, 1, dt_ode_step=0.01, num_moments=2).descriptor()
-    assert lib.njode_tile_rows(tiled) == 128 and lib.njode_tile_rows(rowt) == 32
-    assert lib.njode_ckpt_row_floats(tiled) == 64 and lib.njode_ckpt_row_floats(rowt) == 128
+    rowt = NeuralJumpODE(1, 96, 1, dt_ode_step=0.01, num_moments=2).descriptor()
+    wide = NeuralJumpODE(1, 128, 1, dt_ode_step=0.01, num_moments=2, n_hidden_layers=3).descriptor()
+    assert lib.njode_tile_rows(tiled) == 128 and lib.njode_tile_rows(rowt) == 32 and lib.njode_tile_rows(wide) == 128
+    assert [lib.njode_selected_impl(d) for d in (tiled, rowt, wide)] == [nat.IMPL["tiled"], nat.IMPL["rowtile"], nat.IMPL["wide"]]
+    # wide: (L+1) activation planes + (L+1) data-gradient planes + 8 aux floats per row and slot
+    assert lib.njode_ckpt_row_floats(tiled) == 64 and lib.njode_ckpt_row_floats(rowt) == 192
+    assert lib.njode_ckpt_row_floats(wide) == 2 * 4 * 128 + 8
+    assert lib.njode_forward_workspace_bytes(wide) >= 2 * 10 * 2 * 128 * 128 * 4     # S x (3L+1) split weight images
     sms = 148                                            # what the library assumes when it cannot ask a device
     for N in (0, 1, 31, 32, 33, 1000, 4 * 128 * sms // 4, 40960, 10 ** 6):
         full = (N + 127) // 128
         units = 32 if 4 * full <= sms else 64 if full <= sms else 128
         assert lib.njode_num_tiles(tiled, N) == (N + units - 1) // units, N
         assert lib.njode_num_tiles(rowt, N) == (N + 31) // 32, N
+        assert lib.njode_num_tiles(wide, N) == full, N
     assert lib.njode_num_tiles(tiled, -1) == -1
-    for desc in (tiled, rowt):
+    for desc in (tiled, rowt, wide):
         rows = lib.njode_tile_rows(desc)
         for N, B in ((1, 1), (40960, 4096), (10 ** 6, 10 ** 5)):
             lay0, lay1 = (C.c_int64 * nat.ARENA_WORDS)(), (C.c_int64 * nat.ARENA_WORDS)()
