@@ -224,6 +224,10 @@ int njode_set_kernel_timing(int32_t which, void* ev_start, void* ev_stop);
  * gives up TRAPS after setting its bit, so every later CUDA call on the context fails: a protocol failure can never
  * yield silently wrong numbers.  Synchronises the device. */
 int njode_device_status(uint32_t* status_host);
+/* bring-up detail of the WIDE kernels, uint32[4]: {sweep status, first sweep wait site that gave up, weight-gradient
+ * status, its first site}; site = code | warp << 8 | block << 16.  With NJODE_NO_TRAP=1 in the environment a kernel
+ * that gives up records the site and runs on without waiting (results are garbage) instead of trapping. */
+int njode_device_status_detail(uint32_t* words_host);
 /* Number of CUDA kernels this library has launched in this process (every launch site counts itself);
  * reset != 0 returns the count and sets it to zero.  Measurement aid for bench.py's `gpu_launches`. */
 int64_t njode_kernel_launches(int32_t reset);

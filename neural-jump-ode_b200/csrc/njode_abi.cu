@@ -95,11 +95,20 @@ extern "C" int64_t njode_kernel_launches(int32_t reset) {
 
 extern "C" int njode_device_status(uint32_t* status_host) {
   if (!status_host) NJODE_FAIL(NJODE_EINVAL, "njode_device_status: null output");
-  unsigned v = 0, w1 = 0, w2 = 0;
+  unsigned v = 0, w1[2] = {0, 0}, w2[2] = {0, 0};
   int rc = njode_tiled_status(&v);
-  if (!rc) rc = njode_wide_sweep_status(&w1);
-  if (!rc) rc = njode_wide_wgrad_status(&w2);
-  *status_host = v | w1 | w2;
+  if (!rc) rc = njode_wide_sweep_status(w1);
+  if (!rc) rc = njode_wide_wgrad_status(w2);
+  *status_host = v | w1[0] | w2[0];
+  return rc;
+}
+
+// bring-up detail of the wide kernels: {sweep status, first sweep site that gave up, weight-gradient status, its first site}
+// (site = code | warp << 8 | block << 16; codes in njode_wide.cu / njode_wgrad.cu)
+extern "C" int njode_device_status_detail(uint32_t* words_host) {
+  if (!words_host) NJODE_FAIL(NJODE_EINVAL, "njode_device_status_detail: null output");
+  int rc = njode_wide_sweep_status(words_host);
+  if (!rc) rc = njode_wide_wgrad_status(words_host + 2);
   return rc;
 }
 

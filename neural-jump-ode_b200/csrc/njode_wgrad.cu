@@ -22,7 +22,8 @@
 namespace {
 using namespace wide;
 
-__device__ unsigned g_status = 0;
+__device__ unsigned g_status[2] = {0, 0};
+__device__ unsigned g_notrap = 0;
 
 constexpr int NT3 = NT_W + 128;        // 16 loader / merge warps + one warpgroup whose first warp issues the MMAs (setmaxnreg: 104 / 56 registers)
 constexpr int NSTAGE3 = 3;
@@ -119,19 +120,23 @@ __device__ __forceinline__ void wg_issuer(const SweepArgs& a, uint8_t* ring, Ctl
   const int wi = blockIdx.x / S, n_w = gridDim.x / S;
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&ctl.tmem_base);
   const uint32_t ring_s = umma::smem_u32(ring);
-  constexpr uint32_t idesc_q = umma::idesc_tf32(HW, G::NACC, 1, 1), idesc_x = umma::idesc_tf32(HW, 16, 1, 1);
+  // M = 128 also at H = 64: same tensor time as M = 64 (the floor is max(M, 128) * N / 256 cycles), standard accumulator
+  // layout (row = lane); the A descriptor then runs two blocks past the D tile into the neighbouring (finite) tiles of
+  // the stage, whose products land in accumulator rows 64..127 that nobody reads
+  constexpr uint32_t idesc_q = umma::idesc_tf32(128, G::NACC, 1, 1), idesc_x = umma::idesc_tf32(128, 16, 1, 1);
   Cursor cu;
   cursor_init(cu, a, wi, n_w);
   uint32_t sc = 0, ic = 0;
+  Diag dg{g_status, g_notrap, 16u, false};
   while (cu.valid) {
     const bool has_q = !(cu.kind == CAT_READOUT || cu.kind == CAT_JUMP0);
     const uint32_t b = ic & 1u, use = ic >> 1;
-    if (use > 0) wait_or_die(&ctl.merged[b], (use - 1) & 1u, &g_status, 16u);     // the accumulator's previous content is merged
+    if (use > 0) wait_or_die(&ctl.merged[b], (use - 1) & 1u, dg, 5);     // the accumulator's previous content is merged
     const uint32_t acc = tmem + (b ? FRESH1 : FRESH0);
 #pragma unroll 1
     for (int qs = 0; qs < R / SROWS; ++qs, ++sc) {
       const uint32_t stage = sc % NSTAGE3, sround = sc / NSTAGE3;
-      wait_or_die(&ctl.full[stage], sround & 1u, &g_status, 16u);
+      wait_or_die(&ctl.full[stage], sround & 1u, dg, 6);
       umma::fence_after_sync();
       if (umma::elect_one()) {
         const uint32_t sb = ring_s + stage * G::STAGE;
@@ -174,10 +179,11 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* ring, Ctl
   float* const part = a.partials + (int64_t)blockIdx.x * T.stack_floats;
   const bool loader = warp < G::NLOAD;
   const int sc_kind = a.desc.input_scaling;
+  Diag dg{g_status, g_notrap, 16u, false};
 
-  // accumulator row of this thread: M = 128 -> lane = row; M = 64 -> row i lives in lane (i % 16) + 32 * (i / 16)
-  const bool has_row = HW == 128 ? true : lane < 16;
-  const int irow = HW == 128 ? q * 32 + lane : q * 16 + lane;
+  // accumulator row (output feature) of this thread = its TMEM lane; at H = 64 lanes 64..127 hold nothing useful
+  const int irow = q * 32 + lane;
+  const bool has_row = irow < HW;
 
   auto zero_run = [&]() {
     uint32_t z[4] = {0u, 0u, 0u, 0u};
@@ -198,7 +204,7 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* ring, Ctl
   // running += fresh[b]  (IEEE adds), then release the fresh accumulator
   auto merge = [&](uint32_t ic) {
     const uint32_t b = ic & 1u;
-    wait_or_die(&ctl.fresh_done[b], (ic >> 1) & 1u, &g_status, 16u);
+    wait_or_die(&ctl.fresh_done[b], (ic >> 1) & 1u, dg, 7);
     umma::fence_after_sync();
     const uint32_t fr = my_t + (b ? FRESH1 : FRESH0);
 #pragma unroll
@@ -307,7 +313,7 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* ring, Ctl
       float (&p)[8] = pb[qs & 1];
       float (&qv)[8] = qb[qs & 1];
       float (&x)[8] = xb[qs & 1];
-      wait_or_die(&ctl.empty[stage], (sround & 1u) ^ 1u, &g_status, 16u);
+      wait_or_die(&ctl.empty[stage], (sround & 1u) ^ 1u, dg, 8);
       const uint32_t sb = ring_s + stage * G::STAGE;
       uint32_t hi[8], lo[8];
       if (loader) {
@@ -384,11 +390,17 @@ __global__ void __launch_bounds__(NT3, 1) k_wide_wgrad(SweepArgs a) {
 template <int HW>
 int launch_wgrad(const SweepArgs& a, cudaStream_t st) {
   const size_t smem = 1024 + (size_t)NSTAGE3 * G3<HW>::STAGE + sizeof(Ctl3) + 16;
+  if (njode_no_trap_env()) { const unsigned one = 1; NJODE_CUDA_OK(cudaMemcpyToSymbolAsync(g_notrap, &one, sizeof(one), 0, cudaMemcpyHostToDevice, st)); }
   NJODE_CUDA_OK(cudaFuncSetAttribute(k_wide_wgrad<HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   njode_timing_begin(3, st);
   k_wide_wgrad<HW><<<a.n_workers, NT3, smem, st>>>(a);
   njode_timing_end(3, st);
   NJODE_LAUNCH_OK("k_wide_wgrad");
+  if (njode_debug_sync_env()) {
+    const cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) NJODE_FAIL(NJODE_ECUDA, "NJODE_DEBUG_SYNC: k_wide_wgrad failed: %s", cudaGetErrorString(e));
+    fprintf(stderr, "NJODE_DEBUG_SYNC: k_wide_wgrad ok\n");
+  }
   return NJODE_OK;
 }
 
@@ -400,6 +412,6 @@ int njode_wide_wgrad(const SweepArgs& a, cudaStream_t st) {
 }
 
 int njode_wide_wgrad_status(unsigned* out_host) {
-  NJODE_CUDA_OK(cudaMemcpyFromSymbol(out_host, g_status, sizeof(unsigned)));
+  NJODE_CUDA_OK(cudaMemcpyFromSymbol(out_host, g_status, 2 * sizeof(unsigned)));
   return NJODE_OK;
 }

@@ -23,7 +23,8 @@
 namespace {
 using namespace wide;
 
-__device__ unsigned g_status = 0;
+__device__ unsigned g_status[2] = {0, 0};
+__device__ unsigned g_notrap = 0;
 
 constexpr int NT = NT_W + 128;         // 16 worker warps + one warpgroup holding the MMA issuer warp and the weight producer warp
 // Register budget: the CTA launches with 640 x 96 registers and setmaxnreg moves registers inside that pool:
@@ -112,12 +113,13 @@ __device__ __forceinline__ void producer(const SweepArgs& a, uint8_t* raw, const
   const int s = blockIdx.x % S, worker = blockIdx.x / S, n_workers = gridDim.x / S;
   const uint8_t* simg = reinterpret_cast<const uint8_t*>(img) + (size_t)s * n_mats(L) * C::NSUB * C::STAGE_BYTES;
   uint32_t sc = 0;
+  Diag dg{g_status, g_notrap, BWD ? 8u : 4u, false};
   auto load = [&](int m) {
     const uint8_t* src = simg + (size_t)m * C::NSUB * C::STAGE_BYTES;
 #pragma unroll 1
     for (int j = 0; j < C::NSUB; ++j, ++sc) {
       const uint32_t stage = sc % C::NSTAGE, round = sc / C::NSTAGE;
-      wait_or_die(&ctl.empty[stage], (round & 1u) ^ 1u, &g_status, BWD ? 8u : 4u);
+      wait_or_die(&ctl.empty[stage], (round & 1u) ^ 1u, dg, 1);
       mbar_expect_tx(&ctl.full[stage], C::STAGE_BYTES);
       bulk_g2s(sm.ring + (size_t)stage * C::STAGE_BYTES, src + (size_t)j * C::STAGE_BYTES, C::STAGE_BYTES, &ctl.full[stage]);
     }
@@ -152,7 +154,7 @@ __device__ __forceinline__ void issuer(const SweepArgs& a, uint8_t* raw) {
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&ctl.tmem_base);
   const uint32_t ring_s = umma::smem_u32(sm.ring);
   constexpr uint32_t idesc = umma::idesc_tf32(128, HW, 0, 0);
-  constexpr unsigned bit = BWD ? 8u : 4u;
+  Diag dg{g_status, g_notrap, BWD ? 8u : 4u, false};
   uint32_t sc = 0, gi = 0;
   for (int64_t round = 0; round * n_workers < a.n_tiles; ++round) {
     const int64_t tile = snake_tile(round, worker, n_workers);
@@ -164,8 +166,8 @@ __device__ __forceinline__ void issuer(const SweepArgs& a, uint8_t* raw) {
 #pragma unroll 1
       for (int j = 0; j < C::NSUB; ++j, ++sc) {
         const uint32_t stage = sc % C::NSTAGE, sround = sc / C::NSTAGE;
-        wait_or_die(&ctl.ops[j], gi & 1u, &g_status, bit);            // the A columns of this sub-step are in TMEM
-        wait_or_die(&ctl.full[stage], sround & 1u, &g_status, bit);   // its weights are in the ring
+        wait_or_die(&ctl.ops[j], gi & 1u, dg, 2);            // the A columns of this sub-step are in TMEM
+        wait_or_die(&ctl.full[stage], sround & 1u, dg, 3);   // its weights are in the ring
         umma::fence_after_sync();
         if (umma::elect_one()) {
           const uint64_t dbh = umma::desc_k(ring_s + stage * C::STAGE_BYTES);
@@ -195,8 +197,8 @@ struct WorkerCtx {
   int lane, q, g, row, col0;
   uint32_t lane_base;      // TMEM address of (this lane quadrant, column col0)
   uint32_t gi;             // GEMM counter (same sequence as the issuer's)
-  unsigned bit;
-  __device__ __forceinline__ WorkerCtx(Smem<HW>& sm, unsigned bit_) : ctl(*sm.ctl), sw(*sm.sw), gi(0), bit(bit_) {
+  Diag dg;
+  __device__ __forceinline__ WorkerCtx(Smem<HW>& sm, unsigned bit_) : ctl(*sm.ctl), sw(*sm.sw), gi(0), dg{g_status, g_notrap, bit_, false} {
     const int warp = threadIdx.x >> 5;
     lane = threadIdx.x & 31;
     q = warp & 3;
@@ -219,7 +221,7 @@ struct WorkerCtx {
   }
   // wait for the accumulator of GEMM gi (call once per GEMM, then acc_ld for each sub-chunk, then done())
   __device__ __forceinline__ void wait_acc() {
-    wait_or_die(&ctl.accd[gi & 1u], (gi >> 1) & 1u, &g_status, bit);
+    wait_or_die(&ctl.accd[gi & 1u], (gi >> 1) & 1u, dg, 4);
     umma::fence_after_sync();
   }
   __device__ __forceinline__ void acc_ld(int j, float (&v)[8]) { umma::tmem_ld8(lane_base + C::ACC0 + (gi & 1u) * HW + 8 * j, v); }
@@ -708,22 +710,33 @@ __global__ void __launch_bounds__(NT, 1) k_wide_sweep(SweepArgs a, const float* 
   }
 }
 
+static int debug_sync(const char* what, cudaStream_t st) {
+  if (!njode_debug_sync_env()) return NJODE_OK;
+  const cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) NJODE_FAIL(NJODE_ECUDA, "NJODE_DEBUG_SYNC: %s failed: %s", what, cudaGetErrorString(e));
+  fprintf(stderr, "NJODE_DEBUG_SYNC: %s ok\n", what);
+  return NJODE_OK;
+}
+
 template <int HW, int ACT>
 int launch_wide(const SweepArgs& a, const float* img, cudaStream_t st, bool backward) {
   if (a.n_tiles == 0) return NJODE_OK;
   const size_t smem = Smem<HW>::bytes();
+  if (njode_no_trap_env()) { const unsigned one = 1; NJODE_CUDA_OK(cudaMemcpyToSymbolAsync(g_notrap, &one, sizeof(one), 0, cudaMemcpyHostToDevice, st)); }
   if (backward) {
     NJODE_CUDA_OK(cudaFuncSetAttribute(k_wide_sweep<HW, ACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     njode_timing_begin(2, st);
     k_wide_sweep<HW, ACT, true><<<a.n_workers, NT, smem, st>>>(a, img);
     njode_timing_end(2, st);
     NJODE_LAUNCH_OK("k_wide_sweep<reverse>");
+    return debug_sync("k_wide_sweep<reverse>", st);
   } else {
     NJODE_CUDA_OK(cudaFuncSetAttribute(k_wide_sweep<HW, ACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     njode_timing_begin(1, st);
     k_wide_sweep<HW, ACT, false><<<a.n_workers, NT, smem, st>>>(a, img);
     njode_timing_end(1, st);
     NJODE_LAUNCH_OK("k_wide_sweep<forward>");
+    return debug_sync("k_wide_sweep<forward>", st);
   }
   return NJODE_OK;
 }
@@ -791,6 +804,6 @@ int njode_wide_backward(const SweepArgs& a, float* images, cudaStream_t st) {
 }
 
 int njode_wide_sweep_status(unsigned* out_host) {
-  NJODE_CUDA_OK(cudaMemcpyFromSymbol(out_host, g_status, sizeof(unsigned)));
+  NJODE_CUDA_OK(cudaMemcpyFromSymbol(out_host, g_status, 2 * sizeof(unsigned)));
   return NJODE_OK;
 }

@@ -16,6 +16,8 @@
 //                    of jump layer l                          layer l)
 // The weight-gradient kernel contracts pairs (D plane, A plane) over rows; see njode_wgrad.cu.
 #pragma once
+#include <cstdlib>
+
 #include "njode_common.cuh"
 #include "njode_umma.cuh"
 
@@ -78,14 +80,43 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 }
 
 // sticky diagnostic word (njode_device_status): bit 2 / 3 / 4 = wide forward / reverse / weight-gradient kernel
-// gave up on an mbarrier.  The kernel then TRAPS: a protocol failure must never produce silently wrong numbers.
-// (each translation unit owns its status word: no relocatable device code in this build)
-__device__ __forceinline__ void wait_or_die(uint64_t* bar, uint32_t parity, unsigned* status, unsigned bit) {
-  if (!umma::mbar_wait(bar, parity)) {
-    atomicOr(status, bit);
-    __threadfence_system();
-    __trap();
+// gave up on an mbarrier; bits 8.. = code of the wait site.  The kernel then TRAPS: a protocol failure must never
+// produce silently wrong numbers.  Bring-up aid: with NJODE_NO_TRAP=1 in the environment the thread records the
+// site and carries on without waiting any more (garbage results, but the status word can be read back).
+// (each translation unit owns its status / no-trap words: no relocatable device code in this build)
+struct Diag {
+  unsigned* status;          // [0] = sticky word, [1] = first site that gave up: code | warp << 8 | block << 16
+  unsigned notrap;           // bring-up mode (read once per role from the translation unit's g_notrap)
+  unsigned bit;
+  bool dead;
+};
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity, uint32_t spins) {
+  const uint32_t a = umma::smem_u32(bar);
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < spins; ++spin) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    if (done) return true;
   }
+  return false;
+}
+__device__ __forceinline__ void wait_or_die(uint64_t* bar, uint32_t parity, Diag& dg, unsigned code) {
+  if (dg.dead) return;
+  if (dg.notrap ? mbar_wait_bounded(bar, parity, 1u << 17) : umma::mbar_wait(bar, parity)) return;    // 2^24 polls
+  atomicOr(dg.status, dg.bit | (1u << (8 + code)));
+  atomicCAS(dg.status + 1, 0u, code | ((threadIdx.x >> 5) << 8) | (blockIdx.x << 16));
+  __threadfence_system();
+  if (dg.notrap) dg.dead = true; else __trap();
+}
+// host side of the bring-up switch
+static inline int njode_no_trap_env() {
+  static const int v = [] { const char* e = getenv("NJODE_NO_TRAP"); return e ? atoi(e) : 0; }();
+  return v;
+}
+static inline int njode_debug_sync_env() {
+  static const int v = [] { const char* e = getenv("NJODE_DEBUG_SYNC"); return e ? atoi(e) : 0; }();
+  return v;
 }
 
 }  // namespace wide

@@ -75,6 +75,7 @@ SIGNATURES = {
     "njode_set_kernel_timing": (C.c_int, [_I32, _P, _P]),
     "njode_ffma_peak": (C.c_int, [C.POINTER(C.c_float)]),
     "njode_device_status": (C.c_int, [C.POINTER(C.c_uint32)]),
+    "njode_device_status_detail": (C.c_int, [C.POINTER(C.c_uint32)]),
     "njode_kernel_launches": (_I64, [_I32]),
 }
 

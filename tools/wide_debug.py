@@ -165,7 +165,9 @@ def main():
     import ctypes
     stt = ctypes.c_uint32(99)
     nat.check(nat.load().njode_device_status(ctypes.byref(stt)), "njode_device_status")
-    print(f"  device status word: {stt.value}")
+    det = (ctypes.c_uint32 * 4)()
+    nat.check(nat.load().njode_device_status_detail(det), "njode_device_status_detail")
+    print(f"  device status word: {stt.value}  detail: " + " ".join(hex(v) for v in det))
     print("WIDE DEBUG", "OK" if ok and stt.value == 0 else "FAILED")
     return 0 if ok else 1
 
