@@ -189,7 +189,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ou_shared_b4096", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None, help="override trajectories per GPU")
-    ap.add_argument("--kernel-impl", default="auto", choices=["auto", "generic", "tiled"])
+    ap.add_argument("--kernel-impl", default="auto", choices=["auto", "generic", "tiled", "rowtile", "wide"])
     ap.add_argument("--cpu-sample", type=int, default=384, help="trajectories in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true", help="launch the timed steps eagerly instead of replaying a CUDA graph")

@@ -72,7 +72,13 @@ static inline ParamTable njode_make_table(const NjodeDesc* d) {
 
 template <int ACT>
 __device__ __forceinline__ float act_fwd(float a) {
-  if (ACT == NJODE_ACT_RELU) return fmaxf(a, 0.0f);
+  if (ACT == NJODE_ACT_RELU) {
+    // NaN-propagating maximum, as torch.relu (clamp_min): the reference turns a NaN observation into NaN predictions,
+    // loss and gradients (tests/golden/nan_observation_h32); fmaxf would silently drop the NaN
+    float r;
+    asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(a));
+    return r;
+  }
   if (ACT == NJODE_ACT_TANH) return tanhf(a);
   if (ACT == NJODE_ACT_SIGMOID) return 1.0f / (1.0f + expf(-a));
   if (ACT == NJODE_ACT_ELU) return a > 0.0f ? a : expm1f(a);
@@ -193,6 +199,10 @@ struct SweepArgs {
   const float* grad_preds_before;
   float* partials;           // [n_workers][stack_floats] per-CTA weight-gradient partial sums
   int32_t n_workers;         // CTAs (multiple of S); worker w serves stack w % S
+  // wide flavour: the tensor core adds into its FP32 accumulator with truncation, so a sum built by n MMAs comes out
+  // ~n x 2.1e-8 too small in magnitude (round 1 measured the drift, round 2 modelled it: DESIGN.md); the epilogues
+  // scale what they read back by (1 + that) -- the factors for a chain GEMM and for a weight-gradient plane pair
+  float comp_chain, comp_wgrad;
 };
 
 #define NJODE_GENERIC_TILE_ROWS 32

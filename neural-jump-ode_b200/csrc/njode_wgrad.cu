@@ -179,6 +179,7 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* ring, Ctl
   float* const part = a.partials + (int64_t)blockIdx.x * T.stack_floats;
   const bool loader = warp < G::NLOAD;
   const int sc_kind = a.desc.input_scaling;
+  const float comp = a.comp_wgrad;
   Diag dg{g_status, g_notrap, 16u, false};
 
   // accumulator row (output feature) of this thread = its TMEM lane; at H = 64 lanes 64..127 hold nothing useful
@@ -214,7 +215,7 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* ring, Ctl
       ld4(my_t + RUN + t, r4);
       umma::wait_ld();
 #pragma unroll
-      for (int i = 0; i < 4; ++i) r4[i] += f[i];
+      for (int i = 0; i < 4; ++i) r4[i] = fmaf(f[i], comp, r4[i]);      // (comp: accumulator truncation compensation)
       st4(my_t + RUN + t, r4);
     }
     umma::wait_st();

@@ -197,6 +197,7 @@ struct WorkerCtx {
   int lane, q, g, row, col0;
   uint32_t lane_base;      // TMEM address of (this lane quadrant, column col0)
   uint32_t gi;             // GEMM counter (same sequence as the issuer's)
+  float comp;              // accumulator read-back scale (SweepArgs::comp_chain)
   Diag dg;
   __device__ __forceinline__ WorkerCtx(Smem<HW>& sm, unsigned bit_) : ctl(*sm.ctl), sw(*sm.sw), gi(0), dg{g_status, g_notrap, bit_, false} {
     const int warp = threadIdx.x >> 5;
@@ -224,7 +225,11 @@ struct WorkerCtx {
     wait_or_die(&ctl.accd[gi & 1u], (gi >> 1) & 1u, dg, 4);
     umma::fence_after_sync();
   }
-  __device__ __forceinline__ void acc_ld(int j, float (&v)[8]) { umma::tmem_ld8(lane_base + C::ACC0 + (gi & 1u) * HW + 8 * j, v); }
+  __device__ __forceinline__ void acc_ld(int j, float (&v)[8]) {
+    umma::tmem_ld8(lane_base + C::ACC0 + (gi & 1u) * HW + 8 * j, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= comp;
+  }
   __device__ __forceinline__ void done() { ++gi; }
 };
 
@@ -264,6 +269,7 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
   constexpr int CG = C::CG, NSUB = C::NSUB;
   Smem<HW> sm(raw);
   WorkerCtx<HW> w(sm, 4u);
+  w.comp = a.comp_chain;
   SmallW<HW>& sw = w.sw;
   const ParamTable& T = a.T;
   const int L = T.L, dx = T.d_x, O = T.O, sc_kind = a.desc.input_scaling;
@@ -462,6 +468,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
   constexpr int CG = C::CG, NSUB = C::NSUB;
   Smem<HW> sm(raw);
   WorkerCtx<HW> w(sm, 8u);
+  w.comp = a.comp_chain;
   SmallW<HW>& sw = w.sw;
   const ParamTable& T = a.T;
   const int L = T.L, O = T.O, sc_kind = a.desc.input_scaling;
@@ -789,13 +796,31 @@ int njode_wide_workers(const NjodeDesc* d, int64_t n_tiles) {
   return (int)(per_stack * S);
 }
 
-int njode_wide_forward(const SweepArgs& a, float* images, cudaStream_t st) {
+// Accumulator truncation compensation (SweepArgs::comp_*).  Model: every tcgen05.mma adds its K = 8 products into the
+// FP32 accumulator with round-toward-zero; a CPU simulation of exactly the MMA order used here (tools/sim_3xtf32.py)
+// gives a mean relative shrink of 8.6e-7 for a 48-MMA sum (H = 128 chain GEMM, every weight-gradient plane pair) and
+// 3.5e-7 for a 24-MMA one (H = 64 chain GEMM) -- 2.1e-8 per MMA that lands on a full-size accumulator, the drift
+// round 1 measured on the hardware.  Calibrated on the B200 against the float64 oracle (tools/wide_debug.py, mean
+// signed error of the large gradient entries with the correction off / on: -2.5e-6 / +1.3e-6 at H = 128, L = 3 and
+// -1.1e-6 / +2.8e-7 at H = 64): the hardware loses ~0.7 of the model's figure, which is what is applied.
+// NJODE_WIDE_COMP scales the correction (0 = off) for such calibration runs.
+static void set_comp(SweepArgs& a) {
+  static const float scale = [] { const char* e = getenv("NJODE_WIDE_COMP"); return e ? (float)atof(e) : 1.0f; }();
+  a.comp_chain = 1.0f + scale * (a.desc.hidden == 128 ? 6.0e-7f : 2.7e-7f);
+  a.comp_wgrad = 1.0f + scale * 5.5e-7f;
+}
+
+int njode_wide_forward(const SweepArgs& a_in, float* images, cudaStream_t st) {
+  SweepArgs a = a_in;
+  set_comp(a);
   int rc = a.desc.hidden == 128 ? prep_images<128>(a, images, st, 0) : prep_images<64>(a, images, st, 0);
   if (rc) return rc;
   return a.desc.hidden == 128 ? dispatch_wide<128>(a, images, st, false) : dispatch_wide<64>(a, images, st, false);
 }
 
-int njode_wide_backward(const SweepArgs& a, float* images, cudaStream_t st) {
+int njode_wide_backward(const SweepArgs& a_in, float* images, cudaStream_t st) {
+  SweepArgs a = a_in;
+  set_comp(a);
   int rc = a.desc.hidden == 128 ? prep_images<128>(a, images, st, 1) : prep_images<64>(a, images, st, 1);
   if (rc) return rc;
   rc = a.desc.hidden == 128 ? dispatch_wide<128>(a, images, st, true) : dispatch_wide<64>(a, images, st, true);

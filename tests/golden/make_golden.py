@@ -8,10 +8,21 @@ trajectory) directly by file path -- ``neural_jump_ode.utils`` needs matplotlib,
 is not installed here, and is not on the path.  The reference does not exist on
 the GPU box, so the resulting ``*.npz`` files are committed next to this script.
 
-Each case stores: the model/loss configuration (json), packed inputs, the
+Each case stores: the model/loss configuration (json, incl. the weight seed), packed inputs, the
 reference's state_dict, preds, preds_before, loss, every parameter gradient
 (``None`` gradients stored as zeros + a ``has_grad`` flag), and the float32
 (t_last, t_next) pair of every ``euler_step`` call in call order.
+
+Conditioning.  ReLU / LeakyReLU / SELU have a derivative jump at 0: a pre-activation that sits within
+float32 noise of 0 makes the gradient a coin flip between ANY two float32 implementations (the
+reference on another BLAS included).  Round 2 found one: with weight seed 0 the hidden-64 ragged case
+had a first-layer ODE pre-activation of 5.5e-9 (true value) against a layer scale of 0.5 at x0 = 1,
+t = 0 -- three Euler steps whose contribution (1e-3 of that gradient) appears or not depending on the
+last bit of a 67-term sum.  ``kink_margin`` (float64 re-evaluation of the reference: smallest
+|pre-activation| / largest |pre-activation| over every Linear that feeds a kinked activation) is now
+stored with each case, and a case whose margin is below 1e-6 -- ten times the float32 noise of a hidden-layer
+sum, relative to the layer's largest value -- gets the next weight seed.  (The margin of a case shrinks with
+its size: among the 1.4 M hidden values of the 104-trajectory case the closest sits 2e-6 from the kink.)
 """
 import importlib.util
 import json
@@ -145,14 +156,69 @@ def main():
             data=(t2, v2)),
     }
 
+    # BASELINE config 4's real grid (dt 0.001, 1000 grid steps, obs 0.05 -> 50 observations, ~1037 Euler steps per
+    # trajectory): float32 error has ten times longer to accumulate than in the 100-step cases
+    cases["heston_h128_l3_tanh_dt001"] = dict(
+        model=dict(input_dim=1, hidden_dim=128, output_dim=1, dt_ode_step=0.001, num_moments=2,
+                   n_hidden_layers=3, activation="tanh"),
+        loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct"),
+        data=data("heston", 2, 0.05, n_steps=1000, **heston))
+    # BASELINE config 1's mini-batch tail: n_train 1000 in batches of 128 leaves 104 trajectories
+    cases["bs_h32_sep_b104_tail"] = dict(
+        model=dict(input_dim=1, hidden_dim=32, output_dim=1, dt_ode_step=0.01, num_moments=2),
+        loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct"),
+        data=data("black_scholes", 104, 0.1, **bs))
+    # a NaN observation (the hybrid generator produces one in ~1/2000 paths, data_generation.py:154): the reference
+    # propagates it -- NaN predictions from that observation on, NaN loss, NaN gradients
+    nt, nv = data("black_scholes", 3, 0.1, **bs)
+    nv = [v.clone() for v in nv]
+    nv[1][4, 0] = float("nan")
+    cases["nan_observation_h32"] = dict(
+        model=dict(input_dim=1, hidden_dim=32, output_dim=1, dt_ode_step=0.01, num_moments=2),
+        loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct"),
+        data=(nt, nv))
+
+    KINKED = (torch.nn.ReLU, torch.nn.LeakyReLU, torch.nn.SELU)
+
+    def kink_margin(model, bt, bv):
+        """float64 re-evaluation: min |pre-activation| / max |pre-activation| over the Linears feeding a kinked activation"""
+        import copy
+        m64 = copy.deepcopy(model).double()
+        m64.euler_step = type(model).euler_step.__get__(m64)
+        worst = [float("inf")]
+        hooks = []
+        for mod in m64.modules():
+            if isinstance(mod, torch.nn.Sequential):
+                kids = list(mod.children())
+                for a, b in zip(kids, kids[1:] + [None]):
+                    nxt = b
+                    if isinstance(a, torch.nn.Linear):
+                        # (Dropout sits between a Linear and the next Linear, never between a Linear and its activation)
+                        if isinstance(nxt, KINKED):
+                            def hook(_m, _i, out):
+                                v = out.detach().abs()
+                                v = v[torch.isfinite(v)]
+                                if v.numel():
+                                    worst[0] = min(worst[0], float(v.min() / v.max().clamp_min(1e-300)))
+                            hooks.append(a.register_forward_hook(hook))
+        with torch.no_grad():
+            m64([t.double() for t in bt], [v.double() for v in bv])
+        for h in hooks:
+            h.remove()
+        return worst[0]
+
     for name, case in cases.items():
         mk = dict(case["model"])
-        torch.manual_seed(0)
-        model = jo.NeuralJumpODE(**mk)
-        # make outputs less trivially small so relative errors mean something
         bt, bv = case["data"]
         bt = [t.to(torch.float32) for t in bt]
         bv = [v.to(torch.float32) for v in bv]
+        for seed in range(16):
+            torch.manual_seed(seed)
+            model = jo.NeuralJumpODE(**mk)
+            margin = kink_margin(model, bt, bv)
+            if margin >= 1e-6:
+                break
+            print(f"{name}: weight seed {seed} puts a pre-activation within {margin:.1e} (relative) of an activation kink; next seed")
 
         log = []
         orig = model.euler_step
@@ -171,7 +237,9 @@ def main():
         off = np.zeros(len(n) + 1, np.int64)
         off[1:] = np.cumsum(n)
         out = {
-            "config_json": np.frombuffer(json.dumps(dict(model=mk, loss=lk)).encode(), dtype=np.uint8),
+            "config_json": np.frombuffer(json.dumps(dict(model=mk, loss=lk, seed=seed,
+                                                         kink_margin=None if margin == float("inf") else margin)).encode(),
+                                         dtype=np.uint8),
             "times": torch.cat(bt).numpy(),
             "values": torch.cat(bv).numpy(),
             "offsets": off,
@@ -186,7 +254,7 @@ def main():
             out["has_grad/" + k] = np.array(p.grad is not None)
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **out)
-        print(f"{name}: B={len(bt)} N={off[-1]} steps={len(log)} loss={loss.item():.6f} "
+        print(f"{name}: seed={seed} kink_margin={margin:.2e} B={len(bt)} N={off[-1]} steps={len(log)} loss={loss.item():.6f} "
               f"params={sum(p.numel() for p in model.parameters())} -> {os.path.getsize(path) / 1024:.0f} KiB")
 
 

@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden, golden_names, rel_err
+from conftest import load_golden, golden_names, rel_err, loss_close
 from oracle import njode_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -72,12 +72,12 @@ def test_golden_parity(name, impl):
                                                for t in g["batch_times"]]
     assert rel_err(torch.cat(list(preds)).cpu(), g["preds"]) <= TOL
     assert rel_err(torch.cat(list(before)).cpu(), g["preds_before"]) <= TOL
-    assert abs(loss.item() - g["ref_loss"]) <= TOL_LOSS * abs(g["ref_loss"])
+    assert loss_close(loss.item(), g["ref_loss"], TOL_LOSS)
     first = torch.as_tensor(g["offsets"][:-1])
     assert float(torch.cat(list(before)).cpu()[first].abs().max()) == 0.0
     for k, p in model.named_parameters():
         assert p.grad is not None and g["has_grad"][k], k
-        if float(g["grads"][k].abs().max()) == 0.0:      # stacks of moments >= 2: exactly zero, as in the reference
+        if float(torch.nan_to_num(g["grads"][k], nan=1.0).abs().max()) == 0.0:      # stacks of moments >= 2: exactly zero, as in the reference
             assert float(p.grad.abs().max()) == 0.0, k
         assert rel_err(p.grad.cpu(), g["grads"][k]) <= TOL, k
 
