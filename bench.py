@@ -5,11 +5,15 @@
     python bench.py --impl reference --steps K --warmup W    (CPU port of the reference on a bounded sample)
 
 One "step" = forward sweep + nj_ode_loss + reverse sweep over one batch of the workload (Adam and
-host packing excluded).  Default workload = BASELINE.json configs[1]: experiment_ou.py
---shared-network --cache-data, batch 4096 per GPU, n_steps 100, obs 0.1, hidden 32, 1 layer,
-activation 'identity' (-> ReLU), 2 moments, dt_ode_step 0.01 (run_ou.sh:36).  Data is synthetic
-(on-device OU paths of that shape), weights are random-init of that architecture.
-Prints ONE JSON line on rank 0.
+host packing excluded).  Default workload = BASELINE.json configs[2], the largest
+configuration that fits one GPU: experiment_heston.py defaults (hidden 32, 1 layer, relu, 2 moments,
+separate networks) scaled to 262 144 trajectories in ONE batch, n_steps 200, dt_ode_step 0.005, obs 0.1.
+With --gpus N the SAME global batch is split N ways (strong scaling, as BASELINE asks: "262144
+trajectories ... 1/2/4/8 B200").  Other workloads (--workload): configs[1] (OU shared, 4096 per GPU),
+configs[0] at batch 128, the config-4 shape (hidden 128 / 3 layers / tanh, dt 0.001) at a small batch and
+at its named size (131 072 trajectories per GPU = 1 M on eight, run in waves), the config-5 mixed ragged
+hidden-64 batch.  Data is synthetic (on-device paths of that shape), weights are random-init of that
+architecture.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import ctypes
@@ -31,34 +35,44 @@ import torch  # noqa: E402
 WORKLOADS = {
     # BASELINE.json configs[1]
     "ou_shared_b4096": dict(
-        process="ornstein_uhlenbeck", pkw=dict(theta=1.0, mu=0.5, sigma=0.3, x0=0.0), B=4096, n_steps=100, T=1.0,
+        scaling="weak", process="ornstein_uhlenbeck", pkw=dict(theta=1.0, mu=0.5, sigma=0.3, x0=0.0), B=4096, n_steps=100, T=1.0,
         obs_fraction=0.1, model=dict(input_dim=1, hidden_dim=32, output_dim=1, dt_ode_step=0.01, num_moments=2,
                                      n_hidden_layers=1, activation="identity", shared_network=True),
         loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct")),
     # BASELINE.json configs[0] at batch 128 (the reference's CPU-runnable case)
     "bs_sep_b128": dict(
-        process="black_scholes", pkw=dict(mu=0.1, sigma=0.5, x0=1.0), B=128, n_steps=100, T=1.0,
+        scaling="weak", process="black_scholes", pkw=dict(mu=0.1, sigma=0.5, x0=1.0), B=128, n_steps=100, T=1.0,
         obs_fraction=0.1, model=dict(input_dim=1, hidden_dim=32, output_dim=1, dt_ode_step=0.01, num_moments=2),
         loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct")),
-    # BASELINE.json configs[2]
+    # BASELINE.json configs[2]: B is the GLOBAL batch, split over the ranks (strong scaling)
     "heston_sep_b262144": dict(
-        process="heston", pkw=dict(mu=0.5, kappa=2.0, theta=0.04, xi=0.5, rho=-0.5, x0=1.0, v0=0.04), B=262144,
+        scaling="strong", process="heston", pkw=dict(mu=0.5, kappa=2.0, theta=0.04, xi=0.5, rho=-0.5, x0=1.0, v0=0.04), B=262144,
         n_steps=200, T=1.0, obs_fraction=0.1,
         model=dict(input_dim=1, hidden_dim=32, output_dim=1, dt_ode_step=0.005, num_moments=2),
         loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct")),
-    # BASELINE.json configs[4] (per-GPU slice of the sweep): mixed-process ragged batch, hidden 64 -> generic kernels
+    # BASELINE.json configs[4] (per-GPU slice of the sweep): mixed-process ragged batch, hidden 64 -> wide tcgen05 kernels
     "mixed_h64_ragged": dict(
-        process="mixed", pkw=dict(), B=32768, n_steps=100, T=1.0, obs_fraction=(0.02, 0.2),
+        scaling="weak", process="mixed", pkw=dict(), B=32768, n_steps=100, T=1.0, obs_fraction=(0.02, 0.2),
         model=dict(input_dim=1, hidden_dim=64, output_dim=1, dt_ode_step=0.01, num_moments=2),
         loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct")),
-    # BASELINE.json configs[3] shape at a batch the generic kernels finish in seconds (hidden 128, 3 layers, tanh)
+    # BASELINE.json configs[3] shape at a small batch (hidden 128, 3 layers, tanh): one sweep, no waves
     "heston_h128_l3": dict(
-        process="heston", pkw=dict(mu=0.5, kappa=2.0, theta=0.04, xi=0.5, rho=-0.5, x0=1.0, v0=0.04), B=2048,
+        scaling="weak", process="heston", pkw=dict(mu=0.5, kappa=2.0, theta=0.04, xi=0.5, rho=-0.5, x0=1.0, v0=0.04), B=2048,
         n_steps=1000, T=1.0, obs_fraction=0.05,
         model=dict(input_dim=1, hidden_dim=128, output_dim=1, dt_ode_step=0.001, num_moments=2, n_hidden_layers=3,
                    activation="tanh"),
         loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct")),
+    # BASELINE.json configs[3] at its named size: 1 M trajectories on 8 GPUs = 131 072 per GPU, run in waves of 4096
+    # trajectories (10 MB of checkpoints per trajectory: NeuralJumpODE.forward_backward_waves)
+    "heston_h128_l3_1m": dict(
+        scaling="weak", process="heston", pkw=dict(mu=0.5, kappa=2.0, theta=0.04, xi=0.5, rho=-0.5, x0=1.0, v0=0.04), B=131072,
+        wave=4096, n_steps=1000, T=1.0, obs_fraction=0.05,
+        model=dict(input_dim=1, hidden_dim=128, output_dim=1, dt_ode_step=0.001, num_moments=2, n_hidden_layers=3,
+                   activation="tanh"),
+        loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct")),
 }
+DEFAULT_WORKLOAD = "heston_sep_b262144"
+METRIC = "trajectory-ODE-steps/sec (fwd+bwd)"     # the same string in both arms: the driver divides one by the other
 
 
 def make_batch(wl, n_traj, device, seed):
@@ -170,15 +184,31 @@ def run_reference(args, wl, name):
         steps_tot += steps
     value = steps_tot / t_tot
     sample = f"{n_traj} trajectories of {name} per step ({steps_tot // args.steps} trajectory-ODE-steps), fwd+loss+bwd"
-    out = {"impl": "reference", "metric": "trajectory-ODE-steps/sec (fwd+bwd)", "value": value,
+    out = {"impl": "reference", "metric": METRIC, "value": value,
            "unit": "trajectory-ODE-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f32", "data": "synthetic", "config": {"workload": name, "sample": sample},
+           "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "timing": "host wall clock (CPU)",
+           "config": {"workload": name, "sample": sample},
            "cpu_baseline": {"value": value, "unit": "trajectory-ODE-steps/s", "cores": torch.get_num_threads(),
                             "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": "trajectory-ODE-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
+
+
+# the kernels of each flavour that bench.py can time alone (njode_set_kernel_timing which = 1 forward / 2 reverse
+# sweep / 3 weight-gradient GEMM), the share of the algorithmic flops each of them carries, and the pipe that bounds it
+FLAVOURS = {
+    "tiled": dict(bound="tensor", pipe="tcgen05 kind::tf32, 3xTF32 split (FP32-accurate); chain operands from TMEM, weight-gradient tiles from shared memory",
+                  kernels={1: ("k_tiled_forward", "fwd", 1.0), 2: ("k_tiled_backward (data + weight gradients)", "bwd", 1.0)}),
+    "wide": dict(bound="tensor", pipe="tcgen05 kind::tf32, 3xTF32 split (FP32-accurate); activations in TMEM, weights streamed by cp.async.bulk, weight gradients as a split-K GEMM",
+                 kernels={1: ("k_wide_sweep<forward>", "fwd", 1.0), 2: ("k_wide_sweep<reverse> (data gradients)", "bwd", 0.5),
+                          3: ("k_wide_wgrad (weight gradients)", "bwd", 0.5)}),
+    "rowtile": dict(bound="fp32", pipe="FP32 FMA (CUDA cores), operands from shared memory",
+                    kernels={1: ("k_rowtile_forward", "fwd", 1.0), 2: ("k_rowtile_backward", "bwd", 1.0)}),
+    "generic": dict(bound="fp32", pipe="FP32 FMA (CUDA cores), warp per unit",
+                    kernels={1: ("k_generic_forward", "fwd", 1.0), 2: ("k_generic_backward", "bwd", 1.0)}),
+}
 
 
 def main():
@@ -187,11 +217,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="ou_shared_b4096", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=None, help="override trajectories per GPU")
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="override the workload's batch (global batch for strong-scaling workloads, per GPU otherwise)")
+    ap.add_argument("--wave", type=int, default=None, help="trajectories per wave (workloads that run in waves)")
     ap.add_argument("--kernel-impl", default="auto", choices=["auto", "generic", "tiled", "rowtile", "wide"])
     ap.add_argument("--cpu-sample", type=int, default=384, help="trajectories in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     ap.add_argument("--no-cuda-graph", action="store_true", help="launch the timed steps eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -200,6 +232,8 @@ def main():
     wl = dict(WORKLOADS[name])
     if args.batch:
         wl["B"] = args.batch
+    if args.wave:
+        wl["wave"] = args.wave
 
     if args.impl == "reference":
         run_reference(args, wl, name)
@@ -207,7 +241,7 @@ def main():
 
     import torch.distributed as dist
     from neural_jump_ode import NeuralJumpODE, nj_ode_loss, PackedBatch, _native as nat
-    from neural_jump_ode.simulation import make_packed_batch
+    from neural_jump_ode.sharding import shard_bounds
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -226,38 +260,57 @@ def main():
     if world > 1:
         model.enable_data_parallel()           # gradient all-reduce (NCCL over NVLink) inside the reverse sweep
     params = model.flat_parameters()
-    B = wl["B"]                                # per GPU: weak scaling
-    B_global = B * world
-    batch = make_batch(wl, B, dev, 1000 + rank)
+    strong = wl["scaling"] == "strong"
+    if strong:                                 # one global batch, every rank integrates its contiguous slice
+        B_global = wl["B"]
+        whole = make_batch(wl, B_global, dev, 1000)
+        bounds = shard_bounds(B_global, world)
+        batch = whole.slice(bounds[rank], bounds[rank + 1]) if world > 1 else whole
+        batch = PackedBatch(batch.times.clone(), batch.values.clone(), batch.offsets.clone(), batch.sizes)
+        del whole
+    else:                                      # fixed batch per GPU
+        batch = make_batch(wl, wl["B"], dev, 1000 + rank)
+        B_global = wl["B"] * world
+    B = batch.B
+    wave = wl.get("wave")
     desc = model.descriptor()
-    sched = batch.schedule(desc)               # --cache-data: schedule built once, outside the timed region
-    total_steps_rank = sched.total_steps
+    impl = nat.IMPL_NAME[lib.njode_selected_impl(desc)]
     lk = wl["loss"]
 
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
 
-    def step():
+    def run_on(b):
         for p in params:
             p.grad = None
-        preds, before = model.forward_packed(batch)
-        loss = nj_ode_loss(batch, None, preds, before, traj_scale=1.0 / B_global, **lk)
+        if wave:                               # checkpoints of the whole batch do not fit: waves of `wave` trajectories
+            return model.forward_backward_waves(b, wave, traj_scale=1.0 / B_global, **lk)
+        preds, before = model.forward_packed(b)
+        loss = nj_ode_loss(b, None, preds, before, traj_scale=1.0 / B_global, **lk)
         loss.backward()                        # world > 1: ONE in-place all-reduce of the flat gradient inside backward
         return loss
+
+    def step():
+        return run_on(batch)
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(args.warmup):               # --cache-data: schedules are built here, outside the timed region
         step()
     sync_all()
+    subs = [batch.slice(lo, min(lo + wave, B)) for lo in range(0, B, wave)] if wave else [batch]
+    scheds = [next(iter(b_._schedules.values())) for b_ in subs]
+    total_steps_rank = sum(s_.total_steps for s_ in scheds)
+    sched = scheds[0]
 
     # The step is a fixed sequence of ~10 launches on a cached batch (--cache-data): capture it once in a CUDA graph
     # and replay it, so the host (8 ranks share the box's cores) is out of the timed region's critical path.
-    # Same kernels, same work; falls back to eager launches if capture is not possible.
+    # Same kernels, same work; falls back to eager launches if capture is not possible.  Steps that run in waves
+    # (hundreds of milliseconds each, checkpoint buffers re-allocated per wave) are launched eagerly.
     run_step, graphed = step, False
-    if not args.no_cuda_graph:
+    if not args.no_cuda_graph and not wave:
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -311,80 +364,98 @@ def main():
     t_total_ms = float(t_dev.item())
     value = float(steps_all.item()) * args.steps / (t_total_ms * 1e-3)
 
-    # ---- dominant kernel (reverse sweep) timed alone with events on its stream -> roofline ----
-    bwd_ms = []
-    for i in range(min(args.steps, 10)):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        # torch.cuda.Event creates its cudaEvent lazily on first record: record once so the handle exists
-        e0.record(); e1.record()
-        torch.cuda.synchronize()
-        nat.check(lib.njode_set_kernel_timing(2, ctypes.c_void_p(e0.cuda_event), ctypes.c_void_p(e1.cuda_event)),
-                  "njode_set_kernel_timing")
-        step()
-        torch.cuda.synchronize()
-        bwd_ms.append(e0.elapsed_time(e1))
-    bwd_ms.sort()
-    bwd_med = bwd_ms[len(bwd_ms) // 2]
+    # ---- every sweep kernel of the flavour timed alone (events on its stream around that launch); the slowest is the
+    #      dominant kernel of the roofline block.  With waves the one-shot events catch the first wave's launches, so
+    #      the algorithmic flops are those of the first wave. ----
+    fl_spec = FLAVOURS[impl]
+    first = subs[0]
+    fl = algorithmic_flops(mk, scheds[0].total_steps, first.N, first.B)
+    kernel_ms = {}
+    for which in fl_spec["kernels"]:
+        samples = []
+        for i in range(min(args.steps, 7)):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            # torch.cuda.Event creates its cudaEvent lazily on first record: record once so the handle exists
+            e0.record(); e1.record()
+            torch.cuda.synchronize()
+            nat.check(lib.njode_set_kernel_timing(which, ctypes.c_void_p(e0.cuda_event), ctypes.c_void_p(e1.cuda_event)),
+                      "njode_set_kernel_timing")
+            run_on(first)
+            torch.cuda.synchronize()
+            samples.append(e0.elapsed_time(e1))
+        samples.sort()
+        kernel_ms[which] = samples[len(samples) // 2]
+    dom = max(kernel_ms, key=kernel_ms.get)
+    kname, kphase, kshare = fl_spec["kernels"][dom]
+    dom_flop = fl[kphase] * kshare
+    achieved = dom_flop / (kernel_ms[dom] * 1e-3) * 1e-12
     peak = ctypes.c_float(0.0)
     nat.check(lib.njode_ffma_peak(ctypes.byref(peak)), "njode_ffma_peak")
-    fl = algorithmic_flops(mk, total_steps_rank, batch.N, batch.B)
-    achieved = fl["bwd"] / (bwd_med * 1e-3) * 1e-12
+    peak_fma = float(peak.value)
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
     measured = json.load(open(peaks_file)) if os.path.exists(peaks_file) else {}
-    # measured DRAM traffic of the same kernel on this workload (one `ncu --set full` capture, profiles/)
+    bf16 = measured.get("bf16_tflops", 1590.0)          # fallback: B200_PROFILING.md
+    bf16_src = "MEASURED_PEAKS.json bf16_tflops (burst: the kernel is timed alone)" if "bf16_tflops" in measured else "fallback 1590 TFLOP/s (B200_PROFILING.md)"
+    # measured DRAM traffic of the same kernel on this workload (one `ncu --set full` capture per entry, profiles/)
     traffic = None
-    tfile = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
-    if os.path.exists(tfile):
-        traffic = json.load(open(tfile)).get(f"{name}:{B}", {}).get("reverse_sweep_dram_bytes_per_launch")
-    peak_fma = float(peak.value)
-    bf16 = measured.get("bf16_tflops")
-    roofline = {"bound": "tensor", "pipe": "tcgen05 kind::tf32 with the 3xTF32 split (FP32-accurate), operands from TMEM / shared memory",
-                "kernel": "reverse sweep (k_tiled_backward)", "achieved": achieved,
-                "peak": peak_fma, "unit": "TFLOP/s", "frac": achieved / peak_fma, "traffic": traffic,
-                "peak_source": "FP32-FMA peak measured in this process (njode_ffma_peak): the north star's denominator for "
-                               "FP32-accurate work; MEASURED_PEAKS.json has no FP32 figure. The tensor-pipe ceilings are "
-                               "given beside it: measured bf16 / 2 (tf32) / 3 (split) for 3xTF32",
-                "kernel_ms": bwd_med, "algorithmic_flop_per_launch": fl["bwd"],
-                "frac_of_3xtf32_tensor_peak": (achieved / (bf16 / 6.0)) if bf16 else None,
-                "frac_of_measured_bf16_tensor_peak": (achieved / bf16) if bf16 else None,
-                "whole_step_tflops": fl["total"] * args.steps / (t_total_ms * 1e-3) * 1e-12 / max(world, 1)}
+    for tfile in ("r2_dram_traffic.json", "r1_dram_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tfile)
+        if os.path.exists(tpath) and traffic is None:
+            entry = json.load(open(tpath)).get(f"{name}:{first.B}", {})
+            traffic = entry.get(f"which{dom}_dram_bytes_per_launch", entry.get("reverse_sweep_dram_bytes_per_launch") if dom == 2 else None)
+    if fl_spec["bound"] == "tensor":
+        # 3xTF32: three tf32 MMAs per FP32-accurate product, tf32 runs at half the bf16 rate -> bf16 / 6
+        peak_used = bf16 / 6.0
+        peak_source = (f"tensor pipe: {bf16_src} / 2 (kind::tf32) / 3 (the 3xTF32 split that makes the product FP32-accurate); "
+                       "the FP32-FMA peak measured in this process (njode_ffma_peak, the north star's FP32 denominator) is given beside it")
+    else:
+        peak_used = peak_fma
+        peak_source = "FP32-FMA peak measured in this process (njode_ffma_peak); MEASURED_PEAKS.json has no FP32 figure"
+    roofline = {"bound": "tensor" if fl_spec["bound"] == "tensor" else "fp32", "pipe": fl_spec["pipe"], "kernel": kname,
+                "flavour": impl, "achieved": achieved, "peak": peak_used, "unit": "TFLOP/s", "frac": achieved / peak_used,
+                "traffic": traffic, "peak_source": peak_source, "kernel_ms": kernel_ms[dom],
+                "algorithmic_flop_per_launch": dom_flop,
+                "all_kernels_ms": {fl_spec["kernels"][w][0]: kernel_ms[w] for w in kernel_ms},
+                "fp32_fma_peak_tflops": peak_fma, "frac_of_fp32_fma_peak": achieved / peak_fma,
+                "whole_step_tflops": fl["total"] * (total_steps_rank / max(scheds[0].total_steps, 1)) * args.steps / (t_total_ms * 1e-3) * 1e-12,
+                "whole_step_frac_of_fp32_fma_peak": fl["total"] * (total_steps_rank / max(scheds[0].total_steps, 1)) * args.steps / (t_total_ms * 1e-3) * 1e-12 / peak_fma}
 
     # ---- end to end through the public API: pinned host inputs -> H2D -> schedule -> fwd/loss/bwd -> loss D2H ----
-    h_times = batch.times.cpu().pin_memory()
-    h_values = batch.values.cpu().pin_memory()
-    h_off = batch.offsets.cpu().pin_memory()
-    sizes = batch.sizes
+    e2e = None
+    if not args.no_e2e:
+        h_times = batch.times.cpu().pin_memory()
+        h_values = batch.values.cpu().pin_memory()
+        h_off = batch.offsets.cpu().pin_memory()
+        sizes = batch.sizes
 
-    def e2e_step():
-        b = PackedBatch(h_times.to(dev, non_blocking=True), h_values.to(dev, non_blocking=True),
-                        h_off.to(dev, non_blocking=True), sizes)
-        for p in params:
-            p.grad = None
-        preds, before = model.forward_packed(b)
-        loss = nj_ode_loss(b, None, preds, before, traj_scale=1.0 / B_global, **lk)
-        loss.backward()
-        return loss.item()                     # device -> host read of the step's result (this rank's share of the loss)
+        def e2e_step():
+            b = PackedBatch(h_times.to(dev, non_blocking=True), h_values.to(dev, non_blocking=True),
+                            h_off.to(dev, non_blocking=True), sizes)
+            return run_on(b).item()            # device -> host read of the step's result (this rank's share of the loss)
 
-    for _ in range(3):
-        e2e_step()
-    sync_all()
-    e2e_ev = []
-    for _ in range(args.steps):
-        flush.zero_()
-        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        e2e_step()
-        b_.record()
-        e2e_ev.append((a, b_))
-    sync_all()
-    t_e2e = torch.tensor([sum(a.elapsed_time(b_) for a, b_ in e2e_ev)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = float(steps_all.item()) * args.steps / (float(t_e2e.item()) * 1e-3)
-    h2d = h_times.numel() * 4 + h_values.numel() * 4 + h_off.numel() * 8
-    d2h = 4 + 8 * nat.HDR_WORDS
+        n_e2e = args.steps if not wave else min(args.steps, 3)
+        for _ in range(3 if not wave else 1):
+            e2e_step()
+        sync_all()
+        e2e_ev = []
+        for _ in range(n_e2e):
+            flush.zero_()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            e2e_step()
+            b_.record()
+            e2e_ev.append((a, b_))
+        sync_all()
+        t_e2e = torch.tensor([sum(a.elapsed_time(b_) for a, b_ in e2e_ev)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        e2e_value = float(steps_all.item()) * n_e2e / (float(t_e2e.item()) * 1e-3)
+        h2d = h_times.numel() * 4 + h_values.numel() * 4 + h_off.numel() * 8
+        d2h = 4 + 8 * nat.HDR_WORDS * len(subs)
+        e2e = {"value": e2e_value, "unit": "trajectory-ODE-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "steps": n_e2e, "includes": "H2D of packed inputs from pinned memory, schedule build, fwd, loss, bwd, loss.item()"}
 
     if rank == 0:
         cpu = None
@@ -394,21 +465,19 @@ def main():
                    "sample": f"{args.cpu_sample} trajectories of {name} ({steps} trajectory-ODE-steps, {sec:.1f} s), "
                              f"fwd+loss+bwd, oracle.run_port (eager per-step port of jump_ode.py)",
                    "host_cpus": os.cpu_count()}
-        out = {"metric": "trajectory-ODE-steps/sec (fwd+bwd, device-timed)", "value": value,
+        out = {"metric": METRIC, "value": value,
                "unit": "trajectory-ODE-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": t_total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-               "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "ms_per_step": t_total_ms / args.steps, "higher_is_better": True, "scaling": wl["scaling"],
+               "vs_baseline": None, "dtype": "f32", "data": "synthetic", "timing": "device (CUDA events, max over ranks)",
                "config": {"workload": name, "process": wl["process"], "batch_per_gpu": B, "global_batch": B_global,
                           "n_steps": wl["n_steps"], "obs_fraction": wl["obs_fraction"], "model": mk,
                           "trajectory_ode_steps_per_gpu": total_steps_rank, "observations_per_gpu": batch.N,
-                          "parallelism": f"dp{world}", "kernel_impl": args.kernel_impl,
+                          "parallelism": f"dp{world}", "kernel_impl": args.kernel_impl, "kernel_flavour": impl,
+                          "wave_trajectories": wave, "waves_per_step": len(subs),
                           "tile_rows": sched.tile_rows, "l2": "flushed between steps (256 MiB write)",
                           "cuda_graph": graphed,
                           "flop_per_trajectory_step_ode": fl["per_step_ode"]},
-               "e2e": {"value": e2e_value, "unit": "trajectory-ODE-steps/s", "h2d_bytes_per_step": h2d,
-                       "d2h_bytes_per_step": d2h, "includes": "H2D of packed inputs from pinned memory, schedule "
-                       "build, fwd, loss, bwd, loss.item()"},
-               "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+               "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
                "wall_s_timed_region": wall}
         print(json.dumps(out), flush=True)
     sys.stdout.flush()

@@ -108,7 +108,7 @@ __global__ void k_tile_scan(const int32_t* __restrict__ tile_kmax, int64_t n_til
 // one thread per (tile,row): the float32 knots t_0..t_kmax of that row
 __global__ void k_fill_knots(const float* __restrict__ times, const int32_t* __restrict__ kenc,
                              const int32_t* __restrict__ perm, const int32_t* __restrict__ tile_kmax,
-                             const int64_t* __restrict__ slot_off, int64_t Npad, int tile_rows,
+                             const int64_t* __restrict__ slot_off, int64_t Npad, int tile_rows, int slots_extra,
                              int has_dt, float dt, float* __restrict__ knots) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Npad) return;
@@ -118,7 +118,7 @@ __global__ void k_fill_knots(const float* __restrict__ times, const int32_t* __r
   float* dst = knots + slot_off[tile] * tile_rows + r;
   const int u = perm[idx];
   if (u < 0) {
-    for (int k = 0; k <= km; ++k) dst[(int64_t)k * tile_rows] = 0.0f;
+    for (int k = 0; k <= km + slots_extra; ++k) dst[(int64_t)k * tile_rows] = 0.0f;
     return;
   }
   const int ke = kenc[u];
@@ -129,6 +129,7 @@ __global__ void k_fill_knots(const float* __restrict__ times, const int32_t* __r
     dst[(int64_t)k * tile_rows] = t;
     if (k < K) t = (k == K - 1) ? t1 : __fadd_rn(t, dt);   // closing step lands exactly on t_next
   }
+  for (int k = km + 1; k <= km + slots_extra; ++k) dst[(int64_t)k * tile_rows] = t;     // (a flavour's extra slots: defined, unused)
   (void)has_dt;
 }
 
@@ -195,7 +196,7 @@ extern "C" int njode_schedule_knots(const float* times, const int32_t* kenc, con
   if (N == 0 || n_tiles == 0) return NJODE_OK;
   const int64_t Npad = n_tiles * tile_rows;
   k_fill_knots<<<(unsigned)((Npad + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      times, kenc, perm, tile_kmax, tile_slot_off, Npad, tile_rows, desc->has_dt, desc->dt, knots);
+      times, kenc, perm, tile_kmax, tile_slot_off, Npad, tile_rows, njode_slot_extra(desc), desc->has_dt, desc->dt, knots);
   NJODE_LAUNCH_OK("k_fill_knots");
   return NJODE_OK;
 }

@@ -81,6 +81,18 @@ SIGNATURES = {
 
 _lib = None
 
+# Writes to a parameter buffer that bypass autograd's version counters (njode_adam_step through a raw pointer) are
+# counted here, keyed by the buffer's address; the reverse sweep's guard compares the count it saw at forward time.
+_GENERATION = {}
+
+
+def bump_generation(addr: int) -> None:
+    _GENERATION[addr] = _GENERATION.get(addr, 0) + 1
+
+
+def generation(addr: int) -> int:
+    return _GENERATION.get(addr, 0)
+
 
 def load():
     """Load the shared library once; raise RuntimeError (never fall back) if it cannot be used."""

@@ -13,6 +13,7 @@ The small sub-modules (``JumpNN``, ``ODEFunc``, ``OutputNN``) and ``euler_step``
 """
 from __future__ import annotations
 
+import weakref
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -114,15 +115,36 @@ class _SweepState:
     """What a reverse sweep needs, shared by the sweep's autograd node and -- through ``preds._njode_state`` -- by
     ``nj_ode_loss``, which may run the reverse sweep EARLY (see ``_LossFunction``)."""
     __slots__ = ("desc", "batch", "sched", "dp_group", "shapes", "flat", "ckpt", "versions", "params",
-                 "eager_ok", "early_grad", "early_key")
+                 "eager_ok", "early_grad", "early_key", "consumed", "outputs")
+
+    def current_versions(self):
+        """autograd's version counters of the parameters plus the count of raw-pointer writes to their flat buffer
+        (FlatAdam.step goes through njode_adam_step, which autograd does not see)."""
+        return sum(p._version for p in self.params) + nat.generation(self.flat.data_ptr())
+
+    def check_unmodified(self):
+        if self.current_versions() != self.versions:
+            raise RuntimeError("NeuralJumpODE: a parameter was modified in place between the forward sweep and its "
+                               "backward (the reverse sweep reads the parameters where they live)")
+
+    def hooked(self):
+        """True when a tensor hook sits on the sweep's outputs: a hook may edit the gradient in place (same address),
+        so the early reverse sweep's result must not be matched by address then."""
+        for ref in self.outputs or ():
+            t = ref()
+            if t is not None and getattr(t, "_backward_hooks", None):
+                return True
+        return False
 
     def reverse_sweep(self, g_preds, g_before):
         """njode_backward (+ the data-parallel all-reduce): the flat parameter gradient for these output gradients."""
         if self.ckpt is None:
+            if self.consumed:
+                raise RuntimeError("NeuralJumpODE: the checkpoints of this forward sweep were already consumed by a "
+                                   "backward pass and released (they are the large buffer); a second backward through "
+                                   "the same predictions -- retain_graph=True, or another loss -- needs a new forward")
             raise RuntimeError("NeuralJumpODE: backward requested but the forward sweep ran without checkpoints")
-        if sum(p._version for p in self.params) != self.versions:
-            raise RuntimeError("NeuralJumpODE: a parameter was modified in place between the forward sweep and its "
-                               "backward (the reverse sweep reads the parameters where they live)")
+        self.check_unmodified()
         lib = nat.load()
         desc, batch, sched = self.desc, self.batch, self.sched
         dev = batch.device
@@ -216,10 +238,11 @@ class _SweepFunction(torch.autograd.Function):
         st.dp_group = model._dp_group
         st.shapes = [p.shape for p in params]
         st.flat, st.ckpt = flat, ckpt
-        st.versions = sum(p._version for p in params)
         st.params = params
+        st.versions = st.current_versions()
         st.eager_ok = bool(model.eager_backward) and want_grad
         st.early_grad = st.early_key = None
+        st.consumed, st.outputs = False, None
         ctx.state = st
         model._last_state = st
         return preds, before
@@ -228,16 +251,16 @@ class _SweepFunction(torch.autograd.Function):
     def backward(ctx, g_preds, g_before):
         st = ctx.state
         early = st.early_grad
-        if early is not None and st.early_key is not None and st.early_key[0] == (g_preds.data_ptr(), g_before.data_ptr()):
+        if (early is not None and st.early_key is not None
+                and st.early_key[0] == (g_preds.data_ptr(), g_before.data_ptr()) and not st.hooked()):
             # nj_ode_loss already ran the reverse sweep on its un-scaled gradients, and what arrives here is exactly
-            # those gradients times the loss's upstream gradient (same buffers): scale the result by it
-            if sum(p._version for p in st.params) != st.versions:
-                raise RuntimeError("NeuralJumpODE: a parameter was modified in place between the forward sweep and its "
-                                   "backward (the reverse sweep reads the parameters where they live)")
+            # those gradients times the loss's upstream gradient (same buffers, no hook in between): scale the result
+            st.check_unmodified()
             grad_flat = early * st.early_key[1]
         else:
             grad_flat = st.reverse_sweep(g_preds, g_before)
         st.ckpt = st.early_grad = st.early_key = None     # checkpoints are the big buffer: release them once consumed
+        st.consumed = True
         # Stacks of moments >= 2 get an all-zero gradient from nj_ode_loss (jump_ode.py:328-378); the
         # reference reports zero tensors for them too (torch.stack backward), so nothing is special-cased.
         grads = [g.view(shp) for g, shp in zip(grad_flat.split([shp.numel() for shp in st.shapes]), st.shapes)]
@@ -497,8 +520,64 @@ class NeuralJumpODE(nn.Module):
         preds, before = _SweepFunction.apply(self, desc, batch, want_grad, plan, *params)
         if want_grad:
             preds._njode_state = before._njode_state = self._last_state     # lets nj_ode_loss start the reverse sweep early
+            self._last_state.outputs = (weakref.ref(preds), weakref.ref(before))
         self._last_state = None
         return preds, before
+
+    # -- large batches in waves ----------------------------------------------------------------------
+    def _flat_grad(self, params):
+        """The parameter gradients as ONE flat tensor when they tile one storage in parameter order (what the reverse
+        sweep hands out and in-place accumulation preserves), else None."""
+        first = params[0].grad
+        if first is None:
+            return None
+        base, o = first.data_ptr(), 0
+        for p in params:
+            g = p.grad
+            if g is None or not g.is_contiguous() or g.dtype != torch.float32 or g.data_ptr() != base + 4 * o:
+                return None
+            o += p.numel()
+        if first.untyped_storage().nbytes() - first.storage_offset() * 4 < 4 * o:
+            return None
+        return torch.as_strided(first, (o,), (1,), first.storage_offset())
+
+    def forward_backward_waves(self, batch: PackedBatch, wave: int, traj_scale: Optional[float] = None, **loss_kwargs):
+        """Loss and parameter gradients of a batch that is too large for one sweep's checkpoints (BASELINE config 4:
+        10 MB of checkpoints per trajectory at hidden 128 / 3 layers / ~1040 Euler steps): the batch is cut into
+        waves of ``wave`` trajectories; every wave runs forward sweep, ``nj_ode_loss`` (scaled by ``traj_scale``,
+        default 1 / batch.B -- pass 1 / B_global under data parallelism) and reverse sweep, and its checkpoints are
+        released before the next one starts; gradients accumulate in ``.grad`` (zero them first, as with any
+        backward).  With ``enable_data_parallel()`` the ranks' gradients are summed ONCE, after the last wave.
+        Returns the summed loss (0-dim tensor on the device; no host synchronisation).  The reference computes the
+        same thing in one ``model(batch); nj_ode_loss(...); loss.backward()`` (utils/training.py:88-97): trajectories
+        are independent and the loss is a mean over them (jump_ode.py:383), so waves only change the summation order."""
+        if wave < 1:
+            raise ValueError("forward_backward_waves: wave must be >= 1")
+        B = batch.B
+        scale = 1.0 / B if traj_scale is None else float(traj_scale)
+        dp, self._dp_group = self._dp_group, None
+        total = None
+        try:
+            for lo in range(0, B, wave):
+                sub = batch.slice(lo, min(lo + wave, B))
+                preds, before = self.forward_packed(sub)
+                loss = nj_ode_loss(sub, None, preds, before, traj_scale=scale, **loss_kwargs)
+                loss.backward()
+                total = loss.detach() if total is None else total + loss.detach()
+                del preds, before, loss
+        finally:
+            self._dp_group = dp
+        if dp is not None:
+            import torch.distributed as dist
+            group = None if dp is True else dp
+            params = self.flat_parameters()
+            flat = self._flat_grad(params)
+            if flat is not None:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            else:
+                from ..sharding import allreduce_gradients
+                allreduce_gradients(params, total, group=group)
+        return total
 
     def forward(self, batch_times, batch_values=None):
         """batch_times / batch_values: lists of (n_i,) / (n_i, d_x) tensors (reference jump_ode.py:218-233),
@@ -526,12 +605,16 @@ def _moment_weights(moment_weights, M):
     if moment_weights is None:
         return 1.0, 1.0
     if torch.is_tensor(moment_weights):
+        # (the entry holds a weak reference to the tensor: CPython may hand the id of a collected tensor to a new one)
         key = (id(moment_weights), moment_weights._version)
-        w = _MW_CACHE.get(key)
-        if w is None:
+        hit = _MW_CACHE.get(key)
+        if hit is not None and hit[0]() is moment_weights:
+            w = hit[1]
+        else:
             if len(_MW_CACHE) > 64:
                 _MW_CACHE.clear()
-            w = _MW_CACHE[key] = [float(v) for v in moment_weights.detach().cpu().tolist()]
+            w = [float(v) for v in moment_weights.detach().cpu().tolist()]
+            _MW_CACHE[key] = (weakref.ref(moment_weights), w)
     else:
         w = [float(v) for v in moment_weights]
     if len(w) < min(M, 2):

@@ -12,6 +12,11 @@ of ``njode_adam_step`` (include/njode.h) and the reverse sweep's flat gradient i
 On construction the parameters are re-pointed at slices of the flat buffer (``p.data`` becomes a view; values,
 ``state_dict`` keys and shapes are unchanged).  CUDA float32 parameters only -- like the rest of the package there
 is no CPU fallback.
+
+Checkpoints.  ``state_dict()`` / ``load_state_dict()`` speak ``torch.optim.Adam``'s layout (per parameter ``step``,
+``exp_avg``, ``exp_avg_sq``; the per-parameter tensors are views of the flat moment buffers), so the reference
+Trainer's ``optimizer_state_dict`` (utils/training.py:152-154, :291-304) round-trips and a checkpoint written by
+``torch.optim.Adam`` resumes under ``FlatAdam`` and vice versa.
 """
 from __future__ import annotations
 
@@ -54,7 +59,48 @@ class FlatAdam(torch.optim.Optimizer):
                         p.data = flat[o:o + k].view(p.shape)          # the parameter now lives in the flat buffer
                         o += k
             self._flat.append(dict(params=ps, flat=flat, grad=torch.zeros_like(flat), exp_avg=torch.zeros_like(flat),
-                                   exp_avg_sq=torch.zeros_like(flat), step=0))
+                                   exp_avg_sq=torch.zeros_like(flat), step=0, step_t=torch.zeros((), dtype=torch.float32)))
+
+    # -- torch.optim.Adam-compatible optimizer state (views of the flat moment buffers) ---------------------
+    def _publish_state(self, st):
+        """self.state[p] = {step, exp_avg, exp_avg_sq} as torch.optim.Adam keeps them; the moments are views of the
+        flat buffers, ``step`` is one tensor shared by the group's parameters."""
+        o = 0
+        for p in st["params"]:
+            k = p.numel()
+            self.state[p] = dict(step=st["step_t"], exp_avg=st["exp_avg"][o:o + k].view(p.shape),
+                                 exp_avg_sq=st["exp_avg_sq"][o:o + k].view(p.shape))
+            o += k
+
+    def load_state_dict(self, state_dict):
+        """Accepts what ``FlatAdam.state_dict()`` or ``torch.optim.Adam.state_dict()`` produced for the same
+        parameters (in the same order); moments and step counts are copied into the flat buffers."""
+        super().load_state_dict(state_dict)          # validates groups / sizes, casts tensors to the parameters' device
+        for st in self._flat:
+            if st is None:
+                continue
+            o, steps = 0, set()
+            for p in st["params"]:
+                k = p.numel()
+                ps = self.state.get(p)
+                if ps:
+                    st["exp_avg"][o:o + k].copy_(ps["exp_avg"].reshape(-1))
+                    st["exp_avg_sq"][o:o + k].copy_(ps["exp_avg_sq"].reshape(-1))
+                    steps.add(int(float(ps["step"])))
+                else:                                # a parameter that had not been stepped yet
+                    st["exp_avg"][o:o + k].zero_()
+                    st["exp_avg_sq"][o:o + k].zero_()
+                    steps.add(0)
+                o += k
+            if len(steps) > 1:
+                raise ValueError("FlatAdam.load_state_dict: the parameters of one group carry different step counts "
+                                 f"({sorted(steps)}); a flat group has one")
+            st["step"] = steps.pop() if steps else 0
+            st["step_t"] = torch.tensor(float(st["step"]), dtype=torch.float32)
+            for p in st["params"]:
+                self.state.pop(p, None)
+            if st["step"] > 0:
+                self._publish_state(st)
 
     @staticmethod
     def _adopt(ps, n):
@@ -112,6 +158,9 @@ class FlatAdam(torch.optim.Optimizer):
                 continue
             g = self._gather_grads(st)
             st["step"] += 1
+            st["step_t"] += 1
+            if st["step"] == 1 or st["params"][0] not in self.state:
+                self._publish_state(st)
             flat = st["flat"]
             with torch.cuda.device(flat.device):
                 stream = torch.cuda.current_stream(flat.device).cuda_stream
@@ -119,4 +168,7 @@ class FlatAdam(torch.optim.Optimizer):
                                               flat.numel(), float(group["lr"]), float(group["betas"][0]),
                                               float(group["betas"][1]), float(group["eps"]), float(group["weight_decay"]),
                                               st["step"], 1.0, stream), "njode_adam_step")
+            # the kernel wrote the parameters through a raw pointer: autograd's version counters did not move, so tell
+            # the sweeps' in-place-modification guard (jump_ode._SweepState) that this buffer changed
+            nat.bump_generation(flat.data_ptr())
         return loss

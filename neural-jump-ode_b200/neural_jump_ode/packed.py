@@ -124,6 +124,43 @@ class PackedBatch:
         b._src = self._src
         return b
 
+    # -- sub-batches (device-side, no host copies of the data) ----------------------------------
+    def _host_offsets(self) -> List[int]:
+        if getattr(self, "_off_host", None) is None:
+            self._off_host = list(itertools.accumulate(self.sizes, initial=0))
+        return self._off_host
+
+    def slice(self, lo: int, hi: int) -> "PackedBatch":
+        """Trajectories [lo, hi) as a PackedBatch of views (cached: a wave of a large batch keeps its schedule)."""
+        if not (0 <= lo < hi <= self.B):
+            raise ValueError(f"PackedBatch.slice: need 0 <= lo < hi <= {self.B}")
+        cache = self.__dict__.setdefault("_slices", {})
+        sub = cache.get((lo, hi))
+        if sub is None:
+            off = self._host_offsets()
+            a, b = off[lo], off[hi]
+            sub = PackedBatch(self.times[a:b], self.values[a:b], self.offsets[lo:hi + 1] - a, self.sizes[lo:hi])
+            if len(cache) < 4096:
+                cache[(lo, hi)] = sub
+        return sub
+
+    def gather(self, index: torch.Tensor, index_host: Optional[Sequence[int]] = None) -> "PackedBatch":
+        """The trajectories ``index`` (1-D int64 tensor on this batch's device, any order) as a new PackedBatch, built
+        on the device with no host synchronisation: the host only needs the trajectory lengths it already knows
+        (``index_host`` = the same indices as a Python sequence; taken from ``index`` with one D2H copy if omitted)."""
+        if index_host is None:
+            index_host = index.tolist()
+        sizes_all = self.sizes
+        sizes = [sizes_all[i] for i in index_host]
+        n = sum(sizes)
+        dev = self.device
+        lens = torch.tensor(sizes, dtype=torch.int64).to(dev, non_blocking=True)
+        new_off = torch.zeros(len(sizes) + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(lens, 0, out=new_off[1:])
+        src0 = self.offsets.index_select(0, index)                       # first observation of every picked trajectory
+        obs = torch.repeat_interleave(src0 - new_off[:-1], lens, output_size=n) + torch.arange(n, device=dev)
+        return PackedBatch(self.times.index_select(0, obs), self.values.index_select(0, obs), new_off, sizes)
+
     def came_from(self, batch_times, batch_values) -> bool:
         return self._src is not None and self._src[0] is batch_times and self._src[1] is batch_values
 

@@ -3,6 +3,15 @@ every rank holds a full parameter replica, scales its loss by ``1 / B_global`` (
 traj_scale=...)``) and ONE all-reduce of the flat gradient vector with the loss appended precedes the
 optimiser step.  There is no data-path collective.  Works with any ``torch.distributed`` backend
 (NCCL over NVLink on the B200 box, gloo in the CPU tests).
+
+Two ways to get that all-reduce -- use ONE of them, never both (the gradients would be summed twice):
+  * ``model.enable_data_parallel()``: the reverse sweep all-reduces its flat gradient buffer in place (what
+    ``bench.py`` and the packed training loop use);
+  * ``allreduce_gradients(params, loss)`` below, for gradients that did not come out of the sweep with data
+    parallelism enabled (it also carries the loss in the same collective).
+Every rank must take part in the collective, so every rank needs at least one trajectory: ``shard_bounds`` refuses
+a batch with fewer trajectories than ranks on ALL ranks alike (a rank with an empty shard would raise "empty
+batch" on its own while its peers block in the all-reduce).
 """
 from __future__ import annotations
 
@@ -18,6 +27,9 @@ def shard_bounds(n_traj: int, world_size: int, steps_per_traj: Optional[Sequence
     by the number of Euler steps (the work), still contiguous so a packed batch is sliced, not gathered."""
     if world_size < 1 or n_traj < 0:
         raise ValueError("shard_bounds: world_size must be >= 1 and n_traj >= 0")
+    if 0 < n_traj < world_size:
+        raise ValueError(f"shard_bounds: {n_traj} trajectories cannot be split over {world_size} ranks without an empty "
+                         "shard (every rank takes part in the gradient all-reduce)")
     if steps_per_traj is None:
         return [(n_traj * r) // world_size for r in range(world_size + 1)]
     if len(steps_per_traj) != n_traj:
@@ -31,6 +43,8 @@ def shard_bounds(n_traj: int, world_size: int, steps_per_traj: Optional[Sequence
             b += 1
         bounds.append(b)
     bounds.append(n_traj)
+    for r in range(1, world_size):                       # work balancing must not starve a rank either
+        bounds[r] = min(max(bounds[r], bounds[r - 1] + 1), n_traj - (world_size - r))
     return bounds
 
 
@@ -45,7 +59,8 @@ def shard_lists(batch_times: List[torch.Tensor], batch_values: List[torch.Tensor
 def allreduce_gradients(params: Sequence[torch.Tensor], loss: torch.Tensor, group=None) -> torch.Tensor:
     """Sum the parameter gradients and the (already ``1/B_global``-scaled) loss over the ranks with ONE
     all-reduce of the flat vector ``[grad_0, grad_1, ..., loss]``; gradients are written back in place
-    (a missing ``.grad`` counts as zero and is materialised).  Returns the global loss (0-dim tensor)."""
+    (a missing ``.grad`` counts as zero and is materialised).  Returns the global loss (0-dim tensor).
+    Do NOT combine with ``model.enable_data_parallel()`` (see the module docstring)."""
     import torch.distributed as dist
     for p in params:
         if p.grad is None:

@@ -200,3 +200,78 @@ def test_mixed_ragged_batch():
         t = b.times[off[i]:off[i + 1]]
         assert float(t[0]) == 0.0 and float(t[-1]) == 1.0 and bool((t[1:] > t[:-1]).all())
     assert torch.isfinite(b.values).all()
+
+
+def _check_against_reference_moments(device, n=20000):
+    """Moments of the vectorised generators at T/2 and T against 2000 paths of the unmodified reference generators
+    (tests/golden/generator_stats.json, made by tests/golden/make_generator_stats.py) and, where one exists, the
+    closed form: |mean - mean_ref| within 4.5 standard errors, standard deviations within 8 %."""
+    import json, math, os
+    from conftest import GOLDEN_DIR
+    from neural_jump_ode.simulation import simulate_paths
+    ref = json.load(open(os.path.join(GOLDEN_DIR, "generator_stats.json")))
+    n_ref, n_steps, T = ref["n_paths"], ref["n_steps"], ref["T"]
+    for name, r in ref["processes"].items():
+        g = torch.Generator(device=device).manual_seed(11)
+        _, X = simulate_paths(name, n, n_steps=n_steps, T=T, device=device, generator=g, **r["params"])
+        X = X.double().cpu()
+        for tag, col in (("mid", n_steps // 2), ("end", n_steps)):
+            x = X[:, col]
+            m, s = float(x.mean()), float(x.std())
+            se = math.sqrt(r[f"std_{tag}"] ** 2 / n_ref + s * s / n)
+            assert abs(m - r[f"mean_{tag}"]) <= 4.5 * se, (name, tag, m, r[f"mean_{tag}"], se)
+            assert abs(s / r[f"std_{tag}"] - 1.0) <= 0.08, (name, tag, s, r[f"std_{tag}"])
+        p = r["params"]
+        xT = X[:, -1]
+        if name == "black_scholes":            # E X_T = x0 e^{mu T}; Var = x0^2 e^{2 mu T} (e^{sigma^2 T} - 1)
+            mean = p["x0"] * math.exp(p["mu"] * T)
+            std = mean * math.sqrt(math.exp(p["sigma"] ** 2 * T) - 1.0)
+        elif name == "ornstein_uhlenbeck":     # exact transition: mean mu + (x0 - mu) e^{-theta T}, var sigma^2 (1 - e^{-2 theta T}) / (2 theta)
+            mean = p["mu"] + (p["x0"] - p["mu"]) * math.exp(-p["theta"] * T)
+            std = p["sigma"] * math.sqrt((1.0 - math.exp(-2.0 * p["theta"] * T)) / (2.0 * p["theta"]))
+        elif name == "heston":                 # Euler scheme: E X_T = x0 (1 + mu dt)^n
+            mean, std = p["x0"] * (1.0 + p["mu"] * T / n_steps) ** n_steps, None
+        else:
+            continue
+        assert abs(float(xT.mean()) - mean) <= 4.5 * float(xT.std()) / math.sqrt(n), (name, float(xT.mean()), mean)
+        if std is not None:
+            assert abs(float(xT.std()) / std - 1.0) <= 0.05, (name, float(xT.std()), std)
+
+
+def test_generators_match_reference_moments_cpu():
+    _check_against_reference_moments("cpu", n=8000)
+
+
+def test_moment_weight_cache_ignores_recycled_ids():
+    """The read-back cache of a device moment_weights tensor is keyed by id(): a collected tensor's id can be handed to
+    a new tensor, whose weights must then be read afresh."""
+    import weakref
+    from neural_jump_ode.models import jump_ode as jo
+
+    class Dead:
+        pass
+    d = Dead()
+    ref = weakref.ref(d)
+    del d
+    w = torch.tensor([2.0, 7.0])
+    jo._MW_CACHE[(id(w), w._version)] = (ref, [9.0, 9.0])          # what a recycled id looks like
+    assert jo._moment_weights(w, 2) == (2.0, 7.0)
+    assert jo._moment_weights(w, 2) == (2.0, 7.0)                   # second call hits the (now valid) entry
+    w.mul_(2.0)
+    assert jo._moment_weights(w, 2) == (4.0, 14.0)                  # in-place edit = new version = re-read
+
+
+def test_packed_slice_and_gather():
+    from neural_jump_ode import PackedBatch
+    bt = [torch.tensor([0.0, 0.5, 1.0]), torch.tensor([0.0, 1.0]), torch.tensor([0.0, 0.2, 0.4, 1.0]), torch.tensor([0.3])]
+    bv = [torch.arange(3.0).view(3, 1), 10 + torch.arange(2.0).view(2, 1), 20 + torch.arange(4.0).view(4, 1), torch.tensor([[30.0]])]
+    b = PackedBatch.from_lists(bt, bv)
+    s = b.slice(1, 3)
+    assert s.B == 2 and s.sizes == [2, 4] and s.offsets.tolist() == [0, 2, 6]
+    assert torch.equal(s.times, torch.cat(bt[1:3])) and torch.equal(s.values, torch.cat(bv[1:3]))
+    assert b.slice(1, 3) is s                                       # cached: a wave keeps its schedule
+    g = b.gather(torch.tensor([3, 0, 2]))
+    assert g.sizes == [1, 3, 4] and g.offsets.tolist() == [0, 1, 4, 8]
+    assert torch.equal(g.times, torch.cat([bt[3], bt[0], bt[2]])) and torch.equal(g.values, torch.cat([bv[3], bv[0], bv[2]]))
+    with pytest.raises(ValueError):
+        b.slice(2, 2)

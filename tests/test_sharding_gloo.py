@@ -94,7 +94,9 @@ def test_shard_bounds():
     from neural_jump_ode.sharding import shard_bounds, shard_lists
     assert shard_bounds(10, 1) == [0, 10]
     assert shard_bounds(10, 4) == [0, 2, 5, 7, 10]
-    assert shard_bounds(3, 8)[-1] == 3 and shard_bounds(3, 8)[0] == 0          # more ranks than trajectories
+    with pytest.raises(ValueError, match="empty"):                              # more ranks than trajectories: every rank
+        shard_bounds(3, 8)                                                      # refuses alike (no rank may sit out the all-reduce)
+    assert shard_bounds(4, 4, [100, 1, 1, 1]) == [0, 1, 2, 3, 4]                # balancing by steps never starves a rank
     b = shard_bounds(6, 2, [100, 1, 1, 1, 1, 96])
     assert b == [0, 1, 6]                                                       # balanced by steps, contiguous
     b = shard_bounds(8, 3, [5] * 8)
