@@ -60,37 +60,33 @@ __device__ __forceinline__ int cat_instances(int kind, int kmax) {
   return kind == CAT_ODE ? kmax : (kind == CAT_OUT || kind == CAT_READOUT) ? 2 : 1;
 }
 
-// walks (category, tile of this CTA, instance, 32-row stage) in the order every role uses
+// walks (category, tile of this CTA, instance = plane pair) in the order every role uses
 struct Cursor {
-  int c, kind, l, inst, qs, n_inst, kmax;
-  int64_t r, so;
-  bool valid;
+  int c, inst, n_inst, kmax, r, so;      // category, instance within the tile, instances of the tile, its kmax, round, first slot
 };
+__device__ __forceinline__ bool cursor_valid(const Cursor& cu, int L) { return cu.c < n_cats(L); }
 __device__ __forceinline__ void cursor_seek(Cursor& cu, const SweepArgs& a, int wi, int n_w) {
   const int L = a.T.L;
   while (cu.c < n_cats(L)) {
-    const int64_t tile = wi + cu.r * n_w;
+    const int64_t tile = wi + (int64_t)cu.r * n_w;
     if (tile < a.n_tiles) {
-      cat_decode(L, cu.c, cu.kind, cu.l);
+      int kind, l;
+      cat_decode(L, cu.c, kind, l);
       cu.kmax = a.tile_kmax[tile];
-      cu.n_inst = cat_instances(cu.kind, cu.kmax);
-      if (cu.n_inst > 0) { cu.so = a.tile_slot_off[tile]; cu.inst = 0; cu.qs = 0; cu.valid = true; return; }
+      cu.n_inst = cat_instances(kind, cu.kmax);
+      if (cu.n_inst > 0) { cu.so = (int)a.tile_slot_off[tile]; cu.inst = 0; return; }
       ++cu.r;
     } else {
       ++cu.c;
       cu.r = 0;
     }
   }
-  cu.valid = false;
 }
 __device__ __forceinline__ void cursor_init(Cursor& cu, const SweepArgs& a, int wi, int n_w) {
-  cu.c = 0; cu.r = 0; cu.inst = cu.qs = 0; cu.valid = false;
+  cu.c = 0; cu.r = 0; cu.inst = 0; cu.n_inst = 0; cu.kmax = 0; cu.so = 0;
   cursor_seek(cu, a, wi, n_w);
 }
-// returns true when the step crossed an instance boundary
 __device__ __forceinline__ void cursor_next(Cursor& cu, const SweepArgs& a, int wi, int n_w) {
-  if (++cu.qs < R / SROWS) return;
-  cu.qs = 0;
   if (++cu.inst < cu.n_inst) return;
   ++cu.r;
   cursor_seek(cu, a, wi, n_w);
@@ -98,24 +94,42 @@ __device__ __forceinline__ void cursor_next(Cursor& cu, const SweepArgs& a, int 
 // slots (relative to the tile's first) of the P plane, Q plane and aux rows of the cursor's instance
 __device__ __forceinline__ void cursor_planes(const Cursor& cu, int L, int& p_slot, int& p_plane, bool& p_from_d,
                                               int& q_slot, int& q_plane, bool& has_q, int& x_slot) {
+  int kind, l;
+  cat_decode(L, cu.c, kind, l);
   const int X = cu.kmax + 1 + cu.inst, X3 = cu.kmax + 3;
   p_from_d = true; has_q = true;
-  switch (cu.kind) {
-    case CAT_ODE: p_slot = q_slot = x_slot = cu.inst; p_plane = q_plane = cu.l; break;
+  switch (kind) {
+    case CAT_ODE: p_slot = q_slot = x_slot = cu.inst; p_plane = q_plane = l; break;
     case CAT_OUT:
-      p_slot = x_slot = X; p_plane = cu.l;
-      if (cu.l == 0) { q_slot = cu.inst == 0 ? 0 : cu.kmax; q_plane = 0; } else { q_slot = X; q_plane = cu.l; }
+      p_slot = x_slot = X; p_plane = l;
+      if (l == 0) { q_slot = cu.inst == 0 ? 0 : cu.kmax; q_plane = 0; } else { q_slot = X; q_plane = l; }
       break;
     case CAT_READOUT: p_slot = x_slot = X; p_plane = L; p_from_d = false; has_q = false; q_slot = q_plane = 0; break;
-    case CAT_JUMP: p_slot = q_slot = x_slot = X3; p_plane = cu.l; q_plane = cu.l - 1; break;
+    case CAT_JUMP: p_slot = q_slot = x_slot = X3; p_plane = l; q_plane = l - 1; break;
     default: p_slot = x_slot = X3; p_plane = 0; has_q = false; q_slot = q_plane = 0; break;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
+// (ring and control block are re-derived inside each role: a pointer computed before setmaxnreg is live across the
+//  register re-allocation, gets spilled, and its re-load inside the stage loop is an L2 round trip -- round 1, and the
+//  first ncu capture of this kernel: 1 LDL.64 per stage)
 template <int HW>
-__device__ __forceinline__ void wg_issuer(const SweepArgs& a, uint8_t* ring, Ctl3& ctl) {
+struct Carve3 {
+  uint8_t* ring;
+  Ctl3* ctl;
+  __device__ __forceinline__ explicit Carve3(uint8_t* raw) {
+    ring = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    ctl = reinterpret_cast<Ctl3*>(ring + (size_t)NSTAGE3 * G3<HW>::STAGE);
+  }
+};
+
+template <int HW>
+__device__ __forceinline__ void wg_issuer(const SweepArgs& a, uint8_t* raw) {
   using G = G3<HW>;
+  Carve3<HW> cv(raw);
+  uint8_t* const ring = cv.ring;
+  Ctl3& ctl = *cv.ctl;
   const int S = a.T.S;
   const int wi = blockIdx.x / S, n_w = gridDim.x / S;
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&ctl.tmem_base);
@@ -126,10 +140,13 @@ __device__ __forceinline__ void wg_issuer(const SweepArgs& a, uint8_t* ring, Ctl
   constexpr uint32_t idesc_q = umma::idesc_tf32(128, G::NACC, 1, 1), idesc_x = umma::idesc_tf32(128, 16, 1, 1);
   Cursor cu;
   cursor_init(cu, a, wi, n_w);
+  const int L = a.T.L;
   uint32_t sc = 0, ic = 0;
   Diag dg{g_status, g_notrap, 16u, false};
-  while (cu.valid) {
-    const bool has_q = !(cu.kind == CAT_READOUT || cu.kind == CAT_JUMP0);
+  while (cursor_valid(cu, L)) {
+    int kind, l;
+    cat_decode(L, cu.c, kind, l);
+    const bool has_q = !(kind == CAT_READOUT || kind == CAT_JUMP0);
     const uint32_t b = ic & 1u, use = ic >> 1;
     if (use > 0) wait_or_die(&ctl.merged[b], (use - 1) & 1u, dg, 5);     // the accumulator's previous content is merged
     const uint32_t acc = tmem + (b ? FRESH1 : FRESH0);
@@ -153,16 +170,19 @@ __device__ __forceinline__ void wg_issuer(const SweepArgs& a, uint8_t* ring, Ctl
         if (qs == R / SROWS - 1) umma::commit(&ctl.fresh_done[b]);
       }
       __syncwarp();
-      cursor_next(cu, a, wi, n_w);
     }
+    cursor_next(cu, a, wi, n_w);
     ++ic;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 template <int HW>
-__device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* ring, Ctl3& ctl) {
+__device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* raw) {
   using G = G3<HW>;
+  Carve3<HW> cv(raw);
+  uint8_t* const ring = cv.ring;
+  Ctl3& ctl = *cv.ctl;
   const ParamTable& T = a.T;
   const int L = T.L, S = T.S, dx = T.d_x, O = T.O;
   const int s = blockIdx.x % S, wi = blockIdx.x / S, n_w = gridDim.x / S;
@@ -280,40 +300,68 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* ring, Ctl
   umma::fence_async_smem();
   umma::named_bar_sync(1, NT_W);
 
-  // ---- stage loads, two stages ahead in registers ----
-  Cursor cur, pre;
-  cursor_init(cur, a, wi, n_w);
-  pre = cur;
-  float pb[2][8], qb[2][8], xb[2][8];
-  auto issue_loads = [&](const Cursor& cu, float (&p)[8], float (&qv)[8], float (&x)[8]) {
-    if (!cu.valid) return;
+  // ---- the stage loop ----
+  // The hand-over fence (fence.proxy.async = MEMBAR.ALL.CTA) waits for every load this thread has in flight, so a
+  // register load must land within ONE stage time (~1400 cycles): fine from L2, not from HBM (first capture of this
+  // kernel: a stage took an HBM round trip, 3160 cycles, tensor pipe 27 % active).  So: the loads of stage n+1 are
+  // issued right after the hand-over of stage n, and a second cursor runs PF_AHEAD plane pairs in front pulling the
+  // planes into L2 with prefetch.global.L2 (no destination register, nothing for the fence to wait for).
+  constexpr int PF_AHEAD = 2;            // plane pairs (= 8 stages)
+  struct Src { const float* p; const float* q; const float* x; bool has_q; };
+  auto source = [&](const Cursor& cu) {
     int ps, pp, qsl, qp, xs;
     bool pd, hq;
     cursor_planes(cu, L, ps, pp, pd, qsl, qp, hq, xs);
-    const int rowg = cu.qs * SROWS + lane;
-    if (loader) {
-      ld8g((pd ? baseD : baseA) + ((cu.so + ps) * (L + 1) + pp) * PL + ((int64_t)warp * R + rowg) * 8, p);
-      if (hq) ld8g(baseA + ((cu.so + qsl) * (L + 1) + qp) * PL + ((int64_t)warp * R + rowg) * 8, qv);
-    }
-    if (warp == 0) ld8g(baseX + ((cu.so + xs) * R + rowg) * 8, x);
+    Src sr;
+    sr.p = (pd ? baseD : baseA) + ((int64_t)(cu.so + ps) * (L + 1) + pp) * PL + ((int64_t)warp * R + lane) * 8;
+    sr.q = baseA + ((int64_t)(cu.so + qsl) * (L + 1) + qp) * PL + ((int64_t)warp * R + lane) * 8;
+    sr.x = baseX + ((int64_t)(cu.so + xs) * R + lane) * 8;
+    sr.has_q = hq;
+    return sr;
   };
-  issue_loads(pre, pb[0], qb[0], xb[0]);
-  cursor_next(pre, a, wi, n_w);
-  issue_loads(pre, pb[1], qb[1], xb[1]);
-  if (pre.valid) cursor_next(pre, a, wi, n_w);
+  float p[8], qv[8], x[8];
+  auto issue_loads = [&](const Src& sr, int qs) {
+    if (loader) {
+      ld8g(sr.p + qs * (SROWS * 8), p);
+      if (sr.has_q) ld8g(sr.q + qs * (SROWS * 8), qv);
+    }
+    if (warp == 0) ld8g(sr.x + qs * (SROWS * 8), x);
+  };
+  auto issue_prefetch = [&](const Src& sr, int qs) {
+    if (loader) {
+      prefetch_l2(sr.p + qs * (SROWS * 8));
+      if (sr.has_q) prefetch_l2(sr.q + qs * (SROWS * 8));
+    }
+    if (warp == 0) prefetch_l2(sr.x + qs * (SROWS * 8));
+  };
+  Cursor cur, pf;
+  cursor_init(cur, a, wi, n_w);
+  pf = cur;
+  for (int i = 0; i < PF_AHEAD && cursor_valid(pf, L); ++i) {
+    const Src sr = source(pf);
+#pragma unroll
+    for (int qs = 0; qs < R / SROWS; ++qs) issue_prefetch(sr, qs);
+    cursor_next(pf, a, wi, n_w);
+  }
+  Src src = source(cur);
+  if (cursor_valid(cur, L)) issue_loads(src, 0);
 
   uint32_t sc = 0, ic = 0;
   bool pending = false;                  // instance ic - 1 not merged yet
-  while (cur.valid) {
-    const int kind = cur.kind, l = cur.l, c_now = cur.c;
-    const bool has_q = !(kind == CAT_READOUT || kind == CAT_JUMP0);
+  while (cursor_valid(cur, L)) {
+    int kind, l;
+    cat_decode(L, cur.c, kind, l);
+    const int c_now = cur.c;
+    const bool has_q = src.has_q;
     const bool scale_q = kind == CAT_ODE && l == 0 && sc_kind != NJODE_SCALE_IDENTITY;
+    Cursor nxt = cur;
+    cursor_next(nxt, a, wi, n_w);
+    const bool pf_ok = cursor_valid(pf, L);
+    Src psrc = src;
+    if (pf_ok) psrc = source(pf);
 #pragma unroll
     for (int qs = 0; qs < R / SROWS; ++qs, ++sc) {
       const uint32_t stage = sc % NSTAGE3, sround = sc / NSTAGE3;
-      float (&p)[8] = pb[qs & 1];
-      float (&qv)[8] = qb[qs & 1];
-      float (&x)[8] = xb[qs & 1];
       wait_or_die(&ctl.empty[stage], (sround & 1u) ^ 1u, dg, 8);
       const uint32_t sb = ring_s + stage * G::STAGE;
       uint32_t hi[8], lo[8];
@@ -344,15 +392,21 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* ring, Ctl
       umma::fence_async_smem();
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&ctl.full[stage]);
-      // refill this register stage with the loads of the stage after the next
-      issue_loads(pre, p, qv, x);
-      if (pre.valid) cursor_next(pre, a, wi, n_w);
-      cursor_next(cur, a, wi, n_w);
+      // the next stage's loads (next plane pair after the last stage of this one), and the L2 prefetch far ahead
+      if (qs + 1 < R / SROWS) {
+        issue_loads(src, qs + 1);
+      } else if (cursor_valid(nxt, L)) {
+        src = source(nxt);
+        issue_loads(src, 0);
+      }
+      if (pf_ok) issue_prefetch(psrc, qs);
     }
+    if (pf_ok) cursor_next(pf, a, wi, n_w);
+    cur = nxt;
     if (pending) merge(ic - 1);
     pending = true;
     ++ic;
-    if (!cur.valid || cur.c != c_now) {    // category finished: fold the last accumulator in and flush
+    if (!cursor_valid(cur, L) || cur.c != c_now) {    // category finished: fold the last accumulator in and flush
       merge(ic - 1);
       pending = false;
       flush(kind, l);
@@ -363,29 +417,29 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* ring, Ctl
 template <int HW>
 __global__ void __launch_bounds__(NT3, 1) k_wide_wgrad(SweepArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  using G = G3<HW>;
-  uint8_t* ring = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  Ctl3& ctl = *reinterpret_cast<Ctl3*>(ring + (size_t)NSTAGE3 * G::STAGE);
   const int warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < NSTAGE3; ++i) { umma::mbar_init(&ctl.full[i], NWARP_W); umma::mbar_init(&ctl.empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { umma::mbar_init(&ctl.fresh_done[i], 1); umma::mbar_init(&ctl.merged[i], NWARP_W); }
-    umma::fence_mbar_init();
+  {
+    Ctl3& ctl = *Carve3<HW>(smem_raw).ctl;
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < NSTAGE3; ++i) { umma::mbar_init(&ctl.full[i], NWARP_W); umma::mbar_init(&ctl.empty[i], 1); }
+      for (int i = 0; i < 2; ++i) { umma::mbar_init(&ctl.fresh_done[i], 1); umma::mbar_init(&ctl.merged[i], NWARP_W); }
+      umma::fence_mbar_init();
+    }
+    if (warp == 0) umma::tmem_alloc(&ctl.tmem_base, TMEM3);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
   }
-  if (warp == 0) umma::tmem_alloc(&ctl.tmem_base, TMEM3);
-  umma::fence_before_sync();
-  __syncthreads();
-  umma::fence_after_sync();
   if (warp < NWARP_W) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    wg_worker<HW>(a, ring, ctl);
+    wg_worker<HW>(a, smem_raw);
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    if (warp == NWARP_W) wg_issuer<HW>(a, ring, ctl);
+    if (warp == NWARP_W) wg_issuer<HW>(a, smem_raw);
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_free(*reinterpret_cast<volatile uint32_t*>(&ctl.tmem_base), TMEM3);
+  if (warp == 0) umma::tmem_free(*reinterpret_cast<volatile uint32_t*>(&Carve3<HW>(smem_raw).ctl->tmem_base), TMEM3);
 }
 
 template <int HW>

@@ -28,7 +28,8 @@ __device__ unsigned g_notrap = 0;
 
 constexpr int NT = NT_W + 128;         // 16 worker warps + one warpgroup holding the MMA issuer warp and the weight producer warp
 // Register budget: the CTA launches with 640 x 96 registers and setmaxnreg moves registers inside that pool:
-// 512 x 104 (workers: a 32-float state slice per thread at H = 128) + 128 x 56 = 60416 <= 61440.
+// 512 x 112 (workers: a 32-float state slice plus, in the reverse sweep, a 32-float activation slice per thread at
+// H = 128) + 128 x 32 (issuer / producer: a handful of counters and two descriptors) = 61440.
 
 template <int HW>
 struct __align__(16) SmallW {
@@ -311,8 +312,8 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) z[i] = act_fwd<ACT>(z[i]);
-      if (ck) st8g(cp(X3, 0, j), z);
       w.emit(j, z);
+      if (ck) st8g(cp(X3, 0, j), z);
     }
     for (int l = 1; l <= L; ++l) {
       w.wait_acc();
@@ -323,6 +324,9 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
         ld8s(sw.b_jump[l] + col0 + 8 * j, cb);
 #pragma unroll
         for (int i = 0; i < 8; ++i) z[i] = act_fwd<ACT>(z[i] + cb[i]);
+        w.emit(j, z);                   // next jump layer, or (l == L) the first out-net layer on h_0
+        // (checkpoint stores come AFTER the hand-over: its release-arrive waits for every earlier global store of the
+        //  thread to be acknowledged -- an L2 round trip per sub-step when the store goes first)
         if (l < L) {
           if (ck) st8g(cp(X3, l, j), z);
         } else {
@@ -330,7 +334,6 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
           for (int i = 0; i < 8; ++i) h[8 * j + i] = z[i];
           if (ck) st8g(cp(0, 0, j), z);
         }
-        w.emit(j, z);                   // next jump layer, or (l == L) the first out-net layer on h_0
       }
       w.done();
     }
@@ -349,9 +352,9 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
           ld8s(sw.b_out[l] + col0 + 8 * j, cb);
 #pragma unroll
           for (int i = 0; i < 8; ++i) z[i] = act_fwd<ACT>(z[i] + cb[i]);
+          if (l < L - 1) w.emit(j, z);
           if (ck) st8g(cp(X, l + 1, j), z);
           if (l < L - 1) {
-            w.emit(j, z);
           } else {
 #pragma unroll
             for (int o = 0; o < MAX_O; ++o) if (o < O) {
@@ -415,8 +418,8 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
         ld8s(sw.ext_ode0[dx + 1] + col0 + 8 * j, cw);
 #pragma unroll
         for (int i = 0; i < 8; ++i) z[i] = act_fwd<ACT>(fmaf(cw[i], delta, z[i]));
-        if (ck) st8g(cp(k, 1, j), z);
         w.emit(j, z);
+        if (ck) st8g(cp(k, 1, j), z);
       }
       w.done();
       for (int l = 1; l < L; ++l) {
@@ -428,8 +431,8 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
           ld8s(sw.b_ode[l] + col0 + 8 * j, cb);
 #pragma unroll
           for (int i = 0; i < 8; ++i) z[i] = act_fwd<ACT>(z[i] + cb[i]);
-          if (ck) st8g(cp(k, l + 1, j), z);
           w.emit(j, z);
+          if (ck) st8g(cp(k, l + 1, j), z);
         }
         w.done();
       }
@@ -447,9 +450,16 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] = h[8 * j + i];
+        if (more && sc_kind != NJODE_SCALE_IDENTITY) {
+          float fs[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) fs[i] = f[i];
+          scale8(sc_kind, fs);
+          w.emit(j, fs);
+        } else {
+          w.emit(j, f);
+        }
         if (ck) st8g(cp(k + 1, 0, j), f);
-        if (more) scale8(sc_kind, f);
-        w.emit(j, f);
       }
       w.done();
       asm volatile("mov.f32 %0, %1;" : "=f"(tn_ahead) : "f"(tn_loaded));
@@ -503,6 +513,32 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
 #pragma unroll
     for (int i = 0; i < CG; ++i) gr[i] = 0.0f;
 
+    // One inner layer of a reverse chain: d_out = (accumulator = d_in * W) * act'(z), written as a d plane and handed on
+    // as the next GEMM's operand.  ALL of the layer's z chunks are requested before the accumulator wait: the MMAs
+    // (>= 3000 cycles at H = 128) hide the HBM latency, whereas a load issued inside the sub-step loop is consumed a
+    // few hundred cycles later (measured: long-scoreboard stalls on act'(z) were the top stall of this kernel).
+    auto chain_layer = [&](const float* __restrict__ zsrc, float* __restrict__ ddst, bool emit_next) {
+      float zb[CG];
+#pragma unroll
+      for (int j = 0; j < NSUB; ++j) {
+        float t8[8];
+        ld8g(zsrc + j * (R * 8), t8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) zb[8 * j + i] = t8[i];
+      }
+      w.wait_acc();
+#pragma unroll
+      for (int j = 0; j < NSUB; ++j) {
+        float acc[8];
+        w.acc_ld(j, acc);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] *= act_grad_from_out<ACT>(zb[8 * j + i]);
+        if (emit_next) w.emit(j, acc);
+        st8g(ddst + j * (R * 8), acc);     // (after the hand-over: its release-arrive waits for earlier global stores)
+      }
+      w.done();
+    };
+
     // ---- readout backward at a hidden state: adds d loss / d h to gr ----
     auto out_backward = [&](int X, const float* __restrict__ gsrc, int64_t obs, bool live) {
       float dY[MAX_O];
@@ -528,29 +564,10 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) d[i] *= act_grad_from_out<ACT>(z[i]);
-        st8g(pd(X, L - 1, j), d);
         w.emit(j, d);                                            // -> d * W_out[L-1]
+        st8g(pd(X, L - 1, j), d);
       }
-      for (int l = L - 1; l >= 1; --l) {
-        float z[8];
-        ld8g(pa(X, l, 0), z);
-        w.wait_acc();
-#pragma unroll
-        for (int j = 0; j < NSUB; ++j) {
-          float acc[8], zn[8];
-          if (j + 1 < NSUB) ld8g(pa(X, l, j + 1), zn);
-          w.acc_ld(j, acc);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] *= act_grad_from_out<ACT>(z[i]);
-          st8g(pd(X, l - 1, j), acc);
-          w.emit(j, acc);                                        // -> d * W_out[l-1]
-          if (j + 1 < NSUB) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) z[i] = zn[i];
-          }
-        }
-        w.done();
-      }
+      for (int l = L - 1; l >= 1; --l) chain_layer(pa(X, l, 0), pd(X, l - 1, 0), true);      // -> d * W_out[l-1]
       w.wait_acc();                                              // d * W_out[0] = d loss / d h through this readout
 #pragma unroll
       for (int j = 0; j < NSUB; ++j) {
@@ -578,8 +595,8 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
         float d[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) d[i] = delta * gr[8 * j + i];
-        st8g(pd(kmax - 1, L, j), d);
         w.emit(j, d);                                            // -> d * W_ode[L]
+        st8g(pd(kmax - 1, L, j), d);
       }
     }
     for (int k = kmax - 1; k >= 0; --k) {
@@ -591,27 +608,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
         const float xv[8] = {1.0f, xs[0], two ? xs[1] : tn, two ? tn : delta_k, two ? delta_k : 0.0f, 0.0f, 0.0f, 0.0f};
         st8g(cx + (int64_t)k * (R * 8), xv);
       }
-      for (int l = L; l >= 1; --l) {
-        float z[8];
-        ld8g(pa(k, l, 0), z);
-        if (l > 1) prefetch_l2(pa(k, l - 1, 0)); else if (sc_kind != NJODE_SCALE_IDENTITY) prefetch_l2(pa(k, 0, 0));
-        w.wait_acc();
-#pragma unroll
-        for (int j = 0; j < NSUB; ++j) {
-          float acc[8], zn[8];
-          if (j + 1 < NSUB) ld8g(pa(k, l, j + 1), zn);
-          w.acc_ld(j, acc);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] *= act_grad_from_out<ACT>(z[i]);      // d loss / d (pre-activation of layer l-1)
-          st8g(pd(k, l - 1, j), acc);
-          w.emit(j, acc);                                        // -> d * W_ode[l-1]
-          if (j + 1 < NSUB) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) z[i] = zn[i];
-          }
-        }
-        w.done();
-      }
+      for (int l = L; l >= 1; --l) chain_layer(pa(k, l, 0), pd(k, l - 1, 0), true);           // -> d * W_ode[l-1]
       // d * W_ode[0][:, :H] = d loss / d s(h_k); fused with the next step's first operand delta_{k-1} * g
       const float delta_prev = __fsub_rn(tn, tc_next);           // (unused when k == 0)
       w.wait_acc();
@@ -633,8 +630,8 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
           float d[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) d[i] = delta_prev * gr[8 * j + i];
-          st8g(pd(k - 1, L, j), d);
           w.emit(j, d);
+          st8g(pd(k - 1, L, j), d);
         }
       }
       w.done();
@@ -654,29 +651,10 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
       ld8g(pa(0, 0, j), z);
 #pragma unroll
       for (int i = 0; i < 8; ++i) d[i] = gr[8 * j + i] * act_grad_from_out<ACT>(z[i]);
-      st8g(pd(X3, L, j), d);
       w.emit(j, d);                                              // -> d * W_jump[L]
+      st8g(pd(X3, L, j), d);
     }
-    for (int l = L; l >= 1; --l) {
-      float z[8];
-      ld8g(pa(X3, l - 1, 0), z);
-      w.wait_acc();
-#pragma unroll
-      for (int j = 0; j < NSUB; ++j) {
-        float acc[8], zn[8];
-        if (j + 1 < NSUB) ld8g(pa(X3, l - 1, j + 1), zn);
-        w.acc_ld(j, acc);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] *= act_grad_from_out<ACT>(z[i]);        // d (pre-activation of jump layer l-1)
-        st8g(pd(X3, l - 1, j), acc);
-        if (l > 1) w.emit(j, acc);                               // -> d * W_jump[l-1]
-        if (j + 1 < NSUB) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) z[i] = zn[i];
-        }
-      }
-      w.done();
-    }
+    for (int l = L; l >= 1; --l) chain_layer(pa(X3, l - 1, 0), pd(X3, l - 1, 0), l > 1);      // -> d * W_jump[l-1]
   }
 }
 
@@ -702,10 +680,10 @@ __global__ void __launch_bounds__(NT, 1) k_wide_sweep(SweepArgs a, const float* 
     umma::fence_after_sync();
   }
   if (warp < NWARP_W) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     if (BWD) bwd_worker<HW, ACT>(a, smem_raw); else fwd_worker<HW, ACT>(a, smem_raw);
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == NWARP_W) issuer<HW, BWD>(a, smem_raw);
     else if (threadIdx.x == NT_W + 32) producer<HW, BWD>(a, smem_raw, img);
   }

@@ -72,6 +72,16 @@ class FlatAdam(torch.optim.Optimizer):
                                  exp_avg_sq=st["exp_avg_sq"][o:o + k].view(p.shape))
             o += k
 
+    def state_dict(self):
+        """``torch.optim.Adam``'s layout.  Every parameter gets its OWN ``step`` tensor in the returned dict: inside
+        FlatAdam the group's parameters share one, but torch.optim.Adam increments the step tensors of all parameters
+        with one ``_foreach_add_`` -- a shared tensor would advance once per parameter."""
+        sd = super().state_dict()
+        for ps in sd["state"].values():
+            if torch.is_tensor(ps.get("step")):
+                ps["step"] = ps["step"].clone()
+        return sd
+
     def load_state_dict(self, state_dict):
         """Accepts what ``FlatAdam.state_dict()`` or ``torch.optim.Adam.state_dict()`` produced for the same
         parameters (in the same order); moments and step counts are copied into the flat buffers."""

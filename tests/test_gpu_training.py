@@ -176,7 +176,9 @@ def test_backward_guards():
     from neural_jump_ode import NeuralJumpODE, nj_ode_loss, FlatAdam, PackedBatch
     torch.manual_seed(2)
     model = NeuralJumpODE(**MK).to(DEV)
-    opt = FlatAdam(model.parameters(), lr=1e-3)
+    model.flatten_parameters()                                                 # the sweeps read the parameters in place ...
+    opt = FlatAdam(model.parameters(), lr=1e-3)                                # ... and FlatAdam steps on that very buffer
+    assert opt._flat[0]["flat"].data_ptr() == model.flat_parameters()[0].data_ptr()
     data = PackedBatch.from_lists(*_bs_lists(40, seed=2), device=DEV)
 
     def fwd():
