@@ -228,6 +228,9 @@ int njode_device_status(uint32_t* status_host);
  * status, its first site}; site = code | warp << 8 | block << 16.  With NJODE_NO_TRAP=1 in the environment a kernel
  * that gives up records the site and runs on without waiting (results are garbage) instead of trapping. */
 int njode_device_status_detail(uint32_t* words_host);
+/* bring-up aid: {SM cycles, chain GEMMs} of each of the first n_ctas CTAs of the most recent WIDE sweep launch (forward
+ * or reverse), uint64[n_ctas][2], n_ctas <= 512.  Synchronises the device. */
+int njode_debug_cta_cycles(unsigned long long* out_host, int n_ctas);
 /* Number of CUDA kernels this library has launched in this process (every launch site counts itself);
  * reset != 0 returns the count and sets it to zero.  Measurement aid for bench.py's `gpu_launches`. */
 int64_t njode_kernel_launches(int32_t reset);

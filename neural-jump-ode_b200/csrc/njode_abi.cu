@@ -171,6 +171,13 @@ int32_t njode_slot_extra(const NjodeDesc* d) {
   return pick_impl(d, &why) == NJODE_IMPL_WIDE ? NJODE_WIDE_XSLOTS : 0;
 }
 
+int32_t njode_table_workers(const NjodeDesc* d, int64_t n_tiles) {
+  const char* why = nullptr;
+  if (pick_impl(d, &why) != NJODE_IMPL_WIDE || n_tiles <= 0) return 0;
+  const int S = d->shared_network ? 1 : d->num_moments;
+  return njode_wide_workers(d, n_tiles) / S;
+}
+
 static int sm_count_abi() {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -339,6 +346,8 @@ static SweepArgs make_args(const NjodeDesc* desc, const float* params, const flo
   a.N = N; a.n_tiles = n_tiles; a.total_slots = total_slots; a.tile_rows = tile_rows;
   const TilePlan plan = njode_tile_plan(desc, N);
   a.tile_units = plan.units; a.tile_units_small = plan.units_small; a.n_small_tiles = plan.n_small;
+  a.table_workers = njode_table_workers(desc, n_tiles);
+  a.tile_table = a.table_workers > 0 ? (const int32_t*)(tile_slot_off + n_tiles + 1) : nullptr;
   return a;
 }
 
@@ -430,7 +439,9 @@ extern "C" size_t njode_batch_arena_bytes(const NjodeDesc* desc, int64_t B, int6
   take(NJODE_ARENA_KENC, (size_t)N * sizeof(int32_t));
   take(NJODE_ARENA_PERM, (size_t)n_tiles * tile_rows * sizeof(int32_t));
   take(NJODE_ARENA_TILE_KMAX, (size_t)n_tiles * sizeof(int32_t));
-  take(NJODE_ARENA_TILE_SLOT_OFF, (size_t)(n_tiles + 1) * sizeof(int64_t));
+  // (+ the wide flavour's tile -> worker table behind the slot offsets)
+  take(NJODE_ARENA_TILE_SLOT_OFF, (size_t)(n_tiles + 1) * sizeof(int64_t) +
+                                      njode_table_ints(njode_table_workers(desc, n_tiles), n_tiles) * sizeof(int32_t));
   take(NJODE_ARENA_HEADER, NJODE_HDR_WORDS * sizeof(int64_t));
   take(NJODE_ARENA_KNOTS, (size_t)total_slots * tile_rows * sizeof(float));
   if (layout) memcpy(layout, lay, sizeof(lay));

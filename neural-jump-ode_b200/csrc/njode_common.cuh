@@ -172,6 +172,11 @@ TilePlan njode_tile_plan(const NjodeDesc* d, int64_t N);
 // checkpoint slots a tile owns beyond its kmax + 1 step slots (the wide flavour keeps the jump / readout
 // activations of a tile in three extra slots, see njode_wide.cuh)
 int32_t njode_slot_extra(const NjodeDesc* d);
+// wide flavour: workers per stack the tile table is built for (0 = this flavour has no table) and the table's size
+int32_t njode_table_workers(const NjodeDesc* d, int64_t n_tiles);
+static inline size_t njode_table_ints(int32_t table_workers, int64_t n_tiles) {       // offsets, lists, scratch
+  return table_workers > 0 ? (size_t)(table_workers + 1 + 2 * n_tiles) : 0;
+}
 
 struct SweepArgs {
   NjodeDesc desc;
@@ -203,6 +208,11 @@ struct SweepArgs {
   // ~n x 2.1e-8 too small in magnitude (round 1 measured the drift, round 2 modelled it: DESIGN.md); the epilogues
   // scale what they read back by (1 + that) -- the factors for a chain GEMM and for a weight-gradient plane pair
   float comp_chain, comp_wgrad;
+  // wide flavour: the tiles of worker w (of table_workers per stack), in the order it runs them:
+  // tile_table[n_w + 1 + i] for i in [tile_table[w], tile_table[w + 1]).  Built with the schedule (njode_schedule.cu:
+  // greedy longest-processing-time assignment).
+  const int32_t* tile_table;
+  int32_t table_workers;
 };
 
 #define NJODE_GENERIC_TILE_ROWS 32

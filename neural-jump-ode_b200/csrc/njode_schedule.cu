@@ -105,6 +105,68 @@ __global__ void k_tile_scan(const int32_t* __restrict__ tile_kmax, int64_t n_til
   for (int64_t t = lo; t < hi; ++t) { slot_off[t] = acc; acc += tile_kmax[t] + 1 + slots_extra; }
 }
 
+// Tile -> worker assignment of the wide flavour.  Tiles are sorted by step count, and the longest few are outliers
+// (config-4 shape, 2048 trajectories: kmax 244, 127, 116, ... against a mean of 21), so dealing them out in a fixed
+// snake leaves the worker that got tile 0 with 1.5-1.7x the mean work and the sweep kernels wait for it (measured per
+// CTA: tools/cta_balance.py).  Greedy longest-processing-time: every tile, in descending order of cost, goes to the
+// worker with the least work so far (ties: lowest worker id, so the result is deterministic).  One warp: lane l keeps
+// the loads of workers l, l + 32, ... in registers, the argmin is a shuffle reduction.
+// table = [n_w + 1 offsets][n_tiles tile ids, grouped by worker, in processing order][n_tiles scratch]
+__global__ void __launch_bounds__(32) k_lpt_assign(const int32_t* __restrict__ tile_kmax, int64_t n_tiles, int n_w, int cost_per_step,
+                                                   int cost_fixed, int32_t* __restrict__ table) {
+  const int lane = threadIdx.x;
+  constexpr int PER = 8;                                   // up to 256 workers
+  unsigned int load[PER], count[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { load[i] = 0; count[i] = 0; }
+  int32_t* const off = table;
+  int32_t* const list = table + n_w + 1;
+  int32_t* const owner = list + n_tiles;
+  for (int64_t t = 0; t < n_tiles; ++t) {
+    unsigned long long best = ~0ull;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int w = lane + 32 * i;
+      if (w < n_w) {
+        const unsigned long long k = ((unsigned long long)load[i] << 16) | (unsigned)w;
+        best = k < best ? k : best;
+      }
+    }
+    for (int sft = 16; sft > 0; sft >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, sft);
+      best = o < best ? o : best;
+    }
+    const int w = (int)(best & 0xffffu);
+    const unsigned cost = (unsigned)(tile_kmax[t] * cost_per_step + cost_fixed);
+#pragma unroll
+    for (int i = 0; i < PER; ++i)
+      if (w == lane + 32 * i) { load[i] += cost; count[i] += 1; }
+    if (lane == 0) owner[t] = w;
+  }
+  // offsets: exclusive scan of the counts in worker order (w = lane + 32 i: scan over i-major blocks of 32)
+  unsigned int base = 0;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    unsigned int c = (lane + 32 * i < n_w) ? count[i] : 0, inc = c;
+    for (int sft = 1; sft < 32; sft <<= 1) {
+      const unsigned int o = __shfl_up_sync(0xffffffffu, inc, sft);
+      if (lane >= sft) inc += o;
+    }
+    if (lane + 32 * i < n_w) off[lane + 32 * i] = (int32_t)(base + inc - c);
+    base += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  if (lane == 0) off[n_w] = (int32_t)n_tiles;
+  __syncwarp();
+  // scatter, keeping every worker's tiles in descending order of cost (= ascending tile id)
+  for (int w0 = 0; w0 < n_w; w0 += 32) {                    // lane handles worker w0 + lane: walks the owner array once per 32 workers
+    const int w = w0 + lane;
+    int pos = w < n_w ? off[w] : 0;
+    for (int64_t t = 0; t < n_tiles; ++t) {
+      if (w < n_w && owner[t] == w) list[pos++] = (int32_t)t;
+    }
+  }
+}
+
 // one thread per (tile,row): the float32 knots t_0..t_kmax of that row
 __global__ void k_fill_knots(const float* __restrict__ times, const int32_t* __restrict__ kenc,
                              const int32_t* __restrict__ perm, const int32_t* __restrict__ tile_kmax,
@@ -148,6 +210,8 @@ extern "C" size_t njode_schedule_workspace_bytes(int64_t B, int64_t N, int32_t t
   return 4 * njode_align_up((size_t)N * sizeof(int32_t), 256) + njode_align_up(sort_temp_bytes(N), 256);
 }
 
+// NOTE: for the wide flavour `tile_slot_off` must have room for the tile table behind its n_tiles + 1 entries
+// (njode_table_ints(njode_table_workers(..)) int32); njode_batch_arena_bytes lays the arena out that way.
 extern "C" int njode_schedule_build(const NjodeDesc* desc, const float* times, const int64_t* obs_offsets,
                                     int64_t B, int64_t N, int32_t tile_rows,
                                     int32_t* kenc, int32_t* perm, int32_t* tile_kmax, int64_t* tile_slot_off,
@@ -184,6 +248,13 @@ extern "C" int njode_schedule_build(const NjodeDesc* desc, const float* times, c
   NJODE_LAUNCH_OK("k_spread_perm");
   k_tile_scan<<<1, 1024, 0, st>>>(tile_kmax, n_tiles, njode_slot_extra(desc), tile_slot_off, (long long*)header);
   NJODE_LAUNCH_OK("k_tile_scan");
+  const int n_w = njode_table_workers(desc, n_tiles);
+  if (n_w > 0) {      // the table lives behind the n_tiles + 1 slot offsets (njode_batch_arena_bytes sizes the region for it)
+    if (n_w > 256) NJODE_FAIL(NJODE_EINVAL, "njode_schedule_build: more than 256 workers per stack");
+    k_lpt_assign<<<1, 32, 0, st>>>(tile_kmax, n_tiles, n_w, desc->n_hidden_layers + 1, 3 * desc->n_hidden_layers,
+                                   (int32_t*)(tile_slot_off + n_tiles + 1));
+    NJODE_LAUNCH_OK("k_lpt_assign");
+  }
   return NJODE_OK;
 }
 

@@ -68,8 +68,9 @@ __device__ __forceinline__ bool cursor_valid(const Cursor& cu, int L) { return c
 __device__ __forceinline__ void cursor_seek(Cursor& cu, const SweepArgs& a, int wi, int n_w) {
   const int L = a.T.L;
   while (cu.c < n_cats(L)) {
-    const int64_t tile = wi + (int64_t)cu.r * n_w;
-    if (tile < a.n_tiles) {
+    const int lo = a.tile_table[wi], cnt = a.tile_table[wi + 1] - lo;      // this worker's tiles: the schedule's table, as in the sweeps
+    if (cu.r < cnt) {
+      const int tile = a.tile_table[n_w + 1 + lo + cu.r];
       int kind, l;
       cat_decode(L, cu.c, kind, l);
       cu.kmax = a.tile_kmax[tile];

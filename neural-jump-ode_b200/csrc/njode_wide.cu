@@ -25,6 +25,8 @@ using namespace wide;
 
 __device__ unsigned g_status[2] = {0, 0};
 __device__ unsigned g_notrap = 0;
+// bring-up aid (njode_debug_cta_cycles): cycles and chain GEMMs of every CTA of the last sweep launch
+__device__ unsigned long long g_cta_cycles[512][2];
 
 constexpr int NT = NT_W + 128;         // 16 worker warps + one warpgroup holding the MMA issuer warp and the weight producer warp
 // Register budget: the CTA launches with 640 x 96 registers and setmaxnreg moves registers inside that pool:
@@ -63,9 +65,16 @@ struct Smem {
 __device__ __forceinline__ int64_t pred_index(const ParamTable& T, int64_t obs, int s, int o) {
   return T.S == 1 ? obs * T.d_y * T.M + o : (obs * T.d_y + o) * T.M + s;
 }
-__device__ __forceinline__ int64_t snake_tile(int64_t round, int worker, int n_workers) {
-  return round * n_workers + ((round & 1) ? n_workers - 1 - worker : worker);
-}
+// the tiles of a worker, in the order it runs them: the schedule's longest-processing-time table (SweepArgs::tile_table)
+struct TileList {
+  const int32_t* list;
+  int n;
+  __device__ __forceinline__ TileList(const SweepArgs& a, int worker, int n_workers) {
+    const int lo = a.tile_table[worker];
+    n = a.tile_table[worker + 1] - lo;
+    list = a.tile_table + n_workers + 1 + lo;
+  }
+};
 
 // ------------------------------------------------------------------------------------------------
 // weight images: for every stack and chain matrix, NSUB stages of [hi | lo] x [H rows n][32 k], K-major with the
@@ -125,9 +134,9 @@ __device__ __forceinline__ void producer(const SweepArgs& a, uint8_t* raw, const
       bulk_g2s(sm.ring + (size_t)stage * C::STAGE_BYTES, src + (size_t)j * C::STAGE_BYTES, C::STAGE_BYTES, &ctl.full[stage]);
     }
   };
-  for (int64_t round = 0; round * n_workers < a.n_tiles; ++round) {
-    const int64_t tile = snake_tile(round, worker, n_workers);
-    if (tile >= a.n_tiles) continue;
+  const TileList tl(a, worker, n_workers);
+  for (int ti = 0; ti < tl.n; ++ti) {
+    const int64_t tile = tl.list[ti];
     const int kmax = a.tile_kmax[tile];
     if (!BWD) {
       for (int l = 1; l <= L; ++l) load(mat_jump(L, l));
@@ -157,9 +166,9 @@ __device__ __forceinline__ void issuer(const SweepArgs& a, uint8_t* raw) {
   constexpr uint32_t idesc = umma::idesc_tf32(128, HW, 0, 0);
   Diag dg{g_status, g_notrap, BWD ? 8u : 4u, false};
   uint32_t sc = 0, gi = 0;
-  for (int64_t round = 0; round * n_workers < a.n_tiles; ++round) {
-    const int64_t tile = snake_tile(round, worker, n_workers);
-    if (tile >= a.n_tiles) continue;
+  const TileList tl(a, worker, n_workers);
+  for (int ti = 0; ti < tl.n; ++ti) {
+    const int64_t tile = tl.list[ti];
     const int n_gemm = 3 * L + a.tile_kmax[tile] * (L + 1);
 #pragma unroll 1
     for (int e = 0; e < n_gemm; ++e, ++gi) {
@@ -279,9 +288,9 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
   const int64_t PL = C::PL, slotf = (int64_t)(L + 1) * PL;
   float* const ckpt_s = a.ckpt ? a.ckpt + (int64_t)s * a.total_slots * slotf + ((col0 >> 3) * R + row) * 8 : nullptr;
 
-  for (int64_t round = 0; round * n_workers < a.n_tiles; ++round) {
-    const int64_t tile = snake_tile(round, worker, n_workers);
-    if (tile >= a.n_tiles) continue;
+  const TileList tl(a, worker, n_workers);
+  for (int ti = 0; ti < tl.n; ++ti) {
+    const int64_t tile = tl.list[ti];
     const int kmax = a.tile_kmax[tile];
     const int u = a.perm[tile * R + row];
     float* const ck = ckpt_s ? ckpt_s + a.tile_slot_off[tile] * slotf : nullptr;
@@ -488,9 +497,9 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
   const int64_t half = (int64_t)T.S * a.total_slots * slotf;             // floats of half A
   const int64_t toff = (int64_t)s * a.total_slots * slotf + ((col0 >> 3) * R + row) * 8;
 
-  for (int64_t round = 0; round * n_workers < a.n_tiles; ++round) {
-    const int64_t tile = snake_tile(round, worker, n_workers);
-    if (tile >= a.n_tiles) continue;
+  const TileList tl(a, worker, n_workers);
+  for (int ti = 0; ti < tl.n; ++ti) {
+    const int64_t tile = tl.list[ti];
     const int kmax = a.tile_kmax[tile];
     const int u = a.perm[tile * R + row];
     const int ke = u >= 0 ? a.kenc[u] : 0;
@@ -663,6 +672,7 @@ __global__ void __launch_bounds__(NT, 1) k_wide_sweep(SweepArgs a, const float* 
   extern __shared__ uint8_t smem_raw[];
   using C = Cfg<HW>;
   const int warp = threadIdx.x >> 5;
+  const long long t_start = clock64();
   {
     Smem<HW> sm(smem_raw);
     Ctl& ctl = *sm.ctl;
@@ -692,6 +702,14 @@ __global__ void __launch_bounds__(NT, 1) k_wide_sweep(SweepArgs a, const float* 
   if (warp == 0) {
     Smem<HW> sm(smem_raw);
     umma::tmem_free(*reinterpret_cast<volatile uint32_t*>(&sm.ctl->tmem_base), C::TMEM_COLS);
+  }
+  if (threadIdx.x == 0 && blockIdx.x < 512) {
+    unsigned long long work = 0;
+    const int S = a.T.S, nw = gridDim.x / S;
+    const TileList tl(a, blockIdx.x / S, nw);
+    for (int ti = 0; ti < tl.n; ++ti) work += 3 * a.T.L + a.tile_kmax[tl.list[ti]] * (a.T.L + 1);
+    g_cta_cycles[blockIdx.x][0] = (unsigned long long)(clock64() - t_start);
+    g_cta_cycles[blockIdx.x][1] = work;
   }
 }
 
@@ -788,8 +806,16 @@ static void set_comp(SweepArgs& a) {
   a.comp_wgrad = 1.0f + scale * 5.5e-7f;
 }
 
+static int check_table(const SweepArgs& a) {
+  if (a.n_tiles > 0 && (!a.tile_table || a.table_workers * a.T.S != a.n_workers))
+    NJODE_FAIL(NJODE_EINVAL, "wide kernels: the schedule's tile table was built for %d workers per stack, the launch has %d",
+               a.table_workers, a.n_workers / a.T.S);
+  return NJODE_OK;
+}
+
 int njode_wide_forward(const SweepArgs& a_in, float* images, cudaStream_t st) {
   SweepArgs a = a_in;
+  if (int rc0 = check_table(a)) return rc0;
   set_comp(a);
   int rc = a.desc.hidden == 128 ? prep_images<128>(a, images, st, 0) : prep_images<64>(a, images, st, 0);
   if (rc) return rc;
@@ -798,12 +824,20 @@ int njode_wide_forward(const SweepArgs& a_in, float* images, cudaStream_t st) {
 
 int njode_wide_backward(const SweepArgs& a_in, float* images, cudaStream_t st) {
   SweepArgs a = a_in;
+  if (int rc0 = check_table(a)) return rc0;
   set_comp(a);
   int rc = a.desc.hidden == 128 ? prep_images<128>(a, images, st, 1) : prep_images<64>(a, images, st, 1);
   if (rc) return rc;
   rc = a.desc.hidden == 128 ? dispatch_wide<128>(a, images, st, true) : dispatch_wide<64>(a, images, st, true);
   if (rc) return rc;
   return njode_wide_wgrad(a, st);
+}
+
+extern "C" int njode_debug_cta_cycles(unsigned long long* out_host, int n_ctas) {
+  if (!out_host || n_ctas < 1 || n_ctas > 512) NJODE_FAIL(NJODE_EINVAL, "njode_debug_cta_cycles: need 1..512 CTAs");
+  NJODE_CUDA_OK(cudaDeviceSynchronize());
+  NJODE_CUDA_OK(cudaMemcpyFromSymbol(out_host, g_cta_cycles, (size_t)n_ctas * 2 * sizeof(unsigned long long)));
+  return NJODE_OK;
 }
 
 int njode_wide_sweep_status(unsigned* out_host) {

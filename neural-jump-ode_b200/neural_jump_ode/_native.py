@@ -76,6 +76,7 @@ SIGNATURES = {
     "njode_ffma_peak": (C.c_int, [C.POINTER(C.c_float)]),
     "njode_device_status": (C.c_int, [C.POINTER(C.c_uint32)]),
     "njode_device_status_detail": (C.c_int, [C.POINTER(C.c_uint32)]),
+    "njode_debug_cta_cycles": (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
     "njode_kernel_launches": (_I64, [_I32]),
 }
 
