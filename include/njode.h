@@ -231,6 +231,9 @@ int njode_device_status_detail(uint32_t* words_host);
 /* bring-up aid: {SM cycles, chain GEMMs} of each of the first n_ctas CTAs of the most recent WIDE sweep launch (forward
  * or reverse), uint64[n_ctas][2], n_ctas <= 512.  Synchronises the device. */
 int njode_debug_cta_cycles(unsigned long long* out_host, int n_ctas);
+/* phase-accounting build only (`make phase`, tools/phase_wide.py): per-CTA cycles per phase of the WIDE kernels,
+ * uint64[n_ctas][8]; which = 1: the last sweep launch, 3: the weight-gradient GEMM.  Zeros in the product build. */
+int njode_debug_phase(int32_t which, unsigned long long* out_host, int32_t n_ctas);
 /* Number of CUDA kernels this library has launched in this process (every launch site counts itself);
  * reset != 0 returns the count and sets it to zero.  Measurement aid for bench.py's `gpu_launches`. */
 int64_t njode_kernel_launches(int32_t reset);

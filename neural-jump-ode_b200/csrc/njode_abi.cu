@@ -103,6 +103,17 @@ extern "C" int njode_device_status(uint32_t* status_host) {
   return rc;
 }
 
+// `make phase` build only: per-CTA phase cycles, uint64[n_ctas][8]; which = 1: last sweep launch, worker thread 0 (buckets
+// 0 epilogue, 1 accumulator wait), 2: its MMA issuer (0 operand wait, 1 weight wait, 2 issue), 3: weight-gradient loader role (0 bookkeeping, 1 stage wait, 2 split + stores, 3 fence + hand-over,
+// 4 load issue, 5 merge, 6 flush).  All zeros in the product build.
+int njode_sweep_phase_fetch(unsigned long long* out_host, int n_ctas, int issuer);
+int njode_wgrad_phase_fetch(unsigned long long* out_host, int n_ctas);
+extern "C" int njode_debug_phase(int32_t which, unsigned long long* out_host, int32_t n_ctas) {
+  if (!out_host || n_ctas < 1 || n_ctas > 512) NJODE_FAIL(NJODE_EINVAL, "njode_debug_phase: need 1..512 CTAs");
+  NJODE_CUDA_OK(cudaDeviceSynchronize());
+  return which == 3 ? njode_wgrad_phase_fetch(out_host, n_ctas) : njode_sweep_phase_fetch(out_host, n_ctas, which == 2);
+}
+
 // bring-up detail of the wide kernels: {sweep status, first sweep site that gave up, weight-gradient status, its first site}
 // (site = code | warp << 8 | block << 16; codes in njode_wide.cu / njode_wgrad.cu)
 extern "C" int njode_device_status_detail(uint32_t* words_host) {

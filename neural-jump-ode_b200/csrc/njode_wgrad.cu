@@ -24,6 +24,7 @@ using namespace wide;
 
 __device__ unsigned g_status[2] = {0, 0};
 __device__ unsigned g_notrap = 0;
+__device__ unsigned long long g_phase3[512][8];     // `make phase`: per-CTA phase cycles of the loader role (thread 0)
 
 constexpr int NT3 = NT_W + 128;        // 16 loader / merge warps + one warpgroup whose first warp issues the MMAs (setmaxnreg: 104 / 56 registers)
 constexpr int NSTAGE3 = 3;
@@ -349,6 +350,7 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* raw) {
 
   uint32_t sc = 0, ic = 0;
   bool pending = false;                  // instance ic - 1 not merged yet
+  PH_DECL;
   while (cursor_valid(cur, L)) {
     int kind, l;
     cat_decode(L, cur.c, kind, l);
@@ -363,7 +365,9 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* raw) {
 #pragma unroll
     for (int qs = 0; qs < R / SROWS; ++qs, ++sc) {
       const uint32_t stage = sc % NSTAGE3, sround = sc / NSTAGE3;
+      PH(0);                                                       // bookkeeping between stages
       wait_or_die(&ctl.empty[stage], (sround & 1u) ^ 1u, dg, 8);
+      PH(1);                                                       // waiting for a free stage (MMA side is behind)
       const uint32_t sb = ring_s + stage * G::STAGE;
       uint32_t hi[8], lo[8];
       if (loader) {
@@ -390,9 +394,11 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* raw) {
           for (int o = 0; o < MAX_O; ++o) dbo[o] += x[1 + o];
         }
       }
+      PH(2);                                                       // split + tile stores (incl. waiting for the register loads)
       umma::fence_async_smem();
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&ctl.full[stage]);
+      PH(3);                                                       // proxy fence + hand-over
       // the next stage's loads (next plane pair after the last stage of this one), and the L2 prefetch far ahead
       if (qs + 1 < R / SROWS) {
         issue_loads(src, qs + 1);
@@ -404,15 +410,19 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* raw) {
     }
     if (pf_ok) cursor_next(pf, a, wi, n_w);
     cur = nxt;
+    PH(4);                                                         // issuing loads / prefetches, cursor
     if (pending) merge(ic - 1);
+    PH(5);                                                         // merge (incl. waiting for the accumulator)
     pending = true;
     ++ic;
     if (!cursor_valid(cur, L) || cur.c != c_now) {    // category finished: fold the last accumulator in and flush
       merge(ic - 1);
       pending = false;
       flush(kind, l);
+      PH(6);                                                       // category end: last merge + flush
     }
   }
+  PH_STORE(g_phase3);
 }
 
 template <int HW>
@@ -465,6 +475,11 @@ int launch_wgrad(const SweepArgs& a, cudaStream_t st) {
 int njode_wide_wgrad(const SweepArgs& a, cudaStream_t st) {
   if (a.n_tiles == 0) return NJODE_OK;
   return a.desc.hidden == 128 ? launch_wgrad<128>(a, st) : launch_wgrad<64>(a, st);
+}
+
+int njode_wgrad_phase_fetch(unsigned long long* out_host, int n_ctas) {
+  NJODE_CUDA_OK(cudaMemcpyFromSymbol(out_host, g_phase3, (size_t)n_ctas * 8 * sizeof(unsigned long long)));
+  return NJODE_OK;
 }
 
 int njode_wide_wgrad_status(unsigned* out_host) {

@@ -27,6 +27,8 @@ __device__ unsigned g_status[2] = {0, 0};
 __device__ unsigned g_notrap = 0;
 // bring-up aid (njode_debug_cta_cycles): cycles and chain GEMMs of every CTA of the last sweep launch
 __device__ unsigned long long g_cta_cycles[512][2];
+__device__ unsigned long long g_phase12[512][8];    // `make phase`: per-CTA phase cycles of the worker role (thread 0)
+__device__ unsigned long long g_phase_iss[512][8];  // ... and of the MMA issuer (lane 0): 0 operand wait, 1 weight wait, 2 issue
 
 constexpr int NT = NT_W + 128;         // 16 worker warps + one warpgroup holding the MMA issuer warp and the weight producer warp
 // Register budget: the CTA launches with 640 x 96 registers and setmaxnreg moves registers inside that pool:
@@ -165,6 +167,7 @@ __device__ __forceinline__ void issuer(const SweepArgs& a, uint8_t* raw) {
   const uint32_t ring_s = umma::smem_u32(sm.ring);
   constexpr uint32_t idesc = umma::idesc_tf32(128, HW, 0, 0);
   Diag dg{g_status, g_notrap, BWD ? 8u : 4u, false};
+  PH_DECL_AT(NT_W);
   uint32_t sc = 0, gi = 0;
   const TileList tl(a, worker, n_workers);
   for (int ti = 0; ti < tl.n; ++ti) {
@@ -176,8 +179,11 @@ __device__ __forceinline__ void issuer(const SweepArgs& a, uint8_t* raw) {
 #pragma unroll 1
       for (int j = 0; j < C::NSUB; ++j, ++sc) {
         const uint32_t stage = sc % C::NSTAGE, sround = sc / C::NSTAGE;
+        PH(2);
         wait_or_die(&ctl.ops[j], gi & 1u, dg, 2);            // the A columns of this sub-step are in TMEM
+        PH(0);
         wait_or_die(&ctl.full[stage], sround & 1u, dg, 3);   // its weights are in the ring
+        PH(1);
         umma::fence_after_sync();
         if (umma::elect_one()) {
           const uint64_t dbh = umma::desc_k(ring_s + stage * C::STAGE_BYTES);
@@ -196,6 +202,8 @@ __device__ __forceinline__ void issuer(const SweepArgs& a, uint8_t* raw) {
       }
     }
   }
+  PH(2);
+  PH_STORE(g_phase_iss);
 }
 
 // per-thread view of the worker role
@@ -219,26 +227,45 @@ struct WorkerCtx {
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&ctl.tmem_base);
     lane_base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
   }
-  // sub-chunk j of the next GEMM's A operand: split, store to TMEM, tell the issuer (one arrival per warp)
+  // Both directions of the TMEM traffic are software-pipelined: an epilogue is a chain of short dependent steps
+  // (tcgen05.ld -> wait -> arithmetic -> tcgen05.st -> wait -> fence -> arrive), and run back to back every sub-step
+  // cost ~1000 cycles whatever its arithmetic (phase build: the reverse sweep, a tenth of the forward's arithmetic,
+  // had the same epilogue time).  So the accumulator chunk j + 1 is requested before chunk j is processed, and the
+  // hand-over of chunk j (wait::st, fence, arrive) is issued after the arithmetic of chunk j + 1, when its stores
+  // have long landed.  wait_acc() flushes the last pending hand-over: every emission is followed by one.
+  float nx[8];             // accumulator chunk in flight
+  int pend = -1;           // emitted sub-chunk whose hand-over is still to be signalled
+  __device__ __forceinline__ void signal_pending() {
+    if (pend >= 0) {
+      umma::wait_st();
+      umma::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_relaxed(&ctl.ops[pend]);
+      pend = -1;
+    }
+  }
+  // sub-chunk j of the next GEMM's A operand: split, store to TMEM; the issuer is told one sub-chunk later
   __device__ __forceinline__ void emit(int j, const float (&v)[8]) {
     uint32_t hi[8], lo[8];
     umma::split8(v, hi, lo);
+    signal_pending();
     umma::tmem_st8_raw(lane_base + C::A_HI + 8 * j, hi);
     umma::tmem_st8_raw(lane_base + C::A_LO + 8 * j, lo);
-    umma::wait_st();
-    umma::fence_before_sync();
-    __syncwarp();
-    if (lane == 0) umma::mbar_arrive(&ctl.ops[j]);
+    pend = j;
   }
-  // wait for the accumulator of GEMM gi (call once per GEMM, then acc_ld for each sub-chunk, then done())
+  // wait for the accumulator of GEMM gi (call once per GEMM, then acc_ld for sub-chunks 0, 1, .. in order, then done())
   __device__ __forceinline__ void wait_acc() {
+    signal_pending();
     wait_or_die(&ctl.accd[gi & 1u], (gi >> 1) & 1u, dg, 4);
     umma::fence_after_sync();
+    umma::tmem_ld8_nowait(lane_base + C::ACC0 + (gi & 1u) * HW, nx);
   }
   __device__ __forceinline__ void acc_ld(int j, float (&v)[8]) {
-    umma::tmem_ld8(lane_base + C::ACC0 + (gi & 1u) * HW + 8 * j, v);
+    // (the registers are operands of the wait so that no use of them can be scheduled in front of it)
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(nx[0]), "+f"(nx[1]), "+f"(nx[2]), "+f"(nx[3]), "+f"(nx[4]), "+f"(nx[5]), "+f"(nx[6]), "+f"(nx[7]) :: "memory");
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] *= comp;
+    for (int i = 0; i < 8; ++i) v[i] = nx[i] * comp;
+    if (j + 1 < C::NSUB) umma::tmem_ld8_nowait(lane_base + C::ACC0 + (gi & 1u) * HW + 8 * (j + 1), nx);
   }
   __device__ __forceinline__ void done() { ++gi; }
 };
@@ -270,6 +297,10 @@ __device__ __forceinline__ void scale8(int sc, float (&v)[8]) {
   }
 }
 
+// phase accounting (`make phase`): bucket 0 = everything between accumulator waits (epilogues, emissions, readouts),
+// bucket 1 = waiting for an accumulator (the MMA tail the epilogue cannot hide + barrier latency)
+#define WAIT_ACC() do { PH(0); w.wait_acc(); PH(1); } while (0)
+
 // ------------------------------------------------------------------------------------------------
 // forward sweep: row workers
 // ------------------------------------------------------------------------------------------------
@@ -280,6 +311,7 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
   Smem<HW> sm(raw);
   WorkerCtx<HW> w(sm, 4u);
   w.comp = a.comp_chain;
+  PH_DECL;
   SmallW<HW>& sw = w.sw;
   const ParamTable& T = a.T;
   const int L = T.L, dx = T.d_x, O = T.O, sc_kind = a.desc.input_scaling;
@@ -325,7 +357,7 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
       if (ck) st8g(cp(X3, 0, j), z);
     }
     for (int l = 1; l <= L; ++l) {
-      w.wait_acc();
+      WAIT_ACC();
 #pragma unroll
       for (int j = 0; j < NSUB; ++j) {
         float z[8], cb[8];
@@ -353,7 +385,7 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
 #pragma unroll
       for (int o = 0; o < MAX_O; ++o) y[o] = 0.0f;
       for (int l = 0; l < L; ++l) {
-        w.wait_acc();
+        WAIT_ACC();
 #pragma unroll
         for (int j = 0; j < NSUB; ++j) {
           float z[8], cb[8];
@@ -407,7 +439,7 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
       const float tn_loaded = ldg_na(kn + (k + 2 <= kmax ? k + 2 : kmax) * R);
       const float delta = __fsub_rn(tn, tc);
       // first layer: bias + the x / t_cur / dt columns on the CUDA cores      jump_ode.py:57-61
-      w.wait_acc();
+      WAIT_ACC();
 #pragma unroll
       for (int j = 0; j < NSUB; ++j) {
         float z[8], cw[8];
@@ -432,7 +464,7 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
       }
       w.done();
       for (int l = 1; l < L; ++l) {
-        w.wait_acc();
+        WAIT_ACC();
 #pragma unroll
         for (int j = 0; j < NSUB; ++j) {
           float z[8], cb[8];
@@ -446,7 +478,7 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
         w.done();
       }
       // last layer (no activation) and the Euler update                      jump_ode.py:130-131 / :138-139
-      w.wait_acc();
+      WAIT_ACC();
       const bool more = k + 1 < kmax;
 #pragma unroll
       for (int j = 0; j < NSUB; ++j) {
@@ -475,6 +507,8 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
     }
     readout(X2, a.preds_before, (int64_t)u + 1, u >= 0 && (ke & 1));
   }
+  PH(0);
+  PH_STORE(g_phase12);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -488,6 +522,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
   Smem<HW> sm(raw);
   WorkerCtx<HW> w(sm, 8u);
   w.comp = a.comp_chain;
+  PH_DECL;
   SmallW<HW>& sw = w.sw;
   const ParamTable& T = a.T;
   const int L = T.L, O = T.O, sc_kind = a.desc.input_scaling;
@@ -535,7 +570,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) zb[8 * j + i] = t8[i];
       }
-      w.wait_acc();
+      WAIT_ACC();
 #pragma unroll
       for (int j = 0; j < NSUB; ++j) {
         float acc[8];
@@ -577,7 +612,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
         st8g(pd(X, L - 1, j), d);
       }
       for (int l = L - 1; l >= 1; --l) chain_layer(pa(X, l, 0), pd(X, l - 1, 0), true);      // -> d * W_out[l-1]
-      w.wait_acc();                                              // d * W_out[0] = d loss / d h through this readout
+      WAIT_ACC();                                              // d * W_out[0] = d loss / d h through this readout
 #pragma unroll
       for (int j = 0; j < NSUB; ++j) {
         float acc[8];
@@ -620,7 +655,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
       for (int l = L; l >= 1; --l) chain_layer(pa(k, l, 0), pd(k, l - 1, 0), true);           // -> d * W_ode[l-1]
       // d * W_ode[0][:, :H] = d loss / d s(h_k); fused with the next step's first operand delta_{k-1} * g
       const float delta_prev = __fsub_rn(tn, tc_next);           // (unused when k == 0)
-      w.wait_acc();
+      WAIT_ACC();
 #pragma unroll
       for (int j = 0; j < NSUB; ++j) {
         float acc[8];
@@ -665,6 +700,8 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
     }
     for (int l = L; l >= 1; --l) chain_layer(pa(X3, l - 1, 0), pd(X3, l - 1, 0), l > 1);      // -> d * W_jump[l-1]
   }
+  PH(0);
+  PH_STORE(g_phase12);
 }
 
 template <int HW, int ACT, bool BWD>
@@ -837,6 +874,12 @@ extern "C" int njode_debug_cta_cycles(unsigned long long* out_host, int n_ctas) 
   if (!out_host || n_ctas < 1 || n_ctas > 512) NJODE_FAIL(NJODE_EINVAL, "njode_debug_cta_cycles: need 1..512 CTAs");
   NJODE_CUDA_OK(cudaDeviceSynchronize());
   NJODE_CUDA_OK(cudaMemcpyFromSymbol(out_host, g_cta_cycles, (size_t)n_ctas * 2 * sizeof(unsigned long long)));
+  return NJODE_OK;
+}
+
+int njode_sweep_phase_fetch(unsigned long long* out_host, int n_ctas, int issuer) {
+  if (issuer) NJODE_CUDA_OK(cudaMemcpyFromSymbol(out_host, g_phase_iss, (size_t)n_ctas * 8 * sizeof(unsigned long long)));
+  else NJODE_CUDA_OK(cudaMemcpyFromSymbol(out_host, g_phase12, (size_t)n_ctas * 8 * sizeof(unsigned long long)));
   return NJODE_OK;
 }
 

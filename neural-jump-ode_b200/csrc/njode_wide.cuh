@@ -79,6 +79,15 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                :: "r"(umma::smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(umma::smem_u32(bar)) : "memory");
 }
 
+// mbarrier arrive WITHOUT release semantics.  The default (release) arrive waits until every earlier memory operation
+// of the thread is performed -- including its checkpoint stores to global memory, an L2 round trip (~1000 cycles) that
+// paced every sub-step of the sweeps (measured with the phase build: an epilogue sub-step took ~1000 cycles whatever
+// its arithmetic).  What a hand-over publishes here is TMEM only: the tcgen05.st has completed (tcgen05.wait::st) and
+// tcgen05.fence::before_thread_sync orders it before the arrive, so no memory release is needed.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" :: "r"(umma::smem_u32(bar)) : "memory");
+}
+
 // sticky diagnostic word (njode_device_status): bit 2 / 3 / 4 = wide forward / reverse / weight-gradient kernel
 // gave up on an mbarrier; bits 8.. = code of the wait site.  The kernel then TRAPS: a protocol failure must never
 // produce silently wrong numbers.  Bring-up aid: with NJODE_NO_TRAP=1 in the environment the thread records the
@@ -118,6 +127,20 @@ static inline int njode_debug_sync_env() {
   static const int v = [] { const char* e = getenv("NJODE_DEBUG_SYNC"); return e ? atoi(e) : 0; }();
   return v;
 }
+
+// optional phase accounting (`make phase`, tools/phase_wide.py): thread 0 of every CTA adds up the SM cycles it spends
+// in each phase of its role and stores the sums at the end.  PH(i) closes the current interval into bucket i.
+#ifdef NJODE_PHASE
+#define PH_DECL_AT(tid) long long ph_t__ = clock64(); long long ph_acc__[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const bool ph_on__ = (threadIdx.x == (tid))
+#define PH_DECL PH_DECL_AT(0)
+#define PH(i) do { if (ph_on__) { const long long n__ = clock64(); ph_acc__[i] += n__ - ph_t__; ph_t__ = n__; } } while (0)
+#define PH_STORE(buf) do { if (ph_on__ && blockIdx.x < 512) { for (int i__ = 0; i__ < 8; ++i__) (buf)[blockIdx.x][i__] = (unsigned long long)ph_acc__[i__]; } } while (0)
+#else
+#define PH_DECL_AT(tid) do { } while (0)
+#define PH_DECL do { } while (0)
+#define PH(i) do { } while (0)
+#define PH_STORE(buf) do { } while (0)
+#endif
 
 }  // namespace wide
 

@@ -77,6 +77,7 @@ SIGNATURES = {
     "njode_device_status": (C.c_int, [C.POINTER(C.c_uint32)]),
     "njode_device_status_detail": (C.c_int, [C.POINTER(C.c_uint32)]),
     "njode_debug_cta_cycles": (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
+    "njode_debug_phase": (C.c_int, [_I32, C.POINTER(C.c_uint64), _I32]),
     "njode_kernel_launches": (_I64, [_I32]),
 }
 
