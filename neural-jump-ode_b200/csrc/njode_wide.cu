@@ -562,14 +562,11 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
     // (>= 3000 cycles at H = 128) hide the HBM latency, whereas a load issued inside the sub-step loop is consumed a
     // few hundred cycles later (measured: long-scoreboard stalls on act'(z) were the top stall of this kernel).
     auto chain_layer = [&](const float* __restrict__ zsrc, float* __restrict__ ddst, bool emit_next) {
+      // (each load writes its final registers: through a temporary the compiler re-used one register octet for all
+      //  chunks and every load waited for the previous one to land -- four serial HBM round trips per layer)
       float zb[CG];
 #pragma unroll
-      for (int j = 0; j < NSUB; ++j) {
-        float t8[8];
-        ld8g(zsrc + j * (R * 8), t8);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) zb[8 * j + i] = t8[i];
-      }
+      for (int j = 0; j < NSUB; ++j) ld8g(zsrc + j * (R * 8), *reinterpret_cast<float(*)[8]>(&zb[8 * j]));
       WAIT_ACC();
 #pragma unroll
       for (int j = 0; j < NSUB; ++j) {
@@ -594,10 +591,14 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
         st8g(cx + (int64_t)X * (R * 8), xv);
       }
       // d (pre-activation of out layer L-1) = (sum_o dY[o] * w_out[o][:]) * act'(z_L)
+      float zl[CG];
+#pragma unroll
+      for (int j = 0; j < NSUB; ++j) ld8g(pa(X, L, j), *reinterpret_cast<float(*)[8]>(&zl[8 * j]));      // all chunks in flight at once
 #pragma unroll
       for (int j = 0; j < NSUB; ++j) {
         float z[8], d[8], cw[8];
-        ld8g(pa(X, L, j), z);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[i] = zl[8 * j + i];
 #pragma unroll
         for (int i = 0; i < 8; ++i) d[i] = 0.0f;
 #pragma unroll
@@ -689,12 +690,14 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
       st8g(cx + (int64_t)X3 * (R * 8), xv);
     }
     // d (pre-activation of jump layer L) = g * act'(h_0)
+    float h0[CG];
+#pragma unroll
+    for (int j = 0; j < NSUB; ++j) ld8g(pa(0, 0, j), *reinterpret_cast<float(*)[8]>(&h0[8 * j]));
 #pragma unroll
     for (int j = 0; j < NSUB; ++j) {
-      float z[8], d[8];
-      ld8g(pa(0, 0, j), z);
+      float d[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = gr[8 * j + i] * act_grad_from_out<ACT>(z[i]);
+      for (int i = 0; i < 8; ++i) d[i] = gr[8 * j + i] * act_grad_from_out<ACT>(h0[8 * j + i]);
       w.emit(j, d);                                              // -> d * W_jump[L]
       st8g(pd(X3, L, j), d);
     }
