@@ -10,6 +10,7 @@
  *   njode_loss         nj_ode_loss (value and d/dpreds)       neural_jump_ode/models/jump_ode.py:235-383
  *   njode_backward     what loss.backward() does for this path neural_jump_ode/utils/training.py:69, :97
  *   njode_adam_step    optimizer.step() on the flat buffer    neural_jump_ode/utils/training.py:98, :396
+ *   njode_dense_forward  the model on a dense time grid       neural_jump_ode/utils/plotting.py:133-256
  *
  * Conventions
  *   - All pointers are DEVICE pointers unless the name ends in _host.  The caller (PyTorch) owns
@@ -181,6 +182,18 @@ int njode_forward_batch_finish(const NjodeDesc* desc, const float* params, const
                                void* arena, size_t arena_bytes, int32_t want_ckpt, float* ckpt, int64_t ckpt_floats,
                                void* scratch, size_t scratch_bytes, int64_t* header_host,
                                float* preds, float* preds_before, void* stream);
+
+/* ---- dense-grid inference: the prediction at every time of a grid (utils/plotting.py:133-256) -------------------------
+ * dense: float32 (B, G, d_y, M) raw readouts (mean, W), overwritten.  grid: (G) float32 ascending, shared by all
+ * trajectories.  The step rule is the plotting code's, not the training one: from the current time to each grid time,
+ * n_sub = max(1, int((t - t_cur) / dt_ode_step)) equal Euler sub-steps (1 if dt_ode_step is None), float32 throughout;
+ * a grid time equal to an observation time holds the post-jump value, except at a trajectory's LAST observation
+ * (pre-jump, plotting.py:210), and grid times before the first observation are 0.  Forward only.
+ * workspace: njode_dense_workspace_bytes. */
+size_t njode_dense_workspace_bytes(const NjodeDesc* desc);
+int njode_dense_forward(const NjodeDesc* desc, const float* params, const float* times, const float* values,
+                        const int64_t* obs_offsets, int64_t B, int64_t N, const float* grid, int64_t G,
+                        float* dense, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- loss: value and gradient w.r.t. preds / preds_before in one pass --------------------------
  * loss_out: device float[1].  grad_* may be NULL (value only).  traj_scale = 1/B_global so that

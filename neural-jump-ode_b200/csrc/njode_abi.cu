@@ -437,6 +437,33 @@ extern "C" int njode_forward(const NjodeDesc* desc, const float* params, const f
 }
 
 // ------------------------------------------------------------------------------------------------
+// dense-grid inference (njode_generic.cu: k_generic_dense)
+extern "C" size_t njode_dense_workspace_bytes(const NjodeDesc* desc) {
+  if (njode_param_count(desc) < 0) return 0;
+  return params_bytes(desc);
+}
+
+extern "C" int njode_dense_forward(const NjodeDesc* desc, const float* params, const float* times, const float* values,
+                                   const int64_t* obs_offsets, int64_t B, int64_t N, const float* grid, int64_t G,
+                                   float* dense, void* workspace, size_t workspace_bytes, void* stream) {
+  const char* why = nullptr;
+  if (!njode_desc_ok(desc, &why)) NJODE_FAIL(NJODE_EINVAL, "njode_dense_forward: %s", why);
+  if (!njode_generic_supported(desc, &why)) NJODE_FAIL(NJODE_EINVAL, "njode_dense_forward: %s", why);
+  if (B < 0 || N < 0 || G < 0) NJODE_FAIL(NJODE_EINVAL, "njode_dense_forward: negative size");
+  if (!params || !dense || (N > 0 && (!times || !values || !obs_offsets)) || (G > 0 && !grid))
+    NJODE_FAIL(NJODE_EINVAL, "njode_dense_forward: null pointer");
+  if (workspace_bytes < njode_dense_workspace_bytes(desc)) NJODE_FAIL(NJODE_EWORKSPACE, "njode_dense_forward: workspace too small");
+  if (N * (desc->shared_network ? 1 : desc->num_moments) >= (1ll << 31)) NJODE_FAIL(NJODE_EINVAL, "njode_dense_forward: too many observations for one launch");
+  cudaStream_t st = (cudaStream_t)stream;
+  NJODE_CUDA_OK(cudaMemsetAsync(dense, 0, (size_t)B * G * desc->d_y * desc->num_moments * sizeof(float), st));
+  if (N == 0 || G == 0) return NJODE_OK;
+  float* params_t = (float*)workspace;
+  int rc = relayout(desc, params, params_t, st);
+  if (rc) return rc;
+  return njode_generic_dense(desc, params, params_t, times, values, obs_offsets, B, N, grid, G, dense, st);
+}
+
+// ------------------------------------------------------------------------------------------------
 // one call for an un-cached batch (see include/njode.h)
 // ------------------------------------------------------------------------------------------------
 extern "C" size_t njode_batch_arena_bytes(const NjodeDesc* desc, int64_t B, int64_t N, int64_t total_slots, int64_t* layout) {

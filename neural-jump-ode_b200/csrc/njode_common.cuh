@@ -220,6 +220,8 @@ int  njode_generic_supported(const NjodeDesc* d, const char** why);
 int  njode_generic_workers(const NjodeDesc* d, int64_t n_tiles);
 int  njode_generic_forward(const SweepArgs& a, cudaStream_t st);
 int  njode_generic_backward(const SweepArgs& a, cudaStream_t st);
+int  njode_generic_dense(const NjodeDesc* d, const float* params, const float* params_t, const float* times, const float* values,
+                         const int64_t* off, int64_t B, int64_t N, const float* grid, int64_t G, float* dense, cudaStream_t st);
 
 // row-tiled FP32 kernels (njode_rowtile.cu): hidden_dim in {32,64,96,128}, <= 3 hidden layers; same tile rows and
 // checkpoint layout as the generic flavour

@@ -292,6 +292,90 @@ __global__ void __launch_bounds__(32) k_generic_backward(SweepArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Dense-grid inference: the model's prediction at EVERY time of a grid, not only at observation
+// times -- what the reference's plotting code computes by driving jump_nns / euler_step / output_nns from Python
+// (utils/plotting.py:133-256).  Its step rule differs from training: from the current time to each grid time t it takes
+//     n_sub = max(1, int((t - t_cur) / dt_ode_step))     (1 if dt_ode_step is None)           plotting.py:166-169
+// equal Euler sub-steps of (t - t_cur) / n_sub, all in float32 (t_cur accumulates), holding x_i constant; after a step
+// sequence it evaluates the output net.  Grid times in [T_i, T_{i+1}] belong to observation i; the value at T_{i+1} is
+// then overwritten by observation i+1 (after its jump) -- except when i+1 is the LAST observation, whose own loop only
+// covers times > T_last (plotting.py:210): the grid point at the last observation keeps the pre-jump value.  Grid
+// times before the first observation stay 0.  One warp per (observation, stack); raw readouts (mean, W) are written,
+// the variance transform (W^2, or clamp(W - mean^2, 0)) is left to the caller (plotting.py:189-196).
+template <int NJ>
+__global__ void __launch_bounds__(32) k_generic_dense(NjodeDesc desc, ParamTable T, const float* __restrict__ params,
+                                                      const float* __restrict__ params_t, const float* __restrict__ times,
+                                                      const float* __restrict__ values, const int64_t* __restrict__ off, int64_t B,
+                                                      int64_t N, const float* __restrict__ grid, int64_t G, float* __restrict__ dense) {
+  const int lane = threadIdx.x;
+  const int s = blockIdx.x % T.S;
+  const int64_t u = blockIdx.x / T.S;
+  if (u >= N) return;
+  const float* p = params + (int64_t)s * T.stack_floats;
+  const float* pt = params_t + (int64_t)s * T.stack_floats;
+  const int act_kind = desc.activation, sc_kind = desc.input_scaling;
+  // trajectory of this observation: last b with off[b] <= u
+  int64_t lo = 0, hi = B;
+  while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (off[mid] <= u) lo = mid; else hi = mid; }
+  const int64_t b = lo;
+  const bool last = (u + 1 == off[b + 1]);
+  const bool next_is_last = !last && (u + 2 == off[b + 1]);
+  const float Ti = times[u], Tn = last ? 0.0f : times[u + 1];
+  // first grid index of this observation: grid >= T_i (last observation: grid > T_last)
+  int64_t g0 = 0, g1 = G;
+  while (g0 < g1) { const int64_t mid = (g0 + g1) >> 1; const float t = grid[mid]; if (last ? (t <= Ti) : (t < Ti)) g0 = mid + 1; else g1 = mid; }
+
+  Vec<NJ> z[NJODE_LMAX + 1];
+  float ext[GEN_EXT_MAX];
+  for (int e = 0; e < T.d_x; ++e) ext[e] = values[u * T.d_x + e];
+  Vec<NJ> none;
+#pragma unroll
+  for (int q = 0; q < NJ; ++q) none.v[q] = 0.0f;
+  net_fwd<NJ>(T, NET_JUMP, pt, p, none, ext, act_kind, z);
+  Vec<NJ> h = z[T.L];
+  for (int e = 0; e < T.d_x; ++e) ext[e] = scale_fwd_rt(sc_kind, ext[e]);
+  const float dtf = desc.dt;
+  float t_cur = Ti;
+  for (int64_t g = g0; g < G; ++g) {
+    const float tt = grid[g];
+    if (!last && tt > Tn) break;
+    const float span = __fsub_rn(tt, t_cur);
+    int n_sub = 1;
+    if (desc.has_dt) { n_sub = (int)__fdiv_rn(span, dtf); if (n_sub < 1) n_sub = 1; }
+    const float dts = __fdiv_rn(span, (float)n_sub);
+    for (int i = 0; i < n_sub; ++i) {
+      const float t_new = __fadd_rn(t_cur, dts);
+      const float delta = __fsub_rn(t_new, t_cur);
+      ext[T.d_x] = t_cur;
+      ext[T.d_x + 1] = delta;
+      Vec<NJ> sh;
+#pragma unroll
+      for (int q = 0; q < NJ; ++q) sh.v[q] = scale_fwd_rt(sc_kind, h.v[q]);
+      net_fwd<NJ>(T, NET_ODE, pt, p, sh, ext, act_kind, z);
+#pragma unroll
+      for (int q = 0; q < NJ; ++q) h.v[q] = fmaf(delta, z[T.L].v[q], h.v[q]);
+      t_cur = t_new;
+    }
+    if (!last && tt == Tn && !next_is_last) continue;          // the next observation writes this grid point (after its jump)
+    net_fwd<NJ>(T, NET_OUT, pt, p, h, nullptr, act_kind, z);
+    if (lane < T.O) dense[pred_index(T, b * G + g, s, lane)] = z[T.L].v[0];
+  }
+}
+
+int njode_generic_dense(const NjodeDesc* d, const float* params, const float* params_t, const float* times, const float* values,
+                        const int64_t* off, int64_t B, int64_t N, const float* grid, int64_t G, float* dense, cudaStream_t st) {
+  const ParamTable T = njode_make_table(d);
+  if (N == 0 || G == 0) return NJODE_OK;
+  const int nj = (T.H + 31) / 32;
+  const unsigned blocks = (unsigned)(N * T.S);
+#define NJODE_DENSE(NJ_) k_generic_dense<NJ_><<<blocks, 32, 0, st>>>(*d, T, params, params_t, times, values, off, B, N, grid, G, dense)
+  if (nj <= 1) NJODE_DENSE(1); else if (nj <= 2) NJODE_DENSE(2); else if (nj <= 4) NJODE_DENSE(4); else NJODE_DENSE(8);
+#undef NJODE_DENSE
+  NJODE_LAUNCH_OK("k_generic_dense");
+  return NJODE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 int njode_generic_supported(const NjodeDesc* d, const char** why) {
   if (d->hidden > 32 * GEN_NJ_MAX) { *why = "generic kernels support hidden_dim <= 256"; return 0; }
   if (d->d_x + 2 > GEN_EXT_MAX) { *why = "generic kernels support input_dim <= 8"; return 0; }

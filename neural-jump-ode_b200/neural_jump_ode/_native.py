@@ -66,6 +66,8 @@ SIGNATURES = {
     "njode_forward_batch": (C.c_int, [_DESC, _P, _P, _P, _P, _I64, _I64, _P, _SZ, _I32, _P, _I64, _P, _SZ, _P, _P, _P, _P]),
     "njode_forward_batch_begin": (C.c_int, [_DESC, _P, _P, _I64, _I64, _P, _SZ, _P, _SZ, _P, _P]),
     "njode_forward_batch_finish": (C.c_int, [_DESC, _P, _P, _P, _P, _I64, _I64, _P, _SZ, _I32, _P, _I64, _P, _SZ, _P, _P, _P, _P]),
+    "njode_dense_workspace_bytes": (_SZ, [_DESC]),
+    "njode_dense_forward": (C.c_int, [_DESC, _P, _P, _P, _P, _I64, _I64, _P, _I64, _P, _P, _SZ, _P]),
     "njode_loss_workspace_bytes": (_SZ, [_I64]),
     "njode_loss": (C.c_int, [_LDESC, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _F, _P, _P, _P, _P, _SZ, _P]),
     "njode_backward_workspace_bytes": (_SZ, [_DESC, _I64]),

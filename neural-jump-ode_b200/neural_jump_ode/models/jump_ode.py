@@ -524,6 +524,46 @@ class NeuralJumpODE(nn.Module):
         self._last_state = None
         return preds, before
 
+    # -- dense-grid inference (plots) ----------------------------------------------------------------
+    @torch.no_grad()
+    def predict_on_grid(self, batch, grid_times: torch.Tensor, batch_values=None) -> torch.Tensor:
+        """The model's raw readouts at EVERY time of ``grid_times`` (ascending, shared by all trajectories) for the
+        observed trajectories in ``batch`` (a ``PackedBatch``, or lists of times / values): a (B, G, d_y, M) tensor.
+        This is the simulation the reference's plotting code runs in Python, one ``euler_step`` at a time
+        (utils/plotting.py:133-256), with its own step rule (``n_sub = max(1, int(gap / dt_ode_step))`` equal sub-steps
+        to each grid time) and its conventions: a grid time that is an observation time shows the value after the
+        jump, except at a trajectory's last observation; times before the first observation are 0.
+        ``grid_moments`` turns the second readout into a variance the way the plots do."""
+        params = self.flat_parameters()
+        dev = self._check_runnable(params)
+        if not isinstance(batch, PackedBatch):
+            batch = PackedBatch.from_lists(batch, batch_values, device=dev)
+        elif batch.device != dev:
+            batch = batch.to(dev)
+        grid = grid_times.to(dev, torch.float32).contiguous()
+        lib = nat.load()
+        desc = self.descriptor()
+        G = int(grid.shape[0])
+        with nat.on_device(dev):
+            flat = self._flat_view(params)
+            dense = torch.empty((batch.B, G, self.output_dim, self.num_moments), dtype=torch.float32, device=dev)
+            ws_bytes = lib.njode_dense_workspace_bytes(desc)
+            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+            nat.check(lib.njode_dense_forward(desc, nat.ptr(flat), nat.ptr(batch.times), nat.ptr(batch.values),
+                                              nat.ptr(batch.offsets), batch.B, batch.N, nat.ptr(grid), G, nat.ptr(dense),
+                                              nat.ptr(ws), ws_bytes, nat.current_stream(dev)), "njode_dense_forward")
+        return dense
+
+    def grid_moments(self, dense: torch.Tensor):
+        """(mean, variance) from ``predict_on_grid`` output as the reference's plots derive them (plotting.py:183-196):
+        variance = W^2 (``variance_method='direct'``) or clamp(W - mean^2, 0) (``'second_moment'``); None for one moment."""
+        mean = dense[..., 0]
+        if self.num_moments < 2:
+            return mean, None
+        w = dense[..., 1]
+        var = w * w if self.variance_method == "direct" else torch.clamp(w - mean * mean, min=0.0)
+        return mean, var
+
     # -- large batches in waves ----------------------------------------------------------------------
     def _flat_grad(self, params):
         """The parameter gradients as ONE flat tensor when they tile one storage in parameter order (what the reverse

@@ -67,3 +67,24 @@ def validate_packed(model: NeuralJumpODE, data: PackedBatch, ignore_first_contin
                        moment_weights=moment_weights, variance_method=vm)
     model.train(was)
     return float(loss.item())
+
+
+@torch.no_grad()
+def relative_loss_packed(model: NeuralJumpODE, data: PackedBatch, process_type: str, process_params: dict,
+                         moment_weights=None, variance_method: Optional[str] = None) -> float:
+    """The reference's relative-loss metric (utils/training.py:219-261) on a packed batch:
+    ``(L_model - L_true) / max(L_true, 1e-8)`` where ``L_true`` is ``nj_ode_loss`` evaluated on the closed-form
+    conditional moments at the observations (``simulation.conditional_moments_packed``).  As in the reference neither
+    loss call passes ``ignore_first_continuity`` (training.py:225-227, :250-252)."""
+    from .simulation import conditional_moments_packed
+    was = model.training
+    model.eval()
+    vm = variance_method if variance_method is not None else getattr(model, "variance_method", "direct")
+    preds, before = model.forward_packed(data)
+    l_model = nj_ode_loss(data, None, preds, before, moment_weights=moment_weights, variance_method=vm)
+    true, true_before = conditional_moments_packed(data, process_type, num_moments=model.num_moments, variance_method=vm,
+                                                   **process_params)
+    l_true = nj_ode_loss(data, None, true, true_before, moment_weights=moment_weights, variance_method=vm)
+    model.train(was)
+    lm, lt = float(l_model.item()), float(l_true.item())
+    return (lm - lt) / max(lt, 1e-8)
