@@ -3,20 +3,27 @@
 // After the two chain sweeps (njode_wide.cu) the checkpoint buffer holds, for every Linear layer application of the
 // batch, the layer's input activations (half A) and d loss / d(pre-activation) (half D) as planes of 128 rows.  A
 // weight gradient is a contraction over rows:   dW[out][in] = sum_rows D[row][out] * A[row][in]
-// i.e. a GEMM whose K index is the row, for ~(kmax + 3) x (L + 1) plane pairs per tile.  Both operands are data, so
-// both go through shared memory as MN-major tf32 tiles (SWIZZLE_128B_BASE32B, 128-byte rows of 32 features):
-//     A operand = D plane  [rows][out]  (M = H),   B operand = [A plane | aux columns]  [rows][in + 16]  (N = H + 16)
+// i.e. a GEMM whose K index is the row, for ~(kmax + 3) x (L + 1) plane pairs per tile:
+//     A operand = D plane transposed [out][rows]  (M = 128), from TENSOR MEMORY: the reverse sweep writes its d planes
+//                 as [row octet][feature][8 rows], a worker here loads 8 consecutive rows of its feature (one LDG.256,
+//                 1 KB contiguous per warp), splits them
+//                 into tf32 hi / lo and stores them straight into TMEM (tcgen05.st), lane = output feature;
+//     B operand = [A plane | aux columns] [rows][in + 16]  (N = H + 16), MN-major tf32 tiles in shared memory
+//                 (SWIZZLE_128B_BASE32B, 128-byte rows of 32 features), split by the workers on the way in.
 // The aux columns (1, s(x).., t, dt | 1, dY.. | 1, x..; written per slot by the reverse sweep) make the bias, the
 // x / t / dt columns of the first ODE layer, the readout weights and the first jump layer fall out of the same MMAs.
+// The first version took BOTH operands from shared memory and was bound by its port (8.5 KB per MMA = 68 cycles at
+// 128 B/cycle plus 72 KB of tile stores per stage: ~1400 cycles per 32-row stage against 864 of tensor time); with
+// the D operand in TMEM a stage moves 40 KB + 54 KB through shared memory and the tensor pipe is the bound.
 // FP32 accuracy: 3xTF32 (P_lo*Q_hi + P_hi*Q_lo + P_hi*Q_hi).  The tensor core's accumulate is not round-to-nearest
-// (round 1: ~3000 MMAs into one accumulator drifted a gradient by 6e-5), so each plane pair (48 MMAs at H=128) goes
-// into a FRESH TMEM accumulator (double buffered) that the CUDA cores merge into TMEM-resident running sums with
-// IEEE adds; running sums are flushed per category into this CTA's partial buffer (reduced in a fixed order by
-// k_reduce_partials: deterministic for a given schedule, no atomics).
-// Pipeline: 16 loader warps pull 32-row stages (LDG.256, two stages ahead in registers), split into hi / lo and
-// write the swizzled tiles (3-stage ring, full / empty mbarriers); one issuer warp runs 12 MMAs per stage.
-// The kernel is bound by the shared-memory port: 8.5 KB of operand reads per M128 N144 K8 MMA = 68 cycles at
-// 128 B/cycle -- the tensor floor for this shape is 72 -- plus the tile writes.
+// (round 1: ~3000 MMAs into one accumulator drifted a gradient by 6e-5), so each plane pair (48 MMAs) goes into a
+// FRESH TMEM accumulator (double buffered) that the CUDA cores add into running sums held in REGISTERS (36 per
+// thread: TMEM is taken by the operand ring and the two accumulators) with IEEE adds; the running sums are flushed
+// per category into this CTA's partial buffer (reduced in a fixed order by k_reduce_partials: deterministic for a
+// given schedule, no atomics).
+// Pipeline: 16 worker warps fill 32-row stages (the next stage's loads are issued right after a hand-over and hit L2:
+// a second cursor prefetches two plane pairs ahead), 3-stage ring in shared memory and TMEM, full / empty mbarriers;
+// one issuer warp runs 12 MMAs per stage.
 #include "njode_wide.cuh"
 
 namespace {
@@ -26,19 +33,21 @@ __device__ unsigned g_status[2] = {0, 0};
 __device__ unsigned g_notrap = 0;
 __device__ unsigned long long g_phase3[512][8];     // `make phase`: per-CTA phase cycles of the loader role (thread 0)
 
-constexpr int NT3 = NT_W + 128;        // 16 loader / merge warps + one warpgroup whose first warp issues the MMAs (setmaxnreg: 104 / 56 registers)
+constexpr int NT3 = NT_W + 128;        // 16 loader / merge warps + one warpgroup whose first warp issues the MMAs (setmaxnreg: 112 / 32 registers)
 constexpr int NSTAGE3 = 3;
 constexpr int SROWS = 32;              // rows (K) per stage
 constexpr int BLK = SROWS * 128;       // bytes of one 32-feature block of a stage tile
-constexpr uint32_t FRESH0 = 0, FRESH1 = 160, RUN = 320, TMEM3 = 512;
+// TMEM columns: operand ring (per stage 32 columns hi + 32 lo: 32 rows of the stage), then the two fresh accumulators
+constexpr uint32_t A_RING = 0, FRESH0 = 192, FRESH1 = 352, TMEM3 = 512;
+__host__ __device__ constexpr uint32_t a_hi_col(uint32_t stage) { return A_RING + 64u * stage; }
+__host__ __device__ constexpr uint32_t a_lo_col(uint32_t stage) { return A_RING + 64u * stage + 32u; }
 
 enum { CAT_ODE = 0, CAT_OUT, CAT_READOUT, CAT_JUMP, CAT_JUMP0 };
 
 template <int HW>
 struct G3 {
   static constexpr int NB = HW / 32;                       // 32-feature blocks per operand
-  static constexpr int P_HI = 0, P_LO = NB * BLK, Q_HI = 2 * NB * BLK, X_HI = Q_HI + NB * BLK,
-                       Q_LO = X_HI + BLK, X_LO = Q_LO + NB * BLK, STAGE = X_LO + BLK;
+  static constexpr int Q_HI = 0, X_HI = NB * BLK, Q_LO = X_HI + BLK, X_LO = Q_LO + NB * BLK, STAGE = X_LO + BLK;
   static constexpr int NACC = HW + 16;                     // accumulator columns (in-features + aux block)
   static constexpr int CPT = NACC / 4;                     // columns per merge thread (4 column groups)
   static constexpr int NLOAD = HW / 8;                     // loader warps (one 8-column chunk each)
@@ -106,7 +115,7 @@ __device__ __forceinline__ void cursor_planes(const Cursor& cu, int L, int& p_sl
       p_slot = x_slot = X; p_plane = l;
       if (l == 0) { q_slot = cu.inst == 0 ? 0 : cu.kmax; q_plane = 0; } else { q_slot = X; q_plane = l; }
       break;
-    case CAT_READOUT: p_slot = x_slot = X; p_plane = L; p_from_d = false; has_q = false; q_slot = q_plane = 0; break;
+    case CAT_READOUT: p_slot = x_slot = X; p_plane = L; has_q = false; q_slot = q_plane = 0; break;   // (half D, plane L: the forward sweep's feature-major copy of the last hidden layer)
     case CAT_JUMP: p_slot = q_slot = x_slot = X3; p_plane = l; q_plane = l - 1; break;
     default: p_slot = x_slot = X3; p_plane = 0; has_q = false; q_slot = q_plane = 0; break;
   }
@@ -137,9 +146,9 @@ __device__ __forceinline__ void wg_issuer(const SweepArgs& a, uint8_t* raw) {
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&ctl.tmem_base);
   const uint32_t ring_s = umma::smem_u32(ring);
   // M = 128 also at H = 64: same tensor time as M = 64 (the floor is max(M, 128) * N / 256 cycles), standard accumulator
-  // layout (row = lane); the A descriptor then runs two blocks past the D tile into the neighbouring (finite) tiles of
-  // the stage, whose products land in accumulator rows 64..127 that nobody reads
-  constexpr uint32_t idesc_q = umma::idesc_tf32(128, G::NACC, 1, 1), idesc_x = umma::idesc_tf32(128, 16, 1, 1);
+  // layout (row = lane); TMEM lanes 64..127 of the operand ring then hold zeros and accumulator rows 64..127 are unused.
+  // A from TMEM (lane = output feature, column = row of the stage), B MN-major from shared memory.
+  constexpr uint32_t idesc_q = umma::idesc_tf32(128, G::NACC, 0, 1), idesc_x = umma::idesc_tf32(128, 16, 0, 1);
   Cursor cu;
   cursor_init(cu, a, wi, n_w);
   const int L = a.T.L;
@@ -159,15 +168,15 @@ __device__ __forceinline__ void wg_issuer(const SweepArgs& a, uint8_t* raw) {
       umma::fence_after_sync();
       if (umma::elect_one()) {
         const uint32_t sb = ring_s + stage * G::STAGE;
-        const uint64_t p_hi = umma::desc_mn(sb + G::P_HI, BLK), p_lo = umma::desc_mn(sb + G::P_LO, BLK);
+        const uint32_t p_hi = tmem + a_hi_col(stage), p_lo = tmem + a_lo_col(stage);
         const uint64_t q_hi = umma::desc_mn(sb + (has_q ? G::Q_HI : G::X_HI), BLK), q_lo = umma::desc_mn(sb + (has_q ? G::Q_LO : G::X_LO), BLK);
         const uint32_t idesc = has_q ? idesc_q : idesc_x;
 #pragma unroll
-        for (int ks = 0; ks < SROWS / 8; ++ks) umma::mma_ss(acc, p_lo + 64 * ks, q_hi + 64 * ks, idesc, (qs > 0 || ks > 0) ? 1u : 0u);
+        for (int ks = 0; ks < SROWS / 8; ++ks) umma::mma_ts(acc, p_lo + 8 * ks, q_hi + 64 * ks, idesc, (qs > 0 || ks > 0) ? 1u : 0u);
 #pragma unroll
-        for (int ks = 0; ks < SROWS / 8; ++ks) umma::mma_ss(acc, p_hi + 64 * ks, q_lo + 64 * ks, idesc, 1u);
+        for (int ks = 0; ks < SROWS / 8; ++ks) umma::mma_ts(acc, p_hi + 8 * ks, q_lo + 64 * ks, idesc, 1u);
 #pragma unroll
-        for (int ks = 0; ks < SROWS / 8; ++ks) umma::mma_ss(acc, p_hi + 64 * ks, q_hi + 64 * ks, idesc, 1u);
+        for (int ks = 0; ks < SROWS / 8; ++ks) umma::mma_ts(acc, p_hi + 8 * ks, q_hi + 64 * ks, idesc, 1u);
         umma::commit(&ctl.empty[stage]);
         if (qs == R / SROWS - 1) umma::commit(&ctl.fresh_done[b]);
       }
@@ -191,7 +200,7 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* raw) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = warp & 3, cg = warp >> 2;
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&ctl.tmem_base);
-  const uint32_t my_t = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * G::CPT);     // this thread's accumulator cells
+  const uint32_t quad_t = tmem + ((uint32_t)(q * 32) << 16);                  // this warp's TMEM lane quadrant, column 0
   const uint32_t ring_s = umma::smem_u32(ring);
   const int64_t PL = Cfg<HW>::PL, slotf = (int64_t)(L + 1) * PL;
   const int64_t half = (int64_t)S * a.total_slots * slotf;
@@ -199,48 +208,36 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* raw) {
   const float* const baseD = baseA + half;
   const float* const baseX = a.ckpt + 2 * half + (int64_t)s * a.total_slots * (R * 8);
   float* const part = a.partials + (int64_t)blockIdx.x * T.stack_floats;
-  const bool loader = warp < G::NLOAD;
+  const bool q_loader = warp < G::NLOAD;            // this warp stages one 8-column chunk of the B operand (lane = row)
+  const int irow = q * 32 + lane;                   // this thread's output feature = its TMEM lane
+  const bool has_row = irow < HW;                   // (at H = 64 lanes 64..127 hold nothing)
   const int sc_kind = a.desc.input_scaling;
   const float comp = a.comp_wgrad;
   Diag dg{g_status, g_notrap, 16u, false};
 
-  // accumulator row (output feature) of this thread = its TMEM lane; at H = 64 lanes 64..127 hold nothing useful
-  const int irow = q * 32 + lane;
-  const bool has_row = irow < HW;
-
-  auto zero_run = [&]() {
-    uint32_t z[4] = {0u, 0u, 0u, 0u};
+  // running sums of the current category: accumulator row irow, columns [cg * CPT, +CPT)
+  float run[G::CPT];
 #pragma unroll
-    for (int t = 0; t < G::CPT; t += 4)
-      asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(my_t + RUN + t), "r"(z[0]), "r"(z[1]), "r"(z[2]), "r"(z[3]) : "memory");
-    umma::wait_st();
-  };
+  for (int t = 0; t < G::CPT; ++t) run[t] = 0.0f;
   auto ld4 = [&](uint32_t addr, float (&v)[4]) {
     uint32_t u0, u1, u2, u3;
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3) : "r"(addr));
     v[0] = __uint_as_float(u0); v[1] = __uint_as_float(u1); v[2] = __uint_as_float(u2); v[3] = __uint_as_float(u3);
   };
-  auto st4 = [&](uint32_t addr, const float (&v)[4]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
-                 :: "r"(addr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])) : "memory");
-  };
-  // running += fresh[b]  (IEEE adds), then release the fresh accumulator
+  // running += fresh[b]  (IEEE adds; comp: accumulator truncation compensation), then release the fresh accumulator
   auto merge = [&](uint32_t ic) {
     const uint32_t b = ic & 1u;
     wait_or_die(&ctl.fresh_done[b], (ic >> 1) & 1u, dg, 7);
     umma::fence_after_sync();
-    const uint32_t fr = my_t + (b ? FRESH1 : FRESH0);
+    const uint32_t fr = quad_t + (b ? FRESH1 : FRESH0) + (uint32_t)(cg * G::CPT);
 #pragma unroll
     for (int t = 0; t < G::CPT; t += 4) {
-      float f[4], r4[4];
+      float f[4];
       ld4(fr + t, f);
-      ld4(my_t + RUN + t, r4);
       umma::wait_ld();
 #pragma unroll
-      for (int i = 0; i < 4; ++i) r4[i] = fmaf(f[i], comp, r4[i]);      // (comp: accumulator truncation compensation)
-      st4(my_t + RUN + t, r4);
+      for (int i = 0; i < 4; ++i) run[t + i] = fmaf(f[i], comp, run[t + i]);
     }
-    umma::wait_st();
     umma::fence_before_sync();
     __syncwarp();
     if (lane == 0) umma::mbar_arrive(&ctl.merged[b]);
@@ -254,29 +251,22 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* raw) {
       const int net = kind == CAT_ODE ? NET_ODE : (kind == CAT_OUT || kind == CAT_READOUT) ? NET_OUT : NET_JUMP;
       const int ld = T.n_vec[net][l] + T.n_ext[net][l];
 #pragma unroll
-      for (int t = 0; t < G::CPT; t += 4) {
-        float v[4];
-        ld4(my_t + RUN + t, v);
-        umma::wait_ld();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int n = cg * G::CPT + t + i;
-          if (kind == CAT_READOUT) {
-            if (n >= 1 && n <= O) part[T.w_off[NET_OUT][L] + (n - 1) * HW + irow] = v[i];
-          } else if (kind == CAT_JUMP0) {
-            if (n == 0) part[T.b_off[NET_JUMP][0] + irow] = v[i];
-            else if (n <= dx) part[T.w_off[NET_JUMP][0] + irow * dx + (n - 1)] = v[i];
-          } else if (n < HW) {
-            part[T.w_off[net][l] + irow * ld + n] = v[i];
-          } else if (n == HW) {
-            part[T.b_off[net][l] + irow] = v[i];
-          } else if (kind == CAT_ODE && l == 0 && n - HW - 1 < dx + 2) {
-            part[T.w_off[net][l] + irow * ld + HW + (n - HW - 1)] = v[i];
-          }
+      for (int t = 0; t < G::CPT; ++t) {
+        const int n = cg * G::CPT + t;
+        const float v = run[t];
+        if (kind == CAT_READOUT) {
+          if (n >= 1 && n <= O) part[T.w_off[NET_OUT][L] + (n - 1) * HW + irow] = v;
+        } else if (kind == CAT_JUMP0) {
+          if (n == 0) part[T.b_off[NET_JUMP][0] + irow] = v;
+          else if (n <= dx) part[T.w_off[NET_JUMP][0] + irow * dx + (n - 1)] = v;
+        } else if (n < HW) {
+          part[T.w_off[net][l] + irow * ld + n] = v;
+        } else if (n == HW) {
+          part[T.b_off[net][l] + irow] = v;
+        } else if (kind == CAT_ODE && l == 0 && n - HW - 1 < dx + 2) {
+          part[T.w_off[net][l] + irow * ld + HW + (n - HW - 1)] = v;
         }
       }
-    } else {
-      umma::wait_ld();
     }
     if (kind == CAT_READOUT && warp == 0) {
 #pragma unroll
@@ -286,36 +276,40 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* raw) {
         if (lane == 0 && o < O) part[T.b_off[NET_OUT][L] + o] = v;
       }
     }
-    zero_run();
+#pragma unroll
+    for (int t = 0; t < G::CPT; ++t) run[t] = 0.0f;
   };
 
-  // everything the MMAs may read must be finite: clear the ring (aux columns 8..15 stay zero for good) and TMEM
+  // everything the MMAs may read must be finite: clear the shared-memory ring (aux columns 8..15 stay zero for good),
+  // the TMEM operand ring (lanes of features >= H are never written again) and both accumulators
   for (int i = threadIdx.x; i < NSTAGE3 * G::STAGE / 16; i += NT_W) reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   {
-    uint32_t z[4] = {0u, 0u, 0u, 0u};
-    for (uint32_t c = 0; c < (uint32_t)G::CPT; c += 4) {
-      asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(my_t + FRESH0 + c), "r"(z[0]), "r"(z[1]), "r"(z[2]), "r"(z[3]) : "memory");
-      asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(my_t + FRESH1 + c), "r"(z[0]), "r"(z[1]), "r"(z[2]), "r"(z[3]) : "memory");
-    }
-    zero_run();
+    uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    for (uint32_t c = (uint32_t)cg * 8; c < TMEM3; c += 32) umma::tmem_st8_raw(quad_t + c, z);      // the 4 warps of a quadrant interleave
+    umma::wait_st();
   }
   umma::fence_async_smem();
+  umma::fence_before_sync();
   umma::named_bar_sync(1, NT_W);
+  umma::fence_after_sync();
 
   // ---- the stage loop ----
   // The hand-over fence (fence.proxy.async = MEMBAR.ALL.CTA) waits for every load this thread has in flight, so a
-  // register load must land within ONE stage time (~1400 cycles): fine from L2, not from HBM (first capture of this
-  // kernel: a stage took an HBM round trip, 3160 cycles, tensor pipe 27 % active).  So: the loads of stage n+1 are
-  // issued right after the hand-over of stage n, and a second cursor runs PF_AHEAD plane pairs in front pulling the
-  // planes into L2 with prefetch.global.L2 (no destination register, nothing for the fence to wait for).
+  // register load must land within ONE stage time: fine from L2, not from HBM (first capture of this kernel: a stage
+  // took an HBM round trip, 3160 cycles, tensor pipe 27 % active).  So: the loads of stage n+1 are issued right after
+  // the hand-over of stage n, and a second cursor runs PF_AHEAD plane pairs in front pulling the planes into L2 with
+  // prefetch.global.L2 (no destination register, nothing for the fence to wait for).
   constexpr int PF_AHEAD = 2;            // plane pairs (= 8 stages)
   struct Src { const float* p; const float* q; const float* x; bool has_q; };
   auto source = [&](const Cursor& cu) {
     int ps, pp, qsl, qp, xs;
     bool pd, hq;
     cursor_planes(cu, L, ps, pp, pd, qsl, qp, hq, xs);
+    (void)pd;                                                       // every P plane is a feature-major plane of half D
     Src sr;
-    sr.p = (pd ? baseD : baseA) + ((int64_t)(cu.so + ps) * (L + 1) + pp) * PL + ((int64_t)warp * R + lane) * 8;
+    // P: half-D plane [row octet][feature][8 rows]: this thread's feature, row octet cg of a stage (4 octets per stage)
+    sr.p = baseD + ((int64_t)(cu.so + ps) * (L + 1) + pp) * PL + (int64_t)cg * (HW * 8) + irow * 8;
+    // Q: chunk-major [chunk][row][8]: chunk = warp, row = lane within the stage
     sr.q = baseA + ((int64_t)(cu.so + qsl) * (L + 1) + qp) * PL + ((int64_t)warp * R + lane) * 8;
     sr.x = baseX + ((int64_t)(cu.so + xs) * R + lane) * 8;
     sr.has_q = hq;
@@ -323,17 +317,13 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* raw) {
   };
   float p[8], qv[8], x[8];
   auto issue_loads = [&](const Src& sr, int qs) {
-    if (loader) {
-      ld8g(sr.p + qs * (SROWS * 8), p);
-      if (sr.has_q) ld8g(sr.q + qs * (SROWS * 8), qv);
-    }
+    if (has_row) ld8g(sr.p + qs * (SROWS * HW), p);
+    if (q_loader && sr.has_q) ld8g(sr.q + qs * (SROWS * 8), qv);
     if (warp == 0) ld8g(sr.x + qs * (SROWS * 8), x);
   };
   auto issue_prefetch = [&](const Src& sr, int qs) {
-    if (loader) {
-      prefetch_l2(sr.p + qs * (SROWS * 8));
-      if (sr.has_q) prefetch_l2(sr.q + qs * (SROWS * 8));
-    }
+    if (has_row) prefetch_l2(sr.p + qs * (SROWS * HW));
+    if (q_loader && sr.has_q) prefetch_l2(sr.q + qs * (SROWS * 8));
     if (warp == 0) prefetch_l2(sr.x + qs * (SROWS * 8));
   };
   Cursor cur, pf;
@@ -370,20 +360,20 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* raw) {
       PH(1);                                                       // waiting for a free stage (MMA side is behind)
       const uint32_t sb = ring_s + stage * G::STAGE;
       uint32_t hi[8], lo[8];
-      if (loader) {
-        const uint32_t boff = (uint32_t)(warp >> 2) * BLK;
+      if (has_row) {                                               // A operand: 8 rows of this feature -> TMEM
         umma::split8(p, hi, lo);
-        umma::chunk_to_mn_tile(sb + G::P_HI + boff, lane, warp & 3, hi);
-        umma::chunk_to_mn_tile(sb + G::P_LO + boff, lane, warp & 3, lo);
-        if (has_q) {
-          if (scale_q) {
+        umma::tmem_st8_raw(quad_t + a_hi_col(stage) + 8 * cg, hi);
+        umma::tmem_st8_raw(quad_t + a_lo_col(stage) + 8 * cg, lo);
+      }
+      if (q_loader && has_q) {                                     // B operand: one 8-column chunk of 32 rows -> MN-major tiles
+        const uint32_t boff = (uint32_t)(warp >> 2) * BLK;
+        if (scale_q) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) qv[i] = scale_fwd_rt(sc_kind, qv[i]);
-          }
-          umma::split8(qv, hi, lo);
-          umma::chunk_to_mn_tile(sb + G::Q_HI + boff, lane, warp & 3, hi);
-          umma::chunk_to_mn_tile(sb + G::Q_LO + boff, lane, warp & 3, lo);
+          for (int i = 0; i < 8; ++i) qv[i] = scale_fwd_rt(sc_kind, qv[i]);
         }
+        umma::split8(qv, hi, lo);
+        umma::chunk_to_mn_tile(sb + G::Q_HI + boff, lane, warp & 3, hi);
+        umma::chunk_to_mn_tile(sb + G::Q_LO + boff, lane, warp & 3, lo);
       }
       if (warp == 0) {
         umma::split8(x, hi, lo);
@@ -394,11 +384,13 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* raw) {
           for (int o = 0; o < MAX_O; ++o) dbo[o] += x[1 + o];
         }
       }
-      PH(2);                                                       // split + tile stores (incl. waiting for the register loads)
+      PH(2);                                                       // split + stores (incl. waiting for the register loads)
+      umma::wait_st();
+      umma::fence_before_sync();
       umma::fence_async_smem();
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&ctl.full[stage]);
-      PH(3);                                                       // proxy fence + hand-over
+      PH(3);                                                       // fences + hand-over
       // the next stage's loads (next plane pair after the last stage of this one), and the L2 prefetch far ahead
       if (qs + 1 < R / SROWS) {
         issue_loads(src, qs + 1);
@@ -442,10 +434,10 @@ __global__ void __launch_bounds__(NT3, 1) k_wide_wgrad(SweepArgs a) {
     umma::fence_after_sync();
   }
   if (warp < NWARP_W) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     wg_worker<HW>(a, smem_raw);
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == NWARP_W) wg_issuer<HW>(a, smem_raw);
   }
   umma::fence_before_sync();

@@ -326,6 +326,8 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
     const int kmax = a.tile_kmax[tile];
     const int u = a.perm[tile * R + row];
     float* const ck = ckpt_s ? ckpt_s + a.tile_slot_off[tile] * slotf : nullptr;
+    float* const ckd = a.ckpt ? a.ckpt + ((int64_t)T.S * a.total_slots + (int64_t)s * a.total_slots + a.tile_slot_off[tile]) * slotf +
+                                    dplane_off(HW, col0, row) : nullptr;       // half D, this thread's (first feature, row)
     // plane `pl` of slot `sl`, this thread's sub-chunk j
     auto cp = [&](int sl, int pl, int j) { return ck + ((int64_t)sl * (L + 1) + pl) * PL + j * (R * 8); };
     const float* const kn = a.knots + a.tile_slot_off[tile] * R + row;
@@ -394,7 +396,12 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) z[i] = act_fwd<ACT>(z[i] + cb[i]);
           if (l < L - 1) w.emit(j, z);
-          if (ck) st8g(cp(X, l + 1, j), z);
+          if (ck) {
+            st8g(cp(X, l + 1, j), z);
+            // the readout layer's weight gradient contracts THIS activation with dY: the weight-gradient GEMM wants it as
+            // its TMEM (feature-major) operand, so a second copy goes to half D, plane L of the slot
+            if (l == L - 1) st8t(ckd + ((int64_t)X * (L + 1) + L) * PL + j * 64, z);
+          }
           if (l < L - 1) {
           } else {
 #pragma unroll
@@ -539,9 +546,11 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
     const int u = a.perm[tile * R + row];
     const int ke = u >= 0 ? a.kenc[u] : 0;
     const float* const ca = a.ckpt + toff + a.tile_slot_off[tile] * slotf;       // activations (read)
-    float* const cd = a.ckpt + half + toff + a.tile_slot_off[tile] * slotf;      // d planes (written)
+    float* const cd = a.ckpt + half + (int64_t)s * a.total_slots * slotf + a.tile_slot_off[tile] * slotf +
+                      dplane_off(HW, col0, row);                              // d planes (written; layout: njode_wide.cuh)
     auto pa = [&](int sl, int pl, int j) { return ca + ((int64_t)sl * (L + 1) + pl) * PL + j * (R * 8); };
-    auto pd = [&](int sl, int pl, int j) { return cd + ((int64_t)sl * (L + 1) + pl) * PL + j * (R * 8); };
+    // (half D planes are [row octet][feature][8 rows]: this thread's (first feature of sub-chunk j, row))
+    auto pd = [&](int sl, int pl, int j) { return cd + ((int64_t)sl * (L + 1) + pl) * PL + j * 64; };
     // aux rows of a slot (8 floats per row, written by the column-group-0 thread of the row): the extra B columns of
     // the weight-gradient GEMM -- (1, s(x).., t, dt) for an Euler step, (1, dY..) for a readout, (1, x..) for the jump
     float* const cx = a.ckpt + 2 * half + ((int64_t)s * a.total_slots + a.tile_slot_off[tile]) * (R * 8) + row * 8;
@@ -575,7 +584,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] *= act_grad_from_out<ACT>(zb[8 * j + i]);
         if (emit_next) w.emit(j, acc);
-        st8g(ddst + j * (R * 8), acc);     // (after the hand-over: its release-arrive waits for earlier global stores)
+        st8t(ddst + j * 64, acc);
       }
       w.done();
     };
@@ -610,7 +619,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) d[i] *= act_grad_from_out<ACT>(z[i]);
         w.emit(j, d);                                            // -> d * W_out[L-1]
-        st8g(pd(X, L - 1, j), d);
+        st8t(pd(X, L - 1, j), d);
       }
       for (int l = L - 1; l >= 1; --l) chain_layer(pa(X, l, 0), pd(X, l - 1, 0), true);      // -> d * W_out[l-1]
       WAIT_ACC();                                              // d * W_out[0] = d loss / d h through this readout
@@ -641,7 +650,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) d[i] = delta * gr[8 * j + i];
         w.emit(j, d);                                            // -> d * W_ode[L]
-        st8g(pd(kmax - 1, L, j), d);
+        st8t(pd(kmax - 1, L, j), d);
       }
     }
     for (int k = kmax - 1; k >= 0; --k) {
@@ -676,7 +685,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) d[i] = delta_prev * gr[8 * j + i];
           w.emit(j, d);
-          st8g(pd(k - 1, L, j), d);
+          st8t(pd(k - 1, L, j), d);
         }
       }
       w.done();
@@ -699,7 +708,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) d[i] = gr[8 * j + i] * act_grad_from_out<ACT>(h0[8 * j + i]);
       w.emit(j, d);                                              // -> d * W_jump[L]
-      st8g(pd(X3, L, j), d);
+      st8t(pd(X3, L, j), d);
     }
     for (int l = L; l >= 1; --l) chain_layer(pa(X3, l - 1, 0), pd(X3, l - 1, 0), l > 1);      // -> d * W_jump[l-1]
   }

@@ -11,10 +11,18 @@
 //                    plane l = output of ODE layer l-1
 //   slot X1 = kmax+1 (readout at h_0), X2 = kmax+2 (readout at h_end):
 //                    plane l (1..L) = output of out-net       plane l (0..L-1) = d / d (pre-activation of
-//                    layer l-1                                out-net layer l)
+//                    layer l-1                                out-net layer l); plane L = a copy of half A's
+//                                                             plane L (written by the FORWARD sweep)
 //   slot X3 = kmax+3 (jump net): plane l (0..L-1) = output    plane l (0..L) = d / d (pre-activation of jump
 //                    of jump layer l                          layer l)
-// The weight-gradient kernel contracts pairs (D plane, A plane) over rows; see njode_wgrad.cu.
+// The planes of half D are laid out for the weight-gradient kernel (njode_wgrad.cu), which contracts pairs (D plane,
+// A plane) over rows with the D plane as its TMEM operand, lane = feature, 8 rows per thread and stage:
+//     [16 row octets][H features][8 rows]
+// so that a warp there (32 features, one octet) reads 1 KB contiguous.  (A plain [feature][row] layout made each of its
+// LDG.256 touch 32 different lines, and the LSU time of those -- 80 wavefronts per warp and stage -- ate what taking
+// the operand out of shared memory had saved.)  A row worker of the sweeps owns (row, 8 features): 8 scalar stores,
+// each 4 x 32 contiguous bytes across the warp's 32 rows.
+// A third region holds 8 aux floats per row and slot (the extra B columns of that GEMM).
 #pragma once
 #include <cstdlib>
 
@@ -62,6 +70,13 @@ __device__ __forceinline__ void st8g(float* __restrict__ dst, const float (&v)[8
   asm volatile("st.global.v8.f32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
                :: "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "l"(dst) : "memory");
 }
+// 8 consecutive features of one row into a half-D plane ([row octet][feature][8 rows]); dst points at (first feature, row)
+__device__ __forceinline__ void st8t(float* __restrict__ dst, const float (&v)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) asm volatile("st.global.f32 [%0], %1;" :: "l"(dst + i * 8), "f"(v[i]) : "memory");
+}
+// offset of (feature f, row r) inside a half-D plane of width HW
+__host__ __device__ __forceinline__ int dplane_off(int HW, int f, int r) { return (r >> 3) * (HW * 8) + f * 8 + (r & 7); }
 __device__ __forceinline__ float ldg_na(const float* __restrict__ p) {
   float v;
   asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));

@@ -98,13 +98,15 @@ def golden_main(name):
     PL = 128 * H
     halfA = S * slots_w * (L + 1) * PL
     A = r["ckpt"][:halfA].reshape(S, slots_w, L + 1, H // 8, 128, 8)
-    D = r["ckpt"][halfA:2 * halfA].reshape(S, slots_w, L + 1, H // 8, 128, 8)
+    D = r["ckpt"][halfA:2 * halfA].reshape(S, slots_w, L + 1, 16, H, 8)                     # half D: [row octet][feature][8 rows]
     X = r["ckpt"][2 * halfA:2 * halfA + S * slots_w * 128 * 8].reshape(S, slots_w, 128, 8)
     kmax_w = sw.tile_kmax.cpu().numpy()
     so_w = sw.tile_slot_off.cpu().numpy()
     print("  tiles", sw.n_tiles, "kmax", kmax_w.tolist())
 
     def plane(buf, s, slot, pl):
+        if buf is D:
+            return buf[s, slot, pl].transpose(0, 2, 1).reshape(128, H).astype(np.float64)
         return buf[s, slot, pl].transpose(1, 0, 2).reshape(128, H).astype(np.float64)
 
     dx = mk["input_dim"]
@@ -188,12 +190,14 @@ def main():
         ok &= e <= TOL
 
     # ---- the weight-gradient GEMM against numpy contractions of its own inputs (ODE net only: the bulk) ----
-    D = got["ckpt"][halfA:2 * halfA].reshape(S, slots_w, L + 1, H // 8, 128, 8)
+    D = got["ckpt"][halfA:2 * halfA].reshape(S, slots_w, L + 1, 16, H, 8)                   # half D: [row octet][feature][8 rows]
     X = got["ckpt"][2 * halfA:2 * halfA + S * slots_w * 128 * 8].reshape(S, slots_w, 128, 8)
     kmax_w = sw.tile_kmax.cpu().numpy()
 
-    def plane(buf, s, slot, pl):
-        return buf[s, slot, pl].transpose(1, 0, 2).reshape(128, H).astype(np.float64)      # [row][feature]
+    def plane(buf, s, slot, pl):                                                            # -> [row][feature]
+        if buf is D:
+            return buf[s, slot, pl].transpose(0, 2, 1).reshape(128, H).astype(np.float64)
+        return buf[s, slot, pl].transpose(1, 0, 2).reshape(128, H).astype(np.float64)
 
     keys = list(got["grads"].keys())
     for s in range(S):
