@@ -21,9 +21,13 @@
 // thread: TMEM is taken by the operand ring and the two accumulators) with IEEE adds; the running sums are flushed
 // per category into this CTA's partial buffer (reduced in a fixed order by k_reduce_partials: deterministic for a
 // given schedule, no atomics).
-// Pipeline: 16 worker warps fill 32-row stages (the next stage's loads are issued right after a hand-over and hit L2:
-// a second cursor prefetches two plane pairs ahead), 3-stage ring in shared memory and TMEM, full / empty mbarriers;
-// one issuer warp runs 12 MMAs per stage.
+// Pipeline: a producer thread streams the RAW planes, three bulk copies (TMA engine) per 32-row stage, into a 3-stage
+// staging ring; 16 converter warps read a staged stage from shared memory, split it and write the operand stage (TMEM +
+// MN tiles, 3-stage ring); one issuer warp runs 12 MMAs per stage; full / empty mbarriers between all three.
+// The staging ring exists because of one instruction: the converters' hand-over needs fence.proxy.async (generic ->
+// async proxy), which is a MEMBAR that waits for every global load the thread has in flight -- with the planes loaded
+// straight into registers a stage could not take less than a memory round trip (measured: 2600 cycles per stage at
+// H = 128 against 864 of tensor time, whatever the prefetch depth).  Bulk copies have no thread-side loads.
 #include "njode_wide.cuh"
 
 namespace {
@@ -31,10 +35,11 @@ using namespace wide;
 
 __device__ unsigned g_status[2] = {0, 0};
 __device__ unsigned g_notrap = 0;
-__device__ unsigned long long g_phase3[512][8];     // `make phase`: per-CTA phase cycles of the loader role (thread 0)
+__device__ unsigned long long g_phase3[512][8];     // `make phase`: per-CTA phase cycles of the converter role (thread 0)
 
-constexpr int NT3 = NT_W + 128;        // 16 loader / merge warps + one warpgroup whose first warp issues the MMAs (setmaxnreg: 112 / 32 registers)
-constexpr int NSTAGE3 = 3;
+constexpr int NT3 = NT_W + 128;        // 16 converter / merge warps + one warpgroup: MMA issuer warp, producer warp (setmaxnreg: 112 / 32)
+constexpr int NSTAGE3 = 3;             // operand stages (TMEM ring + MN tiles)
+constexpr int NRAW = 3;                // staging stages (raw planes)
 constexpr int SROWS = 32;              // rows (K) per stage
 constexpr int BLK = SROWS * 128;       // bytes of one 32-feature block of a stage tile
 // TMEM columns: operand ring (per stage 32 columns hi + 32 lo: 32 rows of the stage), then the two fresh accumulators
@@ -50,11 +55,13 @@ struct G3 {
   static constexpr int Q_HI = 0, X_HI = NB * BLK, Q_LO = X_HI + BLK, X_LO = Q_LO + NB * BLK, STAGE = X_LO + BLK;
   static constexpr int NACC = HW + 16;                     // accumulator columns (in-features + aux block)
   static constexpr int CPT = NACC / 4;                     // columns per merge thread (4 column groups)
-  static constexpr int NLOAD = HW / 8;                     // loader warps (one 8-column chunk each)
+  static constexpr int NLOAD = HW / 8;                     // converter warps that stage one 8-column chunk of the B operand
+  // staging stage: 32 rows of the D plane ([4 octets][HW][8]), of the A plane ([HW/8 chunks][32][8]) and of the aux rows
+  static constexpr int RAW_P = 0, RAW_Q = SROWS * HW * 4, RAW_X = 2 * SROWS * HW * 4, RAW = RAW_X + SROWS * 32;
 };
 
 struct Ctl3 {
-  uint64_t full[NSTAGE3], empty[NSTAGE3], fresh_done[2], merged[2];
+  uint64_t raw_full[NRAW], raw_empty[NRAW], full[NSTAGE3], empty[NSTAGE3], fresh_done[2], merged[2];
   uint32_t tmem_base, pad;
 };
 
@@ -69,6 +76,7 @@ __device__ __forceinline__ void cat_decode(int L, int c, int& kind, int& l) {
 __device__ __forceinline__ int cat_instances(int kind, int kmax) {
   return kind == CAT_ODE ? kmax : (kind == CAT_OUT || kind == CAT_READOUT) ? 2 : 1;
 }
+__device__ __forceinline__ bool cat_has_q(int kind) { return !(kind == CAT_READOUT || kind == CAT_JUMP0); }
 
 // walks (category, tile of this CTA, instance = plane pair) in the order every role uses
 struct Cursor {
@@ -102,62 +110,103 @@ __device__ __forceinline__ void cursor_next(Cursor& cu, const SweepArgs& a, int 
   ++cu.r;
   cursor_seek(cu, a, wi, n_w);
 }
-// slots (relative to the tile's first) of the P plane, Q plane and aux rows of the cursor's instance
-__device__ __forceinline__ void cursor_planes(const Cursor& cu, int L, int& p_slot, int& p_plane, bool& p_from_d,
-                                              int& q_slot, int& q_plane, bool& has_q, int& x_slot) {
+// slots (relative to the tile's first) of the P plane (half D), the Q plane (half A) and the aux rows of the instance
+__device__ __forceinline__ void cursor_planes(const Cursor& cu, int L, int& p_slot, int& p_plane, int& q_slot, int& q_plane, int& x_slot) {
   int kind, l;
   cat_decode(L, cu.c, kind, l);
   const int X = cu.kmax + 1 + cu.inst, X3 = cu.kmax + 3;
-  p_from_d = true; has_q = true;
+  q_slot = q_plane = 0;
   switch (kind) {
     case CAT_ODE: p_slot = q_slot = x_slot = cu.inst; p_plane = q_plane = l; break;
     case CAT_OUT:
       p_slot = x_slot = X; p_plane = l;
       if (l == 0) { q_slot = cu.inst == 0 ? 0 : cu.kmax; q_plane = 0; } else { q_slot = X; q_plane = l; }
       break;
-    case CAT_READOUT: p_slot = x_slot = X; p_plane = L; has_q = false; q_slot = q_plane = 0; break;   // (half D, plane L: the forward sweep's feature-major copy of the last hidden layer)
+    case CAT_READOUT: p_slot = x_slot = X; p_plane = L; break;      // (half D, plane L: the forward sweep's copy of the last hidden layer)
     case CAT_JUMP: p_slot = q_slot = x_slot = X3; p_plane = l; q_plane = l - 1; break;
-    default: p_slot = x_slot = X3; p_plane = 0; has_q = false; q_slot = q_plane = 0; break;
+    default: p_slot = x_slot = X3; p_plane = 0; break;
+  }
+}
+
+// (ring and control block are re-derived inside each role: a pointer computed before setmaxnreg is live across the
+//  register re-allocation, gets spilled, and its re-load inside the stage loop is an L2 round trip)
+template <int HW>
+struct Carve3 {
+  uint8_t* ring;      // operand stages (MN tiles)
+  uint8_t* raw;       // staging stages
+  Ctl3* ctl;
+  __device__ __forceinline__ explicit Carve3(uint8_t* base) {
+    ring = (uint8_t*)(((uintptr_t)base + 1023) & ~(uintptr_t)1023);
+    raw = ring + (size_t)NSTAGE3 * G3<HW>::STAGE;
+    ctl = reinterpret_cast<Ctl3*>(raw + (size_t)NRAW * G3<HW>::RAW);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// producer (one thread): raw planes -> staging ring, three bulk copies per 32-row stage
+// ------------------------------------------------------------------------------------------------
+template <int HW>
+__device__ __forceinline__ void wg_producer(const SweepArgs& a, uint8_t* base) {
+  using G = G3<HW>;
+  Carve3<HW> cv(base);
+  Ctl3& ctl = *cv.ctl;
+  const int L = a.T.L, S = a.T.S;
+  const int s = blockIdx.x % S, wi = blockIdx.x / S, n_w = gridDim.x / S;
+  const int64_t PL = Cfg<HW>::PL, slotf = (int64_t)(L + 1) * PL;
+  const int64_t half = (int64_t)S * a.total_slots * slotf;
+  const float* const baseA = a.ckpt + (int64_t)s * a.total_slots * slotf;
+  const float* const baseD = baseA + half;
+  const float* const baseX = a.ckpt + 2 * half + (int64_t)s * a.total_slots * (R * 8);
+  Diag dg{g_status, g_notrap, 16u, false};
+  Cursor cu;
+  cursor_init(cu, a, wi, n_w);
+  uint32_t rc = 0;
+  while (cursor_valid(cu, L)) {
+    int kind, l, ps, pp, qsl, qp, xs;
+    cat_decode(L, cu.c, kind, l);
+    cursor_planes(cu, L, ps, pp, qsl, qp, xs);
+    const bool has_q = cat_has_q(kind);
+    const float* P = baseD + ((int64_t)(cu.so + ps) * (L + 1) + pp) * PL;
+    const float* Q = baseA + ((int64_t)(cu.so + qsl) * (L + 1) + qp) * PL;
+    const float* X = baseX + (int64_t)(cu.so + xs) * (R * 8);
+#pragma unroll 1
+    for (int qs = 0; qs < R / SROWS; ++qs, ++rc) {
+      const uint32_t rs = rc % NRAW, rround = rc / NRAW;
+      wait_or_die(&ctl.raw_empty[rs], (rround & 1u) ^ 1u, dg, 9);
+      uint8_t* dst = cv.raw + (size_t)rs * G::RAW;
+      mbar_expect_tx(&ctl.raw_full[rs], (uint32_t)(SROWS * HW * 4 * (has_q ? 2 : 1) + SROWS * 32));
+      bulk_g2s(dst + G::RAW_P, P + (int64_t)qs * (SROWS * HW), SROWS * HW * 4, &ctl.raw_full[rs]);     // 4 row octets x HW x 8
+      if (has_q) bulk_g2s(dst + G::RAW_Q, Q + (int64_t)qs * (SROWS * HW), SROWS * HW * 4, &ctl.raw_full[rs]);   // one row group: HW/8 chunks x 32 x 8
+      bulk_g2s(dst + G::RAW_X, X + (int64_t)qs * (SROWS * 8), SROWS * 32, &ctl.raw_full[rs]);
+    }
+    cursor_next(cu, a, wi, n_w);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// (ring and control block are re-derived inside each role: a pointer computed before setmaxnreg is live across the
-//  register re-allocation, gets spilled, and its re-load inside the stage loop is an L2 round trip -- round 1, and the
-//  first ncu capture of this kernel: 1 LDL.64 per stage)
+// MMA issuer (one warp)
+// ------------------------------------------------------------------------------------------------
 template <int HW>
-struct Carve3 {
-  uint8_t* ring;
-  Ctl3* ctl;
-  __device__ __forceinline__ explicit Carve3(uint8_t* raw) {
-    ring = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
-    ctl = reinterpret_cast<Ctl3*>(ring + (size_t)NSTAGE3 * G3<HW>::STAGE);
-  }
-};
-
-template <int HW>
-__device__ __forceinline__ void wg_issuer(const SweepArgs& a, uint8_t* raw) {
+__device__ __forceinline__ void wg_issuer(const SweepArgs& a, uint8_t* base) {
   using G = G3<HW>;
-  Carve3<HW> cv(raw);
-  uint8_t* const ring = cv.ring;
+  Carve3<HW> cv(base);
   Ctl3& ctl = *cv.ctl;
-  const int S = a.T.S;
+  const int S = a.T.S, L = a.T.L;
   const int wi = blockIdx.x / S, n_w = gridDim.x / S;
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&ctl.tmem_base);
-  const uint32_t ring_s = umma::smem_u32(ring);
+  const uint32_t ring_s = umma::smem_u32(cv.ring);
   // M = 128 also at H = 64: same tensor time as M = 64 (the floor is max(M, 128) * N / 256 cycles), standard accumulator
   // layout (row = lane); TMEM lanes 64..127 of the operand ring then hold zeros and accumulator rows 64..127 are unused.
   // A from TMEM (lane = output feature, column = row of the stage), B MN-major from shared memory.
   constexpr uint32_t idesc_q = umma::idesc_tf32(128, G::NACC, 0, 1), idesc_x = umma::idesc_tf32(128, 16, 0, 1);
   Cursor cu;
   cursor_init(cu, a, wi, n_w);
-  const int L = a.T.L;
   uint32_t sc = 0, ic = 0;
   Diag dg{g_status, g_notrap, 16u, false};
   while (cursor_valid(cu, L)) {
     int kind, l;
     cat_decode(L, cu.c, kind, l);
-    const bool has_q = !(kind == CAT_READOUT || kind == CAT_JUMP0);
+    const bool has_q = cat_has_q(kind);
     const uint32_t b = ic & 1u, use = ic >> 1;
     if (use > 0) wait_or_die(&ctl.merged[b], (use - 1) & 1u, dg, 5);     // the accumulator's previous content is merged
     const uint32_t acc = tmem + (b ? FRESH1 : FRESH0);
@@ -188,32 +237,36 @@ __device__ __forceinline__ void wg_issuer(const SweepArgs& a, uint8_t* raw) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// converters (16 warps): staged raw stage -> tf32 hi / lo operand stage; merge of finished accumulators; flush
+// ------------------------------------------------------------------------------------------------
 template <int HW>
-__device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* raw) {
+__device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* base) {
   using G = G3<HW>;
-  Carve3<HW> cv(raw);
-  uint8_t* const ring = cv.ring;
-  Ctl3& ctl = *cv.ctl;
   const ParamTable& T = a.T;
   const int L = T.L, S = T.S, dx = T.d_x, O = T.O;
-  const int s = blockIdx.x % S, wi = blockIdx.x / S, n_w = gridDim.x / S;
+  const int wi = blockIdx.x / S, n_w = gridDim.x / S;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = warp & 3, cg = warp >> 2;
-  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&ctl.tmem_base);
+  // shared-window (32-bit) addresses of the rings and the barriers (same carve as Carve3)
+  const uint32_t ring_s = (smem_u32_once(base) + 1023u) & ~1023u;
+  const uint32_t raw_s = ring_s + NSTAGE3 * G::STAGE, ctl_s = raw_s + NRAW * G::RAW;
+  const uint32_t b_raw_full = ctl_s + offsetof(Ctl3, raw_full), b_raw_empty = ctl_s + offsetof(Ctl3, raw_empty);
+  const uint32_t b_full = ctl_s + offsetof(Ctl3, full), b_empty = ctl_s + offsetof(Ctl3, empty);
+  const uint32_t b_fresh = ctl_s + offsetof(Ctl3, fresh_done), b_merged = ctl_s + offsetof(Ctl3, merged);
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(ctl_s + (uint32_t)offsetof(Ctl3, tmem_base)));
   const uint32_t quad_t = tmem + ((uint32_t)(q * 32) << 16);                  // this warp's TMEM lane quadrant, column 0
-  const uint32_t ring_s = umma::smem_u32(ring);
-  const int64_t PL = Cfg<HW>::PL, slotf = (int64_t)(L + 1) * PL;
-  const int64_t half = (int64_t)S * a.total_slots * slotf;
-  const float* const baseA = a.ckpt + (int64_t)s * a.total_slots * slotf;
-  const float* const baseD = baseA + half;
-  const float* const baseX = a.ckpt + 2 * half + (int64_t)s * a.total_slots * (R * 8);
   float* const part = a.partials + (int64_t)blockIdx.x * T.stack_floats;
-  const bool q_loader = warp < G::NLOAD;            // this warp stages one 8-column chunk of the B operand (lane = row)
+  const bool q_loader = warp < G::NLOAD;            // this warp converts one 8-column chunk of the B operand (lane = row)
   const int irow = q * 32 + lane;                   // this thread's output feature = its TMEM lane
   const bool has_row = irow < HW;                   // (at H = 64 lanes 64..127 hold nothing)
   const int sc_kind = a.desc.input_scaling;
   const float comp = a.comp_wgrad;
   Diag dg{g_status, g_notrap, 16u, false};
+  // this thread's pieces of a staging stage
+  const uint32_t rawP = raw_s + G::RAW_P + (uint32_t)(cg * HW + irow) * 32u;        // [octet cg][feature][8 rows]
+  const uint32_t rawQ = raw_s + G::RAW_Q + (uint32_t)(warp * 32 + lane) * 32u;      // [chunk = warp][row][8]
+  const uint32_t rawX = raw_s + G::RAW_X + (uint32_t)lane * 32u;
 
   // running sums of the current category: accumulator row irow, columns [cg * CPT, +CPT)
   float run[G::CPT];
@@ -227,22 +280,32 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* raw) {
   // running += fresh[b]  (IEEE adds; comp: accumulator truncation compensation), then release the fresh accumulator
   auto merge = [&](uint32_t ic) {
     const uint32_t b = ic & 1u;
-    wait_or_die(&ctl.fresh_done[b], (ic >> 1) & 1u, dg, 7);
+    wait_or_die_a(b_fresh + 8u * b, (ic >> 1) & 1u, dg, 7);
     umma::fence_after_sync();
     const uint32_t fr = quad_t + (b ? FRESH1 : FRESH0) + (uint32_t)(cg * G::CPT);
+    constexpr int MB = 12;               // columns per batch of TMEM loads (one wait per batch: the loads' latencies overlap)
 #pragma unroll
-    for (int t = 0; t < G::CPT; t += 4) {
-      float f[4];
-      ld4(fr + t, f);
+    for (int t0 = 0; t0 < G::CPT; t0 += MB) {
+      float f[MB];
+#pragma unroll
+      for (int t = 0; t < MB; t += 4) {
+        if (t0 + t < G::CPT) {
+          float g[4];
+          ld4(fr + t0 + t, g);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) f[t + i] = g[i];
+        }
+      }
       umma::wait_ld();
 #pragma unroll
-      for (int i = 0; i < 4; ++i) run[t + i] = fmaf(f[i], comp, run[t + i]);
+      for (int t = 0; t < MB; ++t)
+        if (t0 + t < G::CPT) run[t0 + t] = fmaf(f[t], comp, run[t0 + t]);
     }
     umma::fence_before_sync();
     __syncwarp();
-    if (lane == 0) umma::mbar_arrive(&ctl.merged[b]);
+    if (lane == 0) mbar_arrive_a(b_merged + 8u * b);
   };
-  float dbo[MAX_O];                      // readout bias gradient: sum over rows of dY (aux loader warp, lane = row % 32)
+  float dbo[MAX_O];                      // readout bias gradient: sum over rows of dY (aux converter warp, lane = row % 32)
 #pragma unroll
   for (int o = 0; o < MAX_O; ++o) dbo[o] = 0.0f;
   // running sums of category (kind, l) -> this CTA's partial buffer (PyTorch layout), then clear them
@@ -280,9 +343,9 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* raw) {
     for (int t = 0; t < G::CPT; ++t) run[t] = 0.0f;
   };
 
-  // everything the MMAs may read must be finite: clear the shared-memory ring (aux columns 8..15 stay zero for good),
-  // the TMEM operand ring (lanes of features >= H are never written again) and both accumulators
-  for (int i = threadIdx.x; i < NSTAGE3 * G::STAGE / 16; i += NT_W) reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // everything the MMAs may read must be finite: clear the operand tiles (aux columns 8..15 stay zero for good), the
+  // TMEM operand ring (lanes of features >= H are never written again) and both accumulators
+  for (uint32_t i = threadIdx.x; i < (uint32_t)(NSTAGE3 * G::STAGE / 16); i += NT_W) umma::st_shared_v4(ring_s + 16u * i, 0u, 0u, 0u, 0u);
   {
     uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
     for (uint32_t c = (uint32_t)cg * 8; c < TMEM3; c += 32) umma::tmem_st8_raw(quad_t + c, z);      // the 4 warps of a quadrant interleave
@@ -293,51 +356,8 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* raw) {
   umma::named_bar_sync(1, NT_W);
   umma::fence_after_sync();
 
-  // ---- the stage loop ----
-  // The hand-over fence (fence.proxy.async = MEMBAR.ALL.CTA) waits for every load this thread has in flight, so a
-  // register load must land within ONE stage time: fine from L2, not from HBM (first capture of this kernel: a stage
-  // took an HBM round trip, 3160 cycles, tensor pipe 27 % active).  So: the loads of stage n+1 are issued right after
-  // the hand-over of stage n, and a second cursor runs PF_AHEAD plane pairs in front pulling the planes into L2 with
-  // prefetch.global.L2 (no destination register, nothing for the fence to wait for).
-  constexpr int PF_AHEAD = 2;            // plane pairs (= 8 stages)
-  struct Src { const float* p; const float* q; const float* x; bool has_q; };
-  auto source = [&](const Cursor& cu) {
-    int ps, pp, qsl, qp, xs;
-    bool pd, hq;
-    cursor_planes(cu, L, ps, pp, pd, qsl, qp, hq, xs);
-    (void)pd;                                                       // every P plane is a feature-major plane of half D
-    Src sr;
-    // P: half-D plane [row octet][feature][8 rows]: this thread's feature, row octet cg of a stage (4 octets per stage)
-    sr.p = baseD + ((int64_t)(cu.so + ps) * (L + 1) + pp) * PL + (int64_t)cg * (HW * 8) + irow * 8;
-    // Q: chunk-major [chunk][row][8]: chunk = warp, row = lane within the stage
-    sr.q = baseA + ((int64_t)(cu.so + qsl) * (L + 1) + qp) * PL + ((int64_t)warp * R + lane) * 8;
-    sr.x = baseX + ((int64_t)(cu.so + xs) * R + lane) * 8;
-    sr.has_q = hq;
-    return sr;
-  };
-  float p[8], qv[8], x[8];
-  auto issue_loads = [&](const Src& sr, int qs) {
-    if (has_row) ld8g(sr.p + qs * (SROWS * HW), p);
-    if (q_loader && sr.has_q) ld8g(sr.q + qs * (SROWS * 8), qv);
-    if (warp == 0) ld8g(sr.x + qs * (SROWS * 8), x);
-  };
-  auto issue_prefetch = [&](const Src& sr, int qs) {
-    if (has_row) prefetch_l2(sr.p + qs * (SROWS * HW));
-    if (q_loader && sr.has_q) prefetch_l2(sr.q + qs * (SROWS * 8));
-    if (warp == 0) prefetch_l2(sr.x + qs * (SROWS * 8));
-  };
-  Cursor cur, pf;
+  Cursor cur;
   cursor_init(cur, a, wi, n_w);
-  pf = cur;
-  for (int i = 0; i < PF_AHEAD && cursor_valid(pf, L); ++i) {
-    const Src sr = source(pf);
-#pragma unroll
-    for (int qs = 0; qs < R / SROWS; ++qs) issue_prefetch(sr, qs);
-    cursor_next(pf, a, wi, n_w);
-  }
-  Src src = source(cur);
-  if (cursor_valid(cur, L)) issue_loads(src, 0);
-
   uint32_t sc = 0, ic = 0;
   bool pending = false;                  // instance ic - 1 not merged yet
   PH_DECL;
@@ -345,19 +365,24 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* raw) {
     int kind, l;
     cat_decode(L, cur.c, kind, l);
     const int c_now = cur.c;
-    const bool has_q = src.has_q;
+    const bool has_q = cat_has_q(kind);
     const bool scale_q = kind == CAT_ODE && l == 0 && sc_kind != NJODE_SCALE_IDENTITY;
-    Cursor nxt = cur;
-    cursor_next(nxt, a, wi, n_w);
-    const bool pf_ok = cursor_valid(pf, L);
-    Src psrc = src;
-    if (pf_ok) psrc = source(pf);
-#pragma unroll
+#pragma unroll 1
     for (int qs = 0; qs < R / SROWS; ++qs, ++sc) {
       const uint32_t stage = sc % NSTAGE3, sround = sc / NSTAGE3;
-      PH(0);                                                       // bookkeeping between stages
-      wait_or_die(&ctl.empty[stage], (sround & 1u) ^ 1u, dg, 8);
-      PH(1);                                                       // waiting for a free stage (MMA side is behind)
+      const uint32_t rs = sc % NRAW, rround = sc / NRAW;
+      PH(0);
+      wait_or_die_a(b_raw_full + 8u * rs, rround & 1u, dg, 10);    // the raw stage has landed (bulk copies complete)
+      PH(1);
+      float p[8], qv[8], x[8];
+      const uint32_t roff = rs * (uint32_t)G::RAW;
+      if (has_row) ld8s_a(rawP + roff, p);
+      if (q_loader && has_q) ld8s_a(rawQ + roff, qv);
+      if (warp == 0) ld8s_a(rawX + roff, x);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(b_raw_empty + 8u * rs);         // in registers: the producer may refill the staging stage
+      wait_or_die_a(b_empty + 8u * stage, (sround & 1u) ^ 1u, dg, 8);   // the operand stage is free (its MMAs are done)
+      PH(2);
       const uint32_t sb = ring_s + stage * G::STAGE;
       uint32_t hi[8], lo[8];
       if (has_row) {                                               // A operand: 8 rows of this feature -> TMEM
@@ -384,25 +409,15 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* raw) {
           for (int o = 0; o < MAX_O; ++o) dbo[o] += x[1 + o];
         }
       }
-      PH(2);                                                       // split + stores (incl. waiting for the register loads)
+      PH(3);                                                       // split + stores
       umma::wait_st();
       umma::fence_before_sync();
       umma::fence_async_smem();
       __syncwarp();
-      if (lane == 0) umma::mbar_arrive(&ctl.full[stage]);
-      PH(3);                                                       // fences + hand-over
-      // the next stage's loads (next plane pair after the last stage of this one), and the L2 prefetch far ahead
-      if (qs + 1 < R / SROWS) {
-        issue_loads(src, qs + 1);
-      } else if (cursor_valid(nxt, L)) {
-        src = source(nxt);
-        issue_loads(src, 0);
-      }
-      if (pf_ok) issue_prefetch(psrc, qs);
+      if (lane == 0) mbar_arrive_a(b_full + 8u * stage);           // operand stage ready for the issuer
+      PH(4);                                                       // fences + hand-over
     }
-    if (pf_ok) cursor_next(pf, a, wi, n_w);
-    cur = nxt;
-    PH(4);                                                         // issuing loads / prefetches, cursor
+    cursor_next(cur, a, wi, n_w);
     if (pending) merge(ic - 1);
     PH(5);                                                         // merge (incl. waiting for the accumulator)
     pending = true;
@@ -424,6 +439,7 @@ __global__ void __launch_bounds__(NT3, 1) k_wide_wgrad(SweepArgs a) {
   {
     Ctl3& ctl = *Carve3<HW>(smem_raw).ctl;
     if (threadIdx.x == 0) {
+      for (int i = 0; i < NRAW; ++i) { umma::mbar_init(&ctl.raw_full[i], 1); umma::mbar_init(&ctl.raw_empty[i], NWARP_W); }
       for (int i = 0; i < NSTAGE3; ++i) { umma::mbar_init(&ctl.full[i], NWARP_W); umma::mbar_init(&ctl.empty[i], 1); }
       for (int i = 0; i < 2; ++i) { umma::mbar_init(&ctl.fresh_done[i], 1); umma::mbar_init(&ctl.merged[i], NWARP_W); }
       umma::fence_mbar_init();
@@ -439,6 +455,7 @@ __global__ void __launch_bounds__(NT3, 1) k_wide_wgrad(SweepArgs a) {
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == NWARP_W) wg_issuer<HW>(a, smem_raw);
+    else if (threadIdx.x == NT_W + 32) wg_producer<HW>(a, smem_raw);
   }
   umma::fence_before_sync();
   __syncthreads();
@@ -447,7 +464,7 @@ __global__ void __launch_bounds__(NT3, 1) k_wide_wgrad(SweepArgs a) {
 
 template <int HW>
 int launch_wgrad(const SweepArgs& a, cudaStream_t st) {
-  const size_t smem = 1024 + (size_t)NSTAGE3 * G3<HW>::STAGE + sizeof(Ctl3) + 16;
+  const size_t smem = 1024 + (size_t)NSTAGE3 * G3<HW>::STAGE + (size_t)NRAW * G3<HW>::RAW + sizeof(Ctl3) + 16;
   if (njode_no_trap_env()) { const unsigned one = 1; NJODE_CUDA_OK(cudaMemcpyToSymbolAsync(g_notrap, &one, sizeof(one), 0, cudaMemcpyHostToDevice, st)); }
   NJODE_CUDA_OK(cudaFuncSetAttribute(k_wide_wgrad<HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   njode_timing_begin(3, st);

@@ -318,7 +318,7 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
   const int s = blockIdx.x % T.S, worker = blockIdx.x / T.S, n_workers = gridDim.x / T.S;
   const int row = w.row, col0 = w.col0, g = w.g;
   const int64_t PL = C::PL, slotf = (int64_t)(L + 1) * PL;
-  float* const ckpt_s = a.ckpt ? a.ckpt + (int64_t)s * a.total_slots * slotf + ((col0 >> 3) * R + row) * 8 : nullptr;
+  float* const ckpt_s = a.ckpt ? a.ckpt + (int64_t)s * a.total_slots * slotf + aplane_off(HW, col0 >> 3, row) : nullptr;
 
   const TileList tl(a, worker, n_workers);
   for (int ti = 0; ti < tl.n; ++ti) {
@@ -329,7 +329,7 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
     float* const ckd = a.ckpt ? a.ckpt + ((int64_t)T.S * a.total_slots + (int64_t)s * a.total_slots + a.tile_slot_off[tile]) * slotf +
                                     dplane_off(HW, col0, row) : nullptr;       // half D, this thread's (first feature, row)
     // plane `pl` of slot `sl`, this thread's sub-chunk j
-    auto cp = [&](int sl, int pl, int j) { return ck + ((int64_t)sl * (L + 1) + pl) * PL + j * (R * 8); };
+    auto cp = [&](int sl, int pl, int j) { return ck + ((int64_t)sl * (L + 1) + pl) * PL + j * 256; };      // (next chunk: + 32 rows x 8)
     const float* const kn = a.knots + a.tile_slot_off[tile] * R + row;
     const int ke = u >= 0 ? a.kenc[u] : 0;
     const int K = ke >> 1;
@@ -537,7 +537,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
   const int row = w.row, col0 = w.col0;
   const int64_t PL = C::PL, slotf = (int64_t)(L + 1) * PL;
   const int64_t half = (int64_t)T.S * a.total_slots * slotf;             // floats of half A
-  const int64_t toff = (int64_t)s * a.total_slots * slotf + ((col0 >> 3) * R + row) * 8;
+  const int64_t toff = (int64_t)s * a.total_slots * slotf + aplane_off(HW, col0 >> 3, row);
 
   const TileList tl(a, worker, n_workers);
   for (int ti = 0; ti < tl.n; ++ti) {
@@ -548,7 +548,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
     const float* const ca = a.ckpt + toff + a.tile_slot_off[tile] * slotf;       // activations (read)
     float* const cd = a.ckpt + half + (int64_t)s * a.total_slots * slotf + a.tile_slot_off[tile] * slotf +
                       dplane_off(HW, col0, row);                              // d planes (written; layout: njode_wide.cuh)
-    auto pa = [&](int sl, int pl, int j) { return ca + ((int64_t)sl * (L + 1) + pl) * PL + j * (R * 8); };
+    auto pa = [&](int sl, int pl, int j) { return ca + ((int64_t)sl * (L + 1) + pl) * PL + j * 256; };
     // (half D planes are [row octet][feature][8 rows]: this thread's (first feature of sub-chunk j, row))
     auto pd = [&](int sl, int pl, int j) { return cd + ((int64_t)sl * (L + 1) + pl) * PL + j * 64; };
     // aux rows of a slot (8 floats per row, written by the column-group-0 thread of the row): the extra B columns of
@@ -575,7 +575,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* raw) {
       //  chunks and every load waited for the previous one to land -- four serial HBM round trips per layer)
       float zb[CG];
 #pragma unroll
-      for (int j = 0; j < NSUB; ++j) ld8g(zsrc + j * (R * 8), *reinterpret_cast<float(*)[8]>(&zb[8 * j]));
+      for (int j = 0; j < NSUB; ++j) ld8g(zsrc + j * 256, *reinterpret_cast<float(*)[8]>(&zb[8 * j]));
       WAIT_ACC();
 #pragma unroll
       for (int j = 0; j < NSUB; ++j) {

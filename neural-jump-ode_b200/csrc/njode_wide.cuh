@@ -3,8 +3,8 @@
 // hidden_dim in {64, 128} and up to 3 hidden layers (BASELINE configs 4 and 5).
 //
 // Checkpoint geometry of this flavour.  A tile of 128 observation units owns (kmax + 1 + NJODE_WIDE_XSLOTS)
-// checkpoint slots; a slot is (L + 1) planes of [H/8 column chunks][128 rows][8 floats] (chunk-major: a warp
-// moving one chunk of 32 rows touches 1 KB contiguous).  The buffer holds two halves of equal size:
+// checkpoint slots; a slot is (L + 1) planes of H x 128 floats.  The buffer holds two halves of equal size (plane
+// layouts: aplane_off / dplane_off below):
 //   half A (written by the forward sweep)              half D (written by the reverse sweep)
 //   slot k <= kmax : plane 0 = h before Euler step k   slot k < kmax: plane l = d loss / d (pre-activation
 //                    (after the last one for k = kmax)                of ODE layer l) of step k, l = 0..L
@@ -75,6 +75,10 @@ __device__ __forceinline__ void st8t(float* __restrict__ dst, const float (&v)[8
 #pragma unroll
   for (int i = 0; i < 8; ++i) asm volatile("st.global.f32 [%0], %1;" :: "l"(dst + i * 8), "f"(v[i]) : "memory");
 }
+// offset of (8-feature chunk c, row r) inside a half-A plane of width HW: [4 row groups][HW/8 chunks][32 rows][8 floats]
+// -- a warp moving one chunk of its 32 rows touches 1 KB contiguous, and the 32 rows of a weight-gradient stage (all
+// chunks) are ONE contiguous block of HW * 128 bytes, i.e. one bulk copy
+__host__ __device__ __forceinline__ int aplane_off(int HW, int c, int r) { return (((r >> 5) * (HW >> 3) + c) * 32 + (r & 31)) * 8; }
 // offset of (feature f, row r) inside a half-D plane of width HW
 __host__ __device__ __forceinline__ int dplane_off(int HW, int f, int r) { return (r >> 3) * (HW * 8) + f * 8 + (r & 7); }
 __device__ __forceinline__ float ldg_na(const float* __restrict__ p) {
@@ -124,6 +128,39 @@ __device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity
     if (done) return true;
   }
   return false;
+}
+// 32-bit shared-window address variants: a generic pointer into shared memory costs an S2R (window base) wherever the
+// compiler rematerialises it, which it does inside register-capped stage loops
+// (volatile: computed once and kept, never rematerialised)
+__device__ __forceinline__ uint32_t smem_u32_once(const void* p) {
+  uint32_t r;
+  asm volatile("{\n\t.reg .u64 t;\n\tcvta.to.shared.u64 t, %1;\n\tcvt.u32.u64 %0, t;\n\t}\n" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ bool mbar_wait_a(uint32_t a, uint32_t parity, uint32_t spins) {
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < spins; ++spin) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    if (done) return true;
+  }
+  return false;
+}
+__device__ __forceinline__ void wait_or_die_a(uint32_t bar_s, uint32_t parity, Diag& dg, unsigned code) {
+  if (dg.dead) return;
+  if (mbar_wait_a(bar_s, parity, dg.notrap ? (1u << 17) : (1u << 24))) return;
+  atomicOr(dg.status, dg.bit | (1u << (8 + code)));
+  atomicCAS(dg.status + 1, 0u, code | ((threadIdx.x >> 5) << 8) | (blockIdx.x << 16));
+  __threadfence_system();
+  if (dg.notrap) dg.dead = true; else __trap();
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_s) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar_s) : "memory");
+}
+__device__ __forceinline__ void ld8s_a(uint32_t a, float (&v)[8]) {
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a));
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(a));
 }
 __device__ __forceinline__ void wait_or_die(uint64_t* bar, uint32_t parity, Diag& dg, unsigned code) {
   if (dg.dead) return;

@@ -44,6 +44,6 @@ for tag, ph, cyc, iss in (("forward sweep", fwd, fwd_c, fwd_i), ("reverse sweep"
     print(f"{name} {tag}: {cyc[:, 0].mean():.4g} cycles per CTA, {g:.0f} chain GEMMs -> {cyc[:, 0].mean() / g:.0f} cycles per GEMM; "
           f"worker thread 0: epilogue + emission {ph[:, 0].mean() / g:.0f}, accumulator wait {ph[:, 1].mean() / g:.0f} per GEMM; "
           f"issuer: operand wait {iss[:, 0].mean() / g:.0f}, weight wait {iss[:, 1].mean() / g:.0f}, issue {iss[:, 2].mean() / g:.0f} per GEMM")
-names = ["bookkeeping", "stage wait", "split+stores", "fence+hand-over", "load issue", "merge", "flush"]
+names = ["bookkeeping", "raw-stage wait", "smem loads + operand-stage wait", "split+stores", "fence+hand-over", "merge", "flush"]
 tot = wg[:, :7].sum(1).mean()
-print(f"{name} weight-gradient GEMM loader thread 0: {tot:.4g} cycles per CTA: " + ", ".join(f"{nm} {100 * wg[:, i].mean() / tot:.1f}%" for i, nm in enumerate(names)))
+print(f"{name} weight-gradient GEMM converter thread 0: {tot:.4g} cycles per CTA: " + ", ".join(f"{nm} {100 * wg[:, i].mean() / tot:.1f}%" for i, nm in enumerate(names)))

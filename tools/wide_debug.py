@@ -97,7 +97,7 @@ def golden_main(name):
     slots_w = sw.total_slots
     PL = 128 * H
     halfA = S * slots_w * (L + 1) * PL
-    A = r["ckpt"][:halfA].reshape(S, slots_w, L + 1, H // 8, 128, 8)
+    A = r["ckpt"][:halfA].reshape(S, slots_w, L + 1, 4, H // 8, 32, 8)
     D = r["ckpt"][halfA:2 * halfA].reshape(S, slots_w, L + 1, 16, H, 8)                     # half D: [row octet][feature][8 rows]
     X = r["ckpt"][2 * halfA:2 * halfA + S * slots_w * 128 * 8].reshape(S, slots_w, 128, 8)
     kmax_w = sw.tile_kmax.cpu().numpy()
@@ -107,7 +107,7 @@ def golden_main(name):
     def plane(buf, s, slot, pl):
         if buf is D:
             return buf[s, slot, pl].transpose(0, 2, 1).reshape(128, H).astype(np.float64)
-        return buf[s, slot, pl].transpose(1, 0, 2).reshape(128, H).astype(np.float64)
+        return buf[s, slot, pl].transpose(0, 2, 1, 3).reshape(128, H).astype(np.float64)
 
     dx = mk["input_dim"]
     for s in range(S):
@@ -168,7 +168,7 @@ def main():
     slots_w, slots_r = sw.total_slots, sr.total_slots
     PL = 128 * H
     halfA = S * slots_w * (L + 1) * PL
-    A = got["ckpt"][:halfA].reshape(S, slots_w, L + 1, H // 8, 128, 8)
+    A = got["ckpt"][:halfA].reshape(S, slots_w, L + 1, 4, H // 8, 32, 8)                    # half A: [row group][chunk][32 rows][8]
     Rk = ref["ckpt"].reshape(S, slots_r, L + 1, 32, H)
     mw, mr = unit_map(sw), unit_map(sr)
     so_w, so_r = sw.tile_slot_off.cpu().numpy(), sr.tile_slot_off.cpu().numpy()
@@ -180,7 +180,7 @@ def main():
             for pl in range(L + 1):
                 if pl > 0 and k == int(K[u]):
                     continue
-                a = A[:, so_w[tw] + k, pl, :, rw, :].reshape(S, H)
+                a = A[:, so_w[tw] + k, pl, rw // 32, :, rw % 32, :].reshape(S, H)
                 r_ = Rk[:, so_r[tr] + k, pl, rr, :]
                 worst[pl] = max(worst[pl], np.abs(a - r_).max())
                 scale[pl] = max(scale[pl], np.abs(r_).max())
@@ -197,7 +197,7 @@ def main():
     def plane(buf, s, slot, pl):                                                            # -> [row][feature]
         if buf is D:
             return buf[s, slot, pl].transpose(0, 2, 1).reshape(128, H).astype(np.float64)
-        return buf[s, slot, pl].transpose(1, 0, 2).reshape(128, H).astype(np.float64)
+        return buf[s, slot, pl].transpose(0, 2, 1, 3).reshape(128, H).astype(np.float64)
 
     keys = list(got["grads"].keys())
     for s in range(S):
