@@ -37,6 +37,11 @@ __device__ unsigned g_status[2] = {0, 0};
 __device__ unsigned g_notrap = 0;
 __device__ unsigned long long g_phase3[512][8];     // `make phase`: per-CTA phase cycles of the converter role (thread 0)
 
+// 1: hand a staging stage back to the producer as soon as it is in registers (needs its own proxy fence, see the
+// converter loop); 0: hand it back together with the operand stage.  Measured: 0 is faster (one fence per stage).
+#ifndef NJODE_K3_EARLY_RELEASE
+#define NJODE_K3_EARLY_RELEASE 0
+#endif
 constexpr int NT3 = NT_W + 128;        // 16 converter / merge warps + one warpgroup: MMA issuer warp, producer warp (setmaxnreg: 112 / 32)
 constexpr int NSTAGE3 = 3;             // operand stages (TMEM ring + MN tiles)
 constexpr int NRAW = 3;                // staging stages (raw planes)
@@ -379,8 +384,15 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* base) {
       if (has_row) ld8s_a(rawP + roff, p);
       if (q_loader && has_q) ld8s_a(rawQ + roff, qv);
       if (warp == 0) ld8s_a(rawX + roff, x);
+#if NJODE_K3_EARLY_RELEASE
+      // The staging stage goes back to the producer as soon as it is in registers.  The proxy fence is what makes
+      // that safe: it waits for the loads above (an arrive alone does not) and orders these generic-proxy reads
+      // before the producer's next bulk copy into the same bytes (async proxy) -- without it one stage in a few
+      // thousand was read after the refill had started (tools/k3_stress.py).  No global load is in flight here.
+      umma::fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive_a(b_raw_empty + 8u * rs);         // in registers: the producer may refill the staging stage
+      if (lane == 0) mbar_arrive_a(b_raw_empty + 8u * rs);
+#endif
       wait_or_die_a(b_empty + 8u * stage, (sround & 1u) ^ 1u, dg, 8);   // the operand stage is free (its MMAs are done)
       PH(2);
       const uint32_t sb = ring_s + stage * G::STAGE;
@@ -414,7 +426,12 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* base) {
       umma::fence_before_sync();
       umma::fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive_a(b_full + 8u * stage);           // operand stage ready for the issuer
+      if (lane == 0) {
+        mbar_arrive_a(b_full + 8u * stage);                        // operand stage ready for the issuer
+#if !NJODE_K3_EARLY_RELEASE
+        mbar_arrive_a(b_raw_empty + 8u * rs);                      // staging stage consumed: the producer may refill it
+#endif
+      }
       PH(4);                                                       // fences + hand-over
     }
     cursor_next(cur, a, wi, n_w);
