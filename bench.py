@@ -405,6 +405,21 @@ def main():
         if os.path.exists(tpath) and traffic is None:
             entry = json.load(open(tpath)).get(f"{name}:{first.B}", {})
             traffic = entry.get(f"which{dom}_dram_bytes_per_launch", entry.get("reverse_sweep_dram_bytes_per_launch") if dom == 2 else None)
+    # algorithmic checkpoint traffic of the dominant kernel (the only large buffer): bytes per unit-slot and
+    # stack that this kernel must move once, x (Euler steps + units) x stacks; slot padding and re-reads not counted
+    Hh, Ll = mk["hidden_dim"], mk.get("n_hidden_layers", 1)
+    n_stacks = 1 if mk.get("shared_network", False) else mk.get("num_moments", 1)
+    plane = 4 * Hh
+    ckpt_bytes = {"tiled": {1: 2 * plane, 2: 2 * plane},
+                  "wide": {1: (1 + Ll) * plane, 2: 2 * (1 + Ll) * plane + 32, 3: 2 * (1 + Ll) * plane + 32},
+                  "rowtile": {1: (1 + Ll) * plane, 2: (1 + Ll) * plane},
+                  "generic": {1: plane, 2: plane}}[impl][dom]
+    hbm_bytes = float(ckpt_bytes) * (scheds[0].total_steps + first.N) * n_stacks
+    hbm_peak = measured.get("hbm_gbs", 7700.0)
+    hbm_gbs = hbm_bytes / (kernel_ms[dom] * 1e-3) * 1e-9
+    hbm_view = {"algorithmic_bytes_per_launch": hbm_bytes, "achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak,
+                "frac": hbm_gbs / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in measured else "fallback 7700 GB/s (B200_PROFILING.md)"}
     if fl_spec["bound"] == "tensor":
         # 3xTF32: three tf32 MMAs per FP32-accurate product, tf32 runs at half the bf16 rate -> bf16 / 6
         peak_used = bf16 / 6.0
@@ -418,6 +433,7 @@ def main():
                 "traffic": traffic, "peak_source": peak_source, "kernel_ms": kernel_ms[dom],
                 "algorithmic_flop_per_launch": dom_flop,
                 "all_kernels_ms": {fl_spec["kernels"][w][0]: kernel_ms[w] for w in kernel_ms},
+                "hbm": hbm_view,
                 "fp32_fma_peak_tflops": peak_fma, "frac_of_fp32_fma_peak": achieved / peak_fma,
                 "whole_step_tflops": fl["total"] * (total_steps_rank / max(scheds[0].total_steps, 1)) * args.steps / (t_total_ms * 1e-3) * 1e-12,
                 "whole_step_frac_of_fp32_fma_peak": fl["total"] * (total_steps_rank / max(scheds[0].total_steps, 1)) * args.steps / (t_total_ms * 1e-3) * 1e-12 / peak_fma}

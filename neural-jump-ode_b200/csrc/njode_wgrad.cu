@@ -5,11 +5,13 @@
 // weight gradient is a contraction over rows:   dW[out][in] = sum_rows D[row][out] * A[row][in]
 // i.e. a GEMM whose K index is the row, for ~(kmax + 3) x (L + 1) plane pairs per tile:
 //     A operand = D plane transposed [out][rows]  (M = 128), from TENSOR MEMORY: the reverse sweep writes its d planes
-//                 as [row octet][feature][8 rows], a worker here loads 8 consecutive rows of its feature (one LDG.256,
-//                 1 KB contiguous per warp), splits them
-//                 into tf32 hi / lo and stores them straight into TMEM (tcgen05.st), lane = output feature;
+//                 as [row octet][feature][8 rows]; a converter thread takes the 8 rows of its feature from the staged
+//                 stage (ld.shared.v4 x 2), splits them into tf32 hi / lo and stores them straight into TMEM
+//                 (tcgen05.st), lane = output feature;
 //     B operand = [A plane | aux columns] [rows][in + 16]  (N = H + 16), MN-major tf32 tiles in shared memory
-//                 (SWIZZLE_128B_BASE32B, 128-byte rows of 32 features), split by the workers on the way in.
+//                 (SWIZZLE_128B_BASE32B, 128-byte rows of 32 features), split by the converters on the way in; the
+//                 forward sweep writes its activation planes as [row group of 32][8-feature chunk][32 rows][8], so
+//                 that the 32 rows of a stage are ONE contiguous block of the plane (one bulk copy).
 // The aux columns (1, s(x).., t, dt | 1, dY.. | 1, x..; written per slot by the reverse sweep) make the bias, the
 // x / t / dt columns of the first ODE layer, the readout weights and the first jump layer fall out of the same MMAs.
 // The first version took BOTH operands from shared memory and was bound by its port (8.5 KB per MMA = 68 cycles at
