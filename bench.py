@@ -428,9 +428,16 @@ def main():
     else:
         peak_used = peak_fma
         peak_source = "FP32-FMA peak measured in this process (njode_ffma_peak); MEASURED_PEAKS.json has no FP32 figure"
-    roofline = {"bound": "tensor" if fl_spec["bound"] == "tensor" else "fp32", "pipe": fl_spec["pipe"], "kernel": kname,
-                "flavour": impl, "achieved": achieved, "peak": peak_used, "unit": "TFLOP/s", "frac": achieved / peak_used,
-                "traffic": traffic, "peak_source": peak_source, "kernel_ms": kernel_ms[dom],
+    compute_view = {"achieved_tflops": achieved, "peak_tflops": peak_used, "frac": achieved / peak_used, "peak_source": peak_source}
+    if hbm_view["frac"] > achieved / peak_used:
+        # the dominant kernel is closer to the HBM roof than to its compute roof: that is the roof that binds it
+        head = {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_view["frac"],
+                "peak_source": hbm_view["peak_source"] + "; algorithmic checkpoint bytes of the kernel (DESIGN.md 5.2) / its event time"}
+    else:
+        head = {"bound": "tensor" if fl_spec["bound"] == "tensor" else "fp32", "achieved": achieved, "peak": peak_used,
+                "unit": "TFLOP/s", "frac": achieved / peak_used, "peak_source": peak_source}
+    roofline = {**head, "pipe": fl_spec["pipe"], "kernel": kname, "flavour": impl, "compute": compute_view,
+                "traffic": traffic, "kernel_ms": kernel_ms[dom],
                 "algorithmic_flop_per_launch": dom_flop,
                 "all_kernels_ms": {fl_spec["kernels"][w][0]: kernel_ms[w] for w in kernel_ms},
                 "hbm": hbm_view,
