@@ -39,11 +39,16 @@ __device__ unsigned g_status[2] = {0, 0};
 __device__ unsigned g_notrap = 0;
 __device__ unsigned long long g_phase3[512][8];     // `make phase`: per-CTA phase cycles of the converter role (thread 0)
 
-// 1: hand a staging stage back to the producer as soon as it is in registers (needs its own proxy fence, see the
-// converter loop); 0: hand it back together with the operand stage.  Measured: 0 is faster (one fence per stage).
-#ifndef NJODE_K3_EARLY_RELEASE
-#define NJODE_K3_EARLY_RELEASE 0
+// Converter groups: the 16 converter warps work as NGRP groups on alternating stages (group = warp / (16 / NGRP)).  With
+// one group every warp takes part in every stage and a stage cannot be shorter than one warp's serial chain (wait ->
+// ld.shared -> split -> tcgen05.st / tile stores -> fences -> arrive: ~2000 cycles, mostly latencies); with two groups
+// a warp converts twice the data per stage, every other stage, and the chains of consecutive stages overlap.
+#ifndef NJODE_K3_GROUPS
+#define NJODE_K3_GROUPS 2
 #endif
+constexpr int NGRP = NJODE_K3_GROUPS;
+constexpr int GWARPS = NWARP_W / NGRP;     // warps per group (a multiple of 4: every group covers the 4 TMEM lane quadrants)
+static_assert(NGRP == 1 || NGRP == 2 || NGRP == 4, "converter groups");      // (coprime with the ring depths: see Ctl3::raw_full)
 constexpr int NT3 = NT_W + 128;        // 16 converter / merge warps + one warpgroup: MMA issuer warp, producer warp (setmaxnreg: 112 / 32)
 constexpr int NSTAGE3 = 3;             // operand stages (TMEM ring + MN tiles)
 constexpr int NRAW = 3;                // staging stages (raw planes)
@@ -68,8 +73,12 @@ struct G3 {
 };
 
 struct Ctl3 {
-  uint64_t raw_full[NRAW], raw_empty[NRAW], full[NSTAGE3], empty[NSTAGE3], fresh_done[2], merged[2];
+  // raw_full is per (converter group, staging stage): a barrier shared by the groups would let a group that is done
+  // with stage sc - 2 wait for stage sc while stage sc - 3 (the other group's, same staging slot) has not landed yet --
+  // one phase too early for the parity test, which then passes at once (bulk copies complete out of order under load)
+  uint64_t raw_full[4][NRAW], raw_empty[NRAW], full[NSTAGE3], empty[NSTAGE3], fresh_done[2], merged[2];
   uint32_t tmem_base, pad;
+  float dbo[4][4];                       // readout-bias partial sums of the converter groups (flush)
 };
 
 __device__ __forceinline__ int n_cats(int L) { return 3 * L + 3; }
@@ -181,10 +190,11 @@ __device__ __forceinline__ void wg_producer(const SweepArgs& a, uint8_t* base) {
       const uint32_t rs = rc % NRAW, rround = rc / NRAW;
       wait_or_die(&ctl.raw_empty[rs], (rround & 1u) ^ 1u, dg, 9);
       uint8_t* dst = cv.raw + (size_t)rs * G::RAW;
-      mbar_expect_tx(&ctl.raw_full[rs], (uint32_t)(SROWS * HW * 4 * (has_q ? 2 : 1) + SROWS * 32));
-      bulk_g2s(dst + G::RAW_P, P + (int64_t)qs * (SROWS * HW), SROWS * HW * 4, &ctl.raw_full[rs]);     // 4 row octets x HW x 8
-      if (has_q) bulk_g2s(dst + G::RAW_Q, Q + (int64_t)qs * (SROWS * HW), SROWS * HW * 4, &ctl.raw_full[rs]);   // one row group: HW/8 chunks x 32 x 8
-      bulk_g2s(dst + G::RAW_X, X + (int64_t)qs * (SROWS * 8), SROWS * 32, &ctl.raw_full[rs]);
+      uint64_t* const landed = &ctl.raw_full[rc % NGRP][rs];       // the barrier of the group that converts this stage
+      mbar_expect_tx(landed, (uint32_t)(SROWS * HW * 4 * (has_q ? 2 : 1) + SROWS * 32));
+      bulk_g2s(dst + G::RAW_P, P + (int64_t)qs * (SROWS * HW), SROWS * HW * 4, landed);     // 4 row octets x HW x 8
+      if (has_q) bulk_g2s(dst + G::RAW_Q, Q + (int64_t)qs * (SROWS * HW), SROWS * HW * 4, landed);   // one row group: HW/8 chunks x 32 x 8
+      bulk_g2s(dst + G::RAW_X, X + (int64_t)qs * (SROWS * 8), SROWS * 32, landed);
     }
     cursor_next(cu, a, wi, n_w);
   }
@@ -253,7 +263,10 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* base) {
   const int L = T.L, S = T.S, dx = T.d_x, O = T.O;
   const int wi = blockIdx.x / S, n_w = gridDim.x / S;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = warp & 3, cg = warp >> 2;
+  const int q = warp & 3, cg = warp >> 2;            // TMEM lane quadrant; accumulator column group (merge / flush)
+  const int grp = warp / GWARPS, wl = warp % GWARPS; // converter group, warp within the group
+  constexpr int OPW = 4 * NGRP / 4;                  // row octets of a stage per warp: 4 octets over GWARPS / 4 warps per quadrant
+  const int oct0 = (wl >> 2) * OPW;                  // first of this warp's octets
   // shared-window (32-bit) addresses of the rings and the barriers (same carve as Carve3)
   const uint32_t ring_s = (smem_u32_once(base) + 1023u) & ~1023u;
   const uint32_t raw_s = ring_s + NSTAGE3 * G::STAGE, ctl_s = raw_s + NRAW * G::RAW;
@@ -264,15 +277,16 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* base) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(ctl_s + (uint32_t)offsetof(Ctl3, tmem_base)));
   const uint32_t quad_t = tmem + ((uint32_t)(q * 32) << 16);                  // this warp's TMEM lane quadrant, column 0
   float* const part = a.partials + (int64_t)blockIdx.x * T.stack_floats;
-  const bool q_loader = warp < G::NLOAD;            // this warp converts one 8-column chunk of the B operand (lane = row)
+  constexpr int CPW = (G::NLOAD + GWARPS - 1) / GWARPS;   // 8-column chunks of the B operand per warp (lane = row)
+  const bool q_loader = wl < G::NLOAD;
   const int irow = q * 32 + lane;                   // this thread's output feature = its TMEM lane
   const bool has_row = irow < HW;                   // (at H = 64 lanes 64..127 hold nothing)
   const int sc_kind = a.desc.input_scaling;
   const float comp = a.comp_wgrad;
   Diag dg{g_status, g_notrap, 16u, false};
   // this thread's pieces of a staging stage
-  const uint32_t rawP = raw_s + G::RAW_P + (uint32_t)(cg * HW + irow) * 32u;        // [octet cg][feature][8 rows]
-  const uint32_t rawQ = raw_s + G::RAW_Q + (uint32_t)(warp * 32 + lane) * 32u;      // [chunk = warp][row][8]
+  const uint32_t rawP = raw_s + G::RAW_P + (uint32_t)(oct0 * HW + irow) * 32u;      // [octet][feature][8 rows]
+  const uint32_t rawQ = raw_s + G::RAW_Q + (uint32_t)(wl * 32 + lane) * 32u;        // [chunk][row][8]: chunks wl, wl + GWARPS, ..
   const uint32_t rawX = raw_s + G::RAW_X + (uint32_t)lane * 32u;
 
   // running sums of the current category: accumulator row irow, columns [cg * CPT, +CPT)
@@ -338,12 +352,26 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* base) {
         }
       }
     }
-    if (kind == CAT_READOUT && warp == 0) {
+    if (kind == CAT_READOUT && wl == 0) {          // the aux-converting warp of each group holds a share of the row sums
+      static_assert(MAX_O == 4, "Ctl3::dbo");
 #pragma unroll
       for (int o = 0; o < MAX_O; ++o) {
         float v = dbo[o];
         for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
-        if (lane == 0 && o < O) part[T.b_off[NET_OUT][L] + o] = v;
+        if (lane == 0) asm volatile("st.shared.f32 [%0], %1;" :: "r"(ctl_s + (uint32_t)offsetof(Ctl3, dbo) + (uint32_t)(grp * 4 + o) * 4u), "f"(v) : "memory");
+      }
+#ifndef NJODE_K3_NO_DBO_BAR
+      if (NGRP > 1) umma::named_bar_sync(2, 32 * NGRP);      // (the category occurs once per kernel)
+      else __syncwarp();
+#endif
+      if (grp == 0 && lane < O) {
+        float v = 0.0f;
+        for (int g2 = 0; g2 < NGRP; ++g2) {
+          float t;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(ctl_s + (uint32_t)offsetof(Ctl3, dbo) + (uint32_t)(g2 * 4 + lane) * 4u) : "memory");
+          v += t;
+        }
+        part[T.b_off[NET_OUT][L] + lane] = v;
       }
     }
 #pragma unroll
@@ -376,45 +404,51 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* base) {
     const bool scale_q = kind == CAT_ODE && l == 0 && sc_kind != NJODE_SCALE_IDENTITY;
 #pragma unroll 1
     for (int qs = 0; qs < R / SROWS; ++qs, ++sc) {
+      if (NGRP > 1 && (int)(sc % NGRP) != grp) continue;           // the other group's stage
       const uint32_t stage = sc % NSTAGE3, sround = sc / NSTAGE3;
-      const uint32_t rs = sc % NRAW, rround = sc / NRAW;
+      const uint32_t rs = sc % NRAW;
       PH(0);
-      wait_or_die_a(b_raw_full + 8u * rs, rround & 1u, dg, 10);    // the raw stage has landed (bulk copies complete)
+      // the raw stage has landed (bulk copies complete); (group, slot) pairs repeat every NRAW * NGRP stages
+      wait_or_die_a(b_raw_full + 8u * (grp * NRAW + rs), (sc / (NRAW * NGRP)) & 1u, dg, 10);
       PH(1);
-      float p[8], qv[8], x[8];
       const uint32_t roff = rs * (uint32_t)G::RAW;
-      if (has_row) ld8s_a(rawP + roff, p);
-      if (q_loader && has_q) ld8s_a(rawQ + roff, qv);
-      if (warp == 0) ld8s_a(rawX + roff, x);
-#if NJODE_K3_EARLY_RELEASE
-      // The staging stage goes back to the producer as soon as it is in registers.  The proxy fence is what makes
-      // that safe: it waits for the loads above (an arrive alone does not) and orders these generic-proxy reads
-      // before the producer's next bulk copy into the same bytes (async proxy) -- without it one stage in a few
-      // thousand was read after the refill had started (tools/k3_stress.py).  No global load is in flight here.
-      umma::fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_a(b_raw_empty + 8u * rs);
-#endif
       wait_or_die_a(b_empty + 8u * stage, (sround & 1u) ^ 1u, dg, 8);   // the operand stage is free (its MMAs are done)
       PH(2);
       const uint32_t sb = ring_s + stage * G::STAGE;
-      uint32_t hi[8], lo[8];
-      if (has_row) {                                               // A operand: 8 rows of this feature -> TMEM
-        umma::split8(p, hi, lo);
-        umma::tmem_st8_raw(quad_t + a_hi_col(stage) + 8 * cg, hi);
-        umma::tmem_st8_raw(quad_t + a_lo_col(stage) + 8 * cg, lo);
-      }
-      if (q_loader && has_q) {                                     // B operand: one 8-column chunk of 32 rows -> MN-major tiles
-        const uint32_t boff = (uint32_t)(warp >> 2) * BLK;
-        if (scale_q) {
+      if (has_row) {                                               // A operand: 8 rows per octet of this feature -> TMEM
 #pragma unroll
-          for (int i = 0; i < 8; ++i) qv[i] = scale_fwd_rt(sc_kind, qv[i]);
+        for (int i = 0; i < OPW; ++i) {
+          float p[8];
+          uint32_t hi[8], lo[8];
+          ld8s_a(rawP + roff + (uint32_t)(i * HW) * 32u, p);
+          umma::split8(p, hi, lo);
+          umma::tmem_st8_raw(quad_t + a_hi_col(stage) + 8 * (oct0 + i), hi);
+          umma::tmem_st8_raw(quad_t + a_lo_col(stage) + 8 * (oct0 + i), lo);
         }
-        umma::split8(qv, hi, lo);
-        umma::chunk_to_mn_tile(sb + G::Q_HI + boff, lane, warp & 3, hi);
-        umma::chunk_to_mn_tile(sb + G::Q_LO + boff, lane, warp & 3, lo);
       }
-      if (warp == 0) {
+      if (q_loader && has_q) {                                     // B operand: 8-column chunks of 32 rows -> MN-major tiles
+#pragma unroll
+        for (int i = 0; i < CPW; ++i) {
+          const int c = wl + i * GWARPS;
+          if (c < G::NLOAD) {
+            float qv[8];
+            uint32_t hi[8], lo[8];
+            ld8s_a(rawQ + roff + (uint32_t)(i * GWARPS) * 1024u, qv);
+            if (scale_q) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) qv[e] = scale_fwd_rt(sc_kind, qv[e]);
+            }
+            umma::split8(qv, hi, lo);
+            const uint32_t boff = (uint32_t)(c >> 2) * BLK;
+            umma::chunk_to_mn_tile(sb + G::Q_HI + boff, lane, c & 3, hi);
+            umma::chunk_to_mn_tile(sb + G::Q_LO + boff, lane, c & 3, lo);
+          }
+        }
+      }
+      if (wl == 0) {
+        float x[8];
+        uint32_t hi[8], lo[8];
+        ld8s_a(rawX + roff, x);
         umma::split8(x, hi, lo);
         umma::chunk_to_mn_tile(sb + G::X_HI, lane, 0, hi);
         umma::chunk_to_mn_tile(sb + G::X_LO, lane, 0, lo);
@@ -423,16 +457,17 @@ __device__ __forceinline__ void wg_worker(const SweepArgs& a, uint8_t* base) {
           for (int o = 0; o < MAX_O; ++o) dbo[o] += x[1 + o];
         }
       }
-      PH(3);                                                       // split + stores
+      PH(3);                                                       // loads + split + stores
+      // One proxy fence covers both hand-overs: it orders the tile stores before the MMAs' reads AND the staging-stage
+      // reads above before the producer's next bulk copy into the same bytes (releasing the staging stage earlier, on a
+      // plain arrive, lost one stage in a few thousand to the refill: tools/k3_stress.py).
       umma::wait_st();
       umma::fence_before_sync();
       umma::fence_async_smem();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive_a(b_full + 8u * stage);                        // operand stage ready for the issuer
-#if !NJODE_K3_EARLY_RELEASE
         mbar_arrive_a(b_raw_empty + 8u * rs);                      // staging stage consumed: the producer may refill it
-#endif
       }
       PH(4);                                                       // fences + hand-over
     }
@@ -458,8 +493,8 @@ __global__ void __launch_bounds__(NT3, 1) k_wide_wgrad(SweepArgs a) {
   {
     Ctl3& ctl = *Carve3<HW>(smem_raw).ctl;
     if (threadIdx.x == 0) {
-      for (int i = 0; i < NRAW; ++i) { umma::mbar_init(&ctl.raw_full[i], 1); umma::mbar_init(&ctl.raw_empty[i], NWARP_W); }
-      for (int i = 0; i < NSTAGE3; ++i) { umma::mbar_init(&ctl.full[i], NWARP_W); umma::mbar_init(&ctl.empty[i], 1); }
+      for (int i = 0; i < NRAW; ++i) { for (int g = 0; g < 4; ++g) umma::mbar_init(&ctl.raw_full[g][i], 1); umma::mbar_init(&ctl.raw_empty[i], GWARPS); }
+      for (int i = 0; i < NSTAGE3; ++i) { umma::mbar_init(&ctl.full[i], GWARPS); umma::mbar_init(&ctl.empty[i], 1); }
       for (int i = 0; i < 2; ++i) { umma::mbar_init(&ctl.fresh_done[i], 1); umma::mbar_init(&ctl.merged[i], NWARP_W); }
       umma::fence_mbar_init();
     }

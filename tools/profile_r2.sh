@@ -28,4 +28,11 @@ full() { # name, kernel regex, skip, count, bench args...
 full h128 "k_wide_sweep|k_wide_wgrad" 3 3 --workload heston_h128_l3 --batch 1024
 full h64 "k_wide_sweep|k_wide_wgrad" 3 3 --workload mixed_h64_ragged --batch 8192
 full h32 "k_tiled_forward|k_tiled_backward" 2 2 --workload heston_sep_b262144 --batch 32768
-ls -la gpurun_out/${TAG}_*.ncu-rep gpurun_out/${TAG}_*.csv
+# summaries on the box (gpurun brings back at most 64 MiB: only the H = 128 report travels)
+for n in h128 h64; do
+  python tools/ncu_summary.py gpurun_out/${TAG}_full_$n.ncu-rep "k_wide" > gpurun_out/${TAG}_ncu_full_wide_$n.txt 2>&1
+  python tools/ncu_lines.py gpurun_out/${TAG}_full_$n.ncu-rep "k_wide" 14 > gpurun_out/${TAG}_ncu_lines_wide_$n.txt 2>&1
+done
+python tools/ncu_summary.py gpurun_out/${TAG}_full_h32.ncu-rep "k_tiled" > gpurun_out/${TAG}_ncu_full_tiled_h32.txt 2>&1
+rm -f gpurun_out/${TAG}_full_h64.ncu-rep gpurun_out/${TAG}_full_h32.ncu-rep
+ls -la gpurun_out/${TAG}_*
