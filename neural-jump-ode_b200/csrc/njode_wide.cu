@@ -30,6 +30,23 @@ __device__ unsigned long long g_cta_cycles[512][2];
 __device__ unsigned long long g_phase12[512][8];    // `make phase`: per-CTA phase cycles of the worker role (thread 0)
 __device__ unsigned long long g_phase_iss[512][8];  // ... and of the MMA issuer (lane 0): 0 operand wait, 1 weight wait, 2 issue
 
+// GEMM order of the chain sweeps.
+//   0: k-major.  A GEMM is NSUB passes, pass j = the 12 MMAs (N = H) over the A columns that sub-step j of the producing
+//      epilogue completes; the next GEMM starts under the tail of the epilogue, but every accumulator column is complete
+//      only after the last pass, so epilogue and MMAs of one layer never overlap (measured: 4100 + 3700 cycles).
+//   1: blocked.  A GEMM is 4 output blocks (block n = the CG accumulator columns of column group n), each over the
+//      whole K; the warps of column group n start their epilogue when block n is done, i.e. under the MMAs of blocks
+//      n+1.., and hold the next operand in registers until the last block is done (the A operand region in TMEM is
+//      still being read; at H = 128 TMEM has no room for a second one).
+// Measured on B200 (profiles/r2_wide_blocked_order_experiment.log): 1 is SLOWER -- a tcgen05.mma with A from TMEM costs
+// ~12 + 0.5 N cycles (N = 16: 19, 32: 29, 64: 50, 128: 76), so the 192 N = 32 MMAs of a blocked H = 128 GEMM take
+// 5650 cycles against 3670 for the 48 N = 128 ones; the epilogue does drop from 4100 to 2760 cycles, the sweep goes
+// from 3.97 to 5.58 ms.  Kept as a build option for the record; the product is 0.
+#ifndef NJODE_WIDE_BLOCKED
+#define NJODE_WIDE_BLOCKED 0
+#endif
+constexpr bool BLOCKED = NJODE_WIDE_BLOCKED != 0;
+
 constexpr int NT = NT_W + 128;         // 16 worker warps + one warpgroup holding the MMA issuer warp and the weight producer warp
 // Register budget: the CTA launches with 640 x 96 registers and setmaxnreg moves registers inside that pool:
 // 512 x 112 (workers: a 32-float state slice plus, in the reverse sweep, a 32-float activation slice per thread at
@@ -46,7 +63,7 @@ struct __align__(16) SmallW {
 };
 
 struct Ctl {
-  uint64_t full[8], empty[8], ops[4], accd[2];
+  uint64_t full[8], empty[8], ops[4], accd[4];      // (blocked order: ops[0] only, accd[n] = block n of the current GEMM)
   uint32_t tmem_base, pad;
 };
 
@@ -105,6 +122,13 @@ __global__ void k_wide_prep(ParamTable T, const float* __restrict__ params, floa
   const float v = transpose ? W[k * ld + n] : W[n * ld + k];
   uint32_t hi, lo;
   umma::split1(v, hi, lo);
+  if (BLOCKED) {
+    // stage = output block n / CG; inside: k-chunk (k / 32) major, then a [CG rows][32 k] swizzled tile
+    float* st = img + ((int64_t)(s * NM + m) * C::NBLK + n / C::CG) * (C::BSTAGE_BYTES / 4) + (k >> 5) * (C::CG * 32);
+    st[umma::swz_k(n % C::CG, k & 31)] = __uint_as_float(hi);
+    st[C::BSTAGE_HALF / 4 + umma::swz_k(n % C::CG, k & 31)] = __uint_as_float(lo);
+    return;
+  }
   const int g = k / C::CG, r = k % C::CG, j = r >> 3, i = r & 7, kk = g * 8 + i;
   float* st = img + ((int64_t)(s * NM + m) * C::NSUB + j) * (C::STAGE_BYTES / 4);
   st[umma::swz_k(n, kk)] = __uint_as_float(hi);
@@ -123,17 +147,19 @@ __device__ __forceinline__ void producer(const SweepArgs& a, uint8_t* raw, const
   Ctl& ctl = *sm.ctl;
   const int S = a.T.S, L = a.T.L;
   const int s = blockIdx.x % S, worker = blockIdx.x / S, n_workers = gridDim.x / S;
-  const uint8_t* simg = reinterpret_cast<const uint8_t*>(img) + (size_t)s * n_mats(L) * C::NSUB * C::STAGE_BYTES;
+  constexpr int NST = BLOCKED ? C::NBLK : C::NSUB;                          // stages per matrix
+  constexpr uint32_t SB = BLOCKED ? C::BSTAGE_BYTES : C::STAGE_BYTES;       // bytes per stage
+  const uint8_t* simg = reinterpret_cast<const uint8_t*>(img) + (size_t)s * n_mats(L) * NST * SB;
   uint32_t sc = 0;
   Diag dg{g_status, g_notrap, BWD ? 8u : 4u, false};
   auto load = [&](int m) {
-    const uint8_t* src = simg + (size_t)m * C::NSUB * C::STAGE_BYTES;
+    const uint8_t* src = simg + (size_t)m * NST * SB;
 #pragma unroll 1
-    for (int j = 0; j < C::NSUB; ++j, ++sc) {
+    for (int j = 0; j < NST; ++j, ++sc) {
       const uint32_t stage = sc % C::NSTAGE, round = sc / C::NSTAGE;
       wait_or_die(&ctl.empty[stage], (round & 1u) ^ 1u, dg, 1);
-      mbar_expect_tx(&ctl.full[stage], C::STAGE_BYTES);
-      bulk_g2s(sm.ring + (size_t)stage * C::STAGE_BYTES, src + (size_t)j * C::STAGE_BYTES, C::STAGE_BYTES, &ctl.full[stage]);
+      mbar_expect_tx(&ctl.full[stage], SB);
+      bulk_g2s(sm.ring + (size_t)stage * SB, src + (size_t)j * SB, SB, &ctl.full[stage]);
     }
   };
   const TileList tl(a, worker, n_workers);
@@ -175,6 +201,39 @@ __device__ __forceinline__ void issuer(const SweepArgs& a, uint8_t* raw) {
     const int n_gemm = 3 * L + a.tile_kmax[tile] * (L + 1);
 #pragma unroll 1
     for (int e = 0; e < n_gemm; ++e, ++gi) {
+      if (BLOCKED) {
+        constexpr uint32_t idesc_b = umma::idesc_tf32(128, C::CG, 0, 0);
+        PH(2);
+        wait_or_die(&ctl.ops[0], gi & 1u, dg, 2);              // the whole A operand of this GEMM is in TMEM
+        PH(0);
+#pragma unroll 1
+        for (int nb = 0; nb < C::NBLK; ++nb, ++sc) {
+          const uint32_t stage = sc % C::NSTAGE, sround = sc / C::NSTAGE;
+          wait_or_die(&ctl.full[stage], sround & 1u, dg, 3);   // the block's weights are in the ring
+          PH(1);
+          umma::fence_after_sync();
+          if (umma::elect_one()) {
+            const uint32_t acc = tmem + C::ACC0 + nb * C::CG;
+            const uint32_t sb = ring_s + stage * C::BSTAGE_BYTES;
+            const uint32_t a_hi = tmem + C::A_HI, a_lo = tmem + C::A_LO;
+            // k-step t = A columns 8t..8t+8 = k-chunk t / 4 (a [CG rows][32 k] tile), 32-byte step t % 4 inside it
+#pragma unroll
+            for (int t = 0; t < HW / 8; ++t)
+              umma::mma_ts(acc, a_lo + 8 * t, umma::desc_k(sb + (t >> 2) * (C::CG * 128)) + 2 * (t & 3), idesc_b, t > 0 ? 1u : 0u);
+#pragma unroll
+            for (int t = 0; t < HW / 8; ++t)
+              umma::mma_ts(acc, a_hi + 8 * t, umma::desc_k(sb + C::BSTAGE_HALF + (t >> 2) * (C::CG * 128)) + 2 * (t & 3), idesc_b, 1u);
+#pragma unroll
+            for (int t = 0; t < HW / 8; ++t)
+              umma::mma_ts(acc, a_hi + 8 * t, umma::desc_k(sb + (t >> 2) * (C::CG * 128)) + 2 * (t & 3), idesc_b, 1u);
+            umma::commit(&ctl.empty[stage]);                   // stage free once these MMAs have read it
+            umma::commit(&ctl.accd[nb]);                       // accumulator block nb complete
+          }
+          __syncwarp();
+          PH(2);
+        }
+        continue;
+      }
       const uint32_t acc = tmem + C::ACC0 + (gi & 1u) * HW;
 #pragma unroll 1
       for (int j = 0; j < C::NSUB; ++j, ++sc) {
@@ -235,7 +294,44 @@ struct WorkerCtx {
   // have long landed.  wait_acc() flushes the last pending hand-over: every emission is followed by one.
   float nx[8];             // accumulator chunk in flight
   int pend = -1;           // emitted sub-chunk whose hand-over is still to be signalled
+  // Blocked order: the A operand region is being read until the current GEMM's last block is done.  The warps of the
+  // last column group emit straight into it (their accumulator wait IS that event); the others park their raw FP32
+  // operand in the spare TMEM columns (the k-major order's second accumulator) and move it over in flush_emits().
+  static constexpr uint32_t STASH = C::ACC0 + HW;
+  bool have = false;
+  __device__ __forceinline__ void flush_emits() {
+    if (!have) return;
+    have = false;
+    if (g == C::NBLK - 1) {
+      umma::wait_st();
+      umma::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_relaxed(&ctl.ops[0]);
+      return;
+    }
+    umma::wait_st();                                             // the parked operand is in TMEM
+    // every MMA that reads the A operand region must be complete: the last block of the previous GEMM of the sequence
+    if (gi > 0) { wait_or_die(&ctl.accd[C::NBLK - 1], (gi - 1) & 1u, dg, 5); umma::fence_after_sync(); }
+    float v[8], vn[8];
+    umma::tmem_ld8_nowait(lane_base + STASH, vn);
+#pragma unroll
+    for (int j = 0; j < C::NSUB; ++j) {
+      asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(vn[0]), "+f"(vn[1]), "+f"(vn[2]), "+f"(vn[3]), "+f"(vn[4]), "+f"(vn[5]), "+f"(vn[6]), "+f"(vn[7]) :: "memory");
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = vn[i];
+      if (j + 1 < C::NSUB) umma::tmem_ld8_nowait(lane_base + STASH + 8 * (j + 1), vn);
+      uint32_t hi[8], lo[8];
+      umma::split8(v, hi, lo);
+      umma::tmem_st8_raw(lane_base + C::A_HI + 8 * j, hi);
+      umma::tmem_st8_raw(lane_base + C::A_LO + 8 * j, lo);
+    }
+    umma::wait_st();
+    umma::fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_relaxed(&ctl.ops[0]);
+  }
   __device__ __forceinline__ void signal_pending() {
+    if (BLOCKED) return;
     if (pend >= 0) {
       umma::wait_st();
       umma::fence_before_sync();
@@ -246,6 +342,21 @@ struct WorkerCtx {
   }
   // sub-chunk j of the next GEMM's A operand: split, store to TMEM; the issuer is told one sub-chunk later
   __device__ __forceinline__ void emit(int j, const float (&v)[8]) {
+    if (BLOCKED) {
+      if (g == C::NBLK - 1) {
+        uint32_t hi[8], lo[8];
+        umma::split8(v, hi, lo);
+        umma::tmem_st8_raw(lane_base + C::A_HI + 8 * j, hi);
+        umma::tmem_st8_raw(lane_base + C::A_LO + 8 * j, lo);
+      } else {
+        uint32_t raw[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) raw[i] = __float_as_uint(v[i]);
+        umma::tmem_st8_raw(lane_base + STASH + 8 * j, raw);
+      }
+      have = true;
+      return;
+    }
     uint32_t hi[8], lo[8];
     umma::split8(v, hi, lo);
     signal_pending();
@@ -255,6 +366,13 @@ struct WorkerCtx {
   }
   // wait for the accumulator of GEMM gi (call once per GEMM, then acc_ld for sub-chunks 0, 1, .. in order, then done())
   __device__ __forceinline__ void wait_acc() {
+    if (BLOCKED) {
+      flush_emits();
+      wait_or_die(&ctl.accd[g], gi & 1u, dg, 4);               // this column group's block of GEMM gi
+      umma::fence_after_sync();
+      umma::tmem_ld8_nowait(lane_base + C::ACC0, nx);
+      return;
+    }
     signal_pending();
     wait_or_die(&ctl.accd[gi & 1u], (gi >> 1) & 1u, dg, 4);
     umma::fence_after_sync();
@@ -265,7 +383,7 @@ struct WorkerCtx {
     asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(nx[0]), "+f"(nx[1]), "+f"(nx[2]), "+f"(nx[3]), "+f"(nx[4]), "+f"(nx[5]), "+f"(nx[6]), "+f"(nx[7]) :: "memory");
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = nx[i] * comp;
-    if (j + 1 < C::NSUB) umma::tmem_ld8_nowait(lane_base + C::ACC0 + (gi & 1u) * HW + 8 * (j + 1), nx);
+    if (j + 1 < C::NSUB) umma::tmem_ld8_nowait(lane_base + C::ACC0 + (BLOCKED ? 0u : (gi & 1u) * HW) + 8 * (j + 1), nx);
   }
   __device__ __forceinline__ void done() { ++gi; }
 };
@@ -728,8 +846,7 @@ __global__ void __launch_bounds__(NT, 1) k_wide_sweep(SweepArgs a, const float* 
     if (threadIdx.x == 0) {
       for (int i = 0; i < C::NSTAGE; ++i) { umma::mbar_init(&ctl.full[i], 1); umma::mbar_init(&ctl.empty[i], 1); }
       for (int i = 0; i < 4; ++i) umma::mbar_init(&ctl.ops[i], NWARP_W);
-      umma::mbar_init(&ctl.accd[0], 1);
-      umma::mbar_init(&ctl.accd[1], 1);
+      for (int i = 0; i < 4; ++i) umma::mbar_init(&ctl.accd[i], 1);
       umma::fence_mbar_init();
     }
     if (warp == 0) umma::tmem_alloc(&ctl.tmem_base, C::TMEM_COLS);

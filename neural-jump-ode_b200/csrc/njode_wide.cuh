@@ -46,6 +46,12 @@ struct Cfg {
   static constexpr int STAGE_HALF = HW * 128;         // bytes of the hi (or lo) part of a weight stage: HW rows x 32 k
   static constexpr int STAGE_BYTES = 2 * STAGE_HALF;  // a stage = the 4 k-steps (one per column group) of one sub-step
   static constexpr int NSTAGE = 6;
+  // Blocked GEMM order (NJODE_WIDE_BLOCKED): a chain GEMM runs as NBLK output blocks of CG columns -- block n is the
+  // accumulator slice of column group n -- each over the whole K; a ring stage is one block's weights
+  // ([hi | lo] x [HW / 32 k-chunks][CG rows][32 k]).
+  static constexpr int NBLK = 4;
+  static constexpr int BSTAGE_HALF = HW * CG * 4;     // bytes
+  static constexpr int BSTAGE_BYTES = 2 * BSTAGE_HALF;
   static constexpr uint32_t A_HI = 0, A_LO = HW, ACC0 = 2 * HW, TMEM_COLS = 4 * HW;
   static constexpr int PL = R * HW;                   // floats per checkpoint plane
 };
