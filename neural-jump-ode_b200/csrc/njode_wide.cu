@@ -405,6 +405,26 @@ __device__ __forceinline__ void load_small(SmallW<HW>& sw, const ParamTable& T, 
   }
 }
 
+// Activation of the epilogues.  tanhf() is ~20 instructions per element on two divergent paths and was more than half
+// of a tanh layer's epilogue (which is issue bound: 835 warp-instructions per layer and warp at H = 128).  Here:
+//     tanh(a) = sign(a) * (1 - 2 / (2^(2 |a| log2 e) + 1))        -- 6 instructions, no branch, exact at 0 and +-inf
+// with MUFU.EX2 / MUFU.RCP (2 ulp each): absolute error <= 2.5e-7, i.e. the size of the 3xTF32 GEMM error that feeds
+// it (the relative error of tiny outputs is larger, which the max-norm parity tolerance and the next GEMM do not see).
+// NJODE_WIDE_EXACT_TANH=1 (build) restores tanhf for comparisons.
+#ifndef NJODE_WIDE_EXACT_TANH
+#define NJODE_WIDE_EXACT_TANH 0
+#endif
+template <int ACT>
+__device__ __forceinline__ float act_w(float a) {
+  if (ACT == NJODE_ACT_TANH && !NJODE_WIDE_EXACT_TANH) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fabsf(a) * 2.8853900817779268f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return copysignf(fmaf(-2.0f, r, 1.0f), a);
+  }
+  return act_fwd<ACT>(a);
+}
+
 __device__ __forceinline__ void scale8(int sc, float (&v)[8]) {
   if (sc == NJODE_SCALE_TANH) {
 #pragma unroll
@@ -472,7 +492,7 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
         for (int i = 0; i < 8; ++i) z[i] = fmaf(cw[i], x[e], z[i]);
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) z[i] = act_fwd<ACT>(z[i]);
+      for (int i = 0; i < 8; ++i) z[i] = act_w<ACT>(z[i]);
       w.emit(j, z);
       if (ck) st8g(cp(X3, 0, j), z);
     }
@@ -484,7 +504,7 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
         w.acc_ld(j, z);
         ld8s(sw.b_jump[l] + col0 + 8 * j, cb);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) z[i] = act_fwd<ACT>(z[i] + cb[i]);
+        for (int i = 0; i < 8; ++i) z[i] = act_w<ACT>(z[i] + cb[i]);
         w.emit(j, z);                   // next jump layer, or (l == L) the first out-net layer on h_0
         // (checkpoint stores come AFTER the hand-over: its release-arrive waits for every earlier global store of the
         //  thread to be acknowledged -- an L2 round trip per sub-step when the store goes first)
@@ -512,7 +532,7 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
           w.acc_ld(j, z);
           ld8s(sw.b_out[l] + col0 + 8 * j, cb);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) z[i] = act_fwd<ACT>(z[i] + cb[i]);
+          for (int i = 0; i < 8; ++i) z[i] = act_w<ACT>(z[i] + cb[i]);
           if (l < L - 1) w.emit(j, z);
           if (ck) {
             st8g(cp(X, l + 1, j), z);
@@ -583,7 +603,7 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
         for (int i = 0; i < 8; ++i) z[i] = fmaf(cw[i], tc, z[i]);
         ld8s(sw.ext_ode0[dx + 1] + col0 + 8 * j, cw);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) z[i] = act_fwd<ACT>(fmaf(cw[i], delta, z[i]));
+        for (int i = 0; i < 8; ++i) z[i] = act_w<ACT>(fmaf(cw[i], delta, z[i]));
         w.emit(j, z);
         if (ck) st8g(cp(k, 1, j), z);
       }
@@ -596,7 +616,7 @@ __device__ __forceinline__ void fwd_worker(const SweepArgs& a, uint8_t* raw) {
           w.acc_ld(j, z);
           ld8s(sw.b_ode[l] + col0 + 8 * j, cb);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) z[i] = act_fwd<ACT>(z[i] + cb[i]);
+          for (int i = 0; i < 8; ++i) z[i] = act_w<ACT>(z[i] + cb[i]);
           w.emit(j, z);
           if (ck) st8g(cp(k, l + 1, j), z);
         }

@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 B="python bench.py --no-cpu-baseline --no-e2e"
 # 1
 timeout 300 $B --steps 2 --warmup 3 > gpurun_out/${TAG}_plain_default.json 2> gpurun_out/${TAG}_plain_default.err || { echo "plain default failed"; exit 1; }
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches_default.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^k_|^Device" -c 400 --csv --log-file gpurun_out/${TAG}_launches_default.csv \
     $B --steps 2 --warmup 3 > gpurun_out/${TAG}_ncu_launches.log 2>&1; echo "launch list rc=$?"
 # 2
 for spec in "heston_sep_b262144:" "heston_h128_l3:" "mixed_h64_ragged:" "ou_shared_b4096:"; do

@@ -16,7 +16,8 @@ run() { # name n args...
 for n in 1 2 4 8; do run default $n --steps 10 --warmup 3 --no-cpu-baseline; done
 for n in 1 8; do run ou $n --workload ou_shared_b4096 --steps 20 --warmup 5 --no-cpu-baseline; done
 for n in 8 1; do run h128_1m $n --workload heston_h128_l3_1m --steps 2 --warmup 3 --no-cpu-baseline; done
-run h64 8 --workload mixed_h64_ragged --steps 5 --warmup 3 --no-cpu-baseline --no-e2e
+for n in 8 1; do run h64 $n --workload mixed_h64_ragged --steps 5 --warmup 3 --no-cpu-baseline --no-e2e; done
+for n in 8 1; do run h128 $n --workload heston_h128_l3 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e; done
 python - <<PY
 import json, glob
 for f in sorted(glob.glob("gpurun_out/scale_${TAG}_*.json")):
