@@ -20,6 +20,8 @@
 // core's accumulate is not round-to-nearest: ~3000 MMAs into one TMEM accumulator drifted by 6e-5
 // (measured), so every step accumulates its 48 MMAs into a FRESH TMEM accumulator that the CUDA cores then
 // merge into running sums (also TMEM-resident) with IEEE fp32 adds.  See DESIGN.md for the measurements.
+#include <cstdlib>
+
 #include "njode_common.cuh"
 #include "njode_umma.cuh"
 
@@ -44,6 +46,15 @@ struct __align__(16) SmallParams {
 
 // sticky diagnostic word: bit 0 = forward, bit 1 = backward saw an mbarrier wait time out (njode_device_status)
 __device__ unsigned g_tiled_status = 0;
+// A wait that gives up is fatal: the role records it in the status word and traps, so that the next CUDA call of the
+// process fails instead of training on predictions and gradients from unfinished MMAs (a spurious time-out is possible
+// under time-slicing, MPS or a debugger).  NJODE_NO_TRAP=1 (bring-up): record and carry on, the status word stays readable.
+__device__ unsigned g_tiled_notrap = 0;
+__device__ __forceinline__ void tiled_gave_up(unsigned bit) {
+  atomicOr(&g_tiled_status, bit);
+  __threadfence_system();
+  if (!g_tiled_notrap) __trap();
+}
 
 // optional phase trace (`make trace`): one thread per role of CTA 0 records (clock64 << 8 | id) at phase
 // boundaries.  Forward: thread 0 writes straight to global memory.  Reverse sweep: worker thread 0 and the MMA
@@ -387,7 +398,7 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
   }
 
   TR_END(0);
-  if (!ok && tid == 0) atomicOr(&g_tiled_status, 1u);
+  if (!ok && tid == 0) tiled_gave_up(1u);
   umma::fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_free(tmem, F_TMEM_COLS);
@@ -523,7 +534,7 @@ __device__ __forceinline__ void bwd_issuer(const SweepArgs& a, uint8_t* smem_raw
     TRW_FLIP;
   }
   TR_END(2);
-  if (!ok && (threadIdx.x & 31) == 0) atomicOr(&g_tiled_status, 2u);
+  if (!ok && (threadIdx.x & 31) == 0) tiled_gave_up(2u);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -865,7 +876,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
     }
   }
   TR_END(1);
-  if (!ok && lane == 0) atomicOr(&g_tiled_status, 2u);
+  if (!ok && lane == 0) tiled_gave_up(2u);
 }
 
 // Reverse sweep.  Warps 0-15 are row workers (see the header), warp 16 only issues MMAs: the workers hand
@@ -913,6 +924,8 @@ __global__ void __launch_bounds__(NT_B, 1) k_tiled_backward(SweepArgs a) {
 template <int ACT>
 int launch_tiled(const SweepArgs& a, cudaStream_t st, bool backward) {
   if (a.n_tiles == 0) return NJODE_OK;
+  static const int no_trap = [] { const char* e = getenv("NJODE_NO_TRAP"); return e ? atoi(e) : 0; }();
+  if (no_trap) { const unsigned one = 1; NJODE_CUDA_OK(cudaMemcpyToSymbolAsync(g_tiled_notrap, &one, sizeof(one), 0, cudaMemcpyHostToDevice, st)); }
   if (backward) {
     NJODE_CUDA_OK(cudaFuncSetAttribute(k_tiled_backward<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
     njode_timing_begin(2, st);

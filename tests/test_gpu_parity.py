@@ -220,11 +220,15 @@ def test_oracle_parity_many_tiles(impl, hidden):
     assert status.value == 0          # no mbarrier wait timed out in the tcgen05 kernels
 
 
-@pytest.mark.parametrize("workload,B", [("heston_sep_b262144", 16384), ("mixed_h64_ragged", 4096)])
+@pytest.mark.parametrize("workload,B", [("heston_sep_b262144", 16384), ("mixed_h64_ragged", 4096), ("mixed_h64_ragged", 32768),
+                                        ("heston_h128_l3", 2048)])
 def test_additivity_over_trajectories_at_scale(workload, B):
     """Size-independent property at sizes the oracle cannot reach: the loss and every gradient of a batch equal the
     sum over its two halves when each half is scaled by 1/B_full (trajectories are independent, jump_ode.py:383).
-    The halves get different tilings, step schedules and CTA assignments than the full batch."""
+    The halves get different tilings, step schedules and CTA assignments than the full batch.
+    The two largest cases are the bench sizes of the wide flavour: several tiles per CTA and checkpoints far larger than
+    L2 (20 GB at H = 128), where the weight-gradient GEMM's bulk copies complete out of order -- a barrier-phase bug in
+    its staging ring passed every smaller test and only showed from ~1 500 trajectories up."""
     import bench
     from neural_jump_ode import NeuralJumpODE, nj_ode_loss, PackedBatch
     wl = bench.WORKLOADS[workload]
