@@ -173,6 +173,23 @@ class _BatchPlan:
     __slots__ = ("tile_rows", "n_tiles", "row_floats", "key", "sched", "slots", "arena", "layout", "scratch", "scratch_bytes", "host")
 
 
+def _alloc_ckpt(model, n_floats: int, dev):
+    """Checkpoint buffer of a sweep.  Normally a fresh allocation (the caching allocator recycles it); inside
+    ``forward_backward_waves`` one grow-only buffer is shared by all waves: consecutive waves need slightly different
+    sizes (41 GB +- a few MB at hidden 128), which the allocator can only serve by freeing and re-allocating device
+    memory -- a device synchronisation and ~4 ms per wave.  Re-use is safe because the next wave's forward sweep is
+    enqueued behind the previous wave's reverse sweep on the same stream."""
+    n_floats = max(int(n_floats), 1)
+    if not getattr(model, "_ckpt_pool_on", False):
+        return torch.empty(n_floats, dtype=torch.float32, device=dev)
+    pool = getattr(model, "_ckpt_pool", None)
+    if pool is None or pool.numel() < n_floats or pool.device != torch.device(dev):
+        model._ckpt_pool = pool = None                       # release the old one before growing
+        pool = torch.empty(n_floats + n_floats // 32 + 4096, dtype=torch.float32, device=dev)
+        model._ckpt_pool = pool
+    return pool[:n_floats]
+
+
 class _SweepFunction(torch.autograd.Function):
     """preds, preds_before = sweep(batch; params).  Forward = ``njode_forward`` on a batch whose schedule is cached,
     ``njode_forward_batch_begin`` / ``_finish`` (schedule + knots + sweep, no Python between the schedule's host sync
@@ -195,7 +212,7 @@ class _SweepFunction(torch.autograd.Function):
             ckpt = None
             if sched is not None:
                 if want_grad:
-                    ckpt = torch.empty(S * sched.total_slots * tile_rows * row_floats, dtype=torch.float32, device=dev)
+                    ckpt = _alloc_ckpt(model, S * sched.total_slots * tile_rows * row_floats, dev)
                 ws_bytes = lib.njode_forward_workspace_bytes(desc)
                 ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
                 nat.check(lib.njode_forward(desc, nat.ptr(flat), nat.ptr(batch.times), nat.ptr(batch.values),
@@ -209,7 +226,7 @@ class _SweepFunction(torch.autograd.Function):
                 # was seen before) so that no Python runs between the schedule's host sync and the sweep
                 slots, arena, layout, scratch, scratch_bytes, host = plan.slots, plan.arena, plan.layout, plan.scratch, plan.scratch_bytes, plan.host
                 ckpt_floats = S * slots * tile_rows * row_floats if want_grad else 0
-                ckpt = torch.empty(max(ckpt_floats, 1), dtype=torch.float32, device=dev) if want_grad else None
+                ckpt = _alloc_ckpt(model, ckpt_floats, dev) if want_grad else None
                 rc = lib.njode_forward_batch_finish(desc, nat.ptr(flat), nat.ptr(batch.times), nat.ptr(batch.values),
                                                     nat.ptr(batch.offsets), B, N, nat.ptr(arena), arena.numel(),
                                                     1 if want_grad else 0, nat.ptr(ckpt), ckpt_floats,
@@ -221,7 +238,7 @@ class _SweepFunction(torch.autograd.Function):
                     arena = ckpt = None
                     arena = torch.empty(lib.njode_batch_arena_bytes(desc, B, N, slots, layout), dtype=torch.uint8, device=dev)
                     ckpt_floats = S * slots * tile_rows * row_floats if want_grad else 0
-                    ckpt = torch.empty(max(ckpt_floats, 1), dtype=torch.float32, device=dev) if want_grad else None
+                    ckpt = _alloc_ckpt(model, ckpt_floats, dev) if want_grad else None
                     rc = lib.njode_forward_batch(desc, nat.ptr(flat), nat.ptr(batch.times), nat.ptr(batch.values),
                                                  nat.ptr(batch.offsets), B, N, nat.ptr(arena), arena.numel(),
                                                  1 if want_grad else 0, nat.ptr(ckpt), ckpt_floats,
@@ -581,6 +598,10 @@ class NeuralJumpODE(nn.Module):
             return None
         return torch.as_strided(first, (o,), (1,), first.storage_offset())
 
+    def release_wave_buffers(self) -> None:
+        """Free the checkpoint buffer that ``forward_backward_waves`` keeps between calls."""
+        self._ckpt_pool = None
+
     def forward_backward_waves(self, batch: PackedBatch, wave: int, traj_scale: Optional[float] = None, **loss_kwargs):
         """Loss and parameter gradients of a batch that is too large for one sweep's checkpoints (BASELINE config 4:
         10 MB of checkpoints per trajectory at hidden 128 / 3 layers / ~1040 Euler steps): the batch is cut into
@@ -588,7 +609,8 @@ class NeuralJumpODE(nn.Module):
         default 1 / batch.B -- pass 1 / B_global under data parallelism) and reverse sweep, and its checkpoints are
         released before the next one starts; gradients accumulate in ``.grad`` (zero them first, as with any
         backward).  With ``enable_data_parallel()`` the ranks' gradients are summed ONCE, after the last wave.
-        Returns the summed loss (0-dim tensor on the device; no host synchronisation).  The reference computes the
+        All waves share one checkpoint buffer, which the model keeps for the next call (``release_wave_buffers()``
+        frees it).  Returns the summed loss (0-dim tensor on the device; no host synchronisation).  The reference computes the
         same thing in one ``model(batch); nj_ode_loss(...); loss.backward()`` (utils/training.py:88-97): trajectories
         are independent and the loss is a mean over them (jump_ode.py:383), so waves only change the summation order."""
         if wave < 1:
@@ -597,6 +619,7 @@ class NeuralJumpODE(nn.Module):
         scale = 1.0 / B if traj_scale is None else float(traj_scale)
         dp, self._dp_group = self._dp_group, None
         total = None
+        self._ckpt_pool_on = True             # one checkpoint buffer for all waves (_alloc_ckpt); kept for the next call
         try:
             for lo in range(0, B, wave):
                 sub = batch.slice(lo, min(lo + wave, B))
@@ -607,6 +630,7 @@ class NeuralJumpODE(nn.Module):
                 del preds, before, loss
         finally:
             self._dp_group = dp
+            self._ckpt_pool_on = False
         if dp is not None:
             import torch.distributed as dist
             group = None if dp is True else dp
