@@ -42,6 +42,9 @@ __device__ unsigned long long g_phase_iss[512][8];  // ... and of the MMA issuer
 // ~12 + 0.5 N cycles (N = 16: 19, 32: 29, 64: 50, 128: 76), so the 192 N = 32 MMAs of a blocked H = 128 GEMM take
 // 5650 cycles against 3670 for the 48 N = 128 ones; the epilogue does drop from 4100 to 2760 cycles, the sweep goes
 // from 3.97 to 5.58 ms.  Kept as a build option for the record; the product is 0.
+#ifndef NJODE_WIDE_EARLY_SIGNAL
+#define NJODE_WIDE_EARLY_SIGNAL 1
+#endif
 #ifndef NJODE_WIDE_BLOCKED
 #define NJODE_WIDE_BLOCKED 0
 #endif
@@ -294,6 +297,11 @@ struct WorkerCtx {
   // have long landed.  wait_acc() flushes the last pending hand-over: every emission is followed by one.
   float nx[8];             // accumulator chunk in flight
   int pend = -1;           // emitted sub-chunk whose hand-over is still to be signalled
+  // When a sub-chunk's hand-over is signalled (measured on B200, forward + reverse sweep):
+  //   0: at the next emission (one sub-chunk of arithmetic later)          H=128: 3.98 + 4.46 ms   H=64: 1.49 + 1.82 ms
+  //   1: after the next accumulator load has been waited for               H=128: 3.71 + 4.49      H=64: 1.41 + 1.84
+  //   2: at once, behind its own tcgen05.st (the worker eats the latency)  H=128: 3.70 + 4.57      H=64: 1.36 + 1.79
+  static constexpr int ES = NJODE_WIDE_EARLY_SIGNAL == 0 ? 0 : (HW == 64 ? 2 : 1);
   // Blocked order: the A operand region is being read until the current GEMM's last block is done.  The warps of the
   // last column group emit straight into it (their accumulator wait IS that event); the others park their raw FP32
   // operand in the spare TMEM columns (the k-major order's second accumulator) and move it over in flush_emits().
@@ -363,6 +371,7 @@ struct WorkerCtx {
     umma::tmem_st8_raw(lane_base + C::A_HI + 8 * j, hi);
     umma::tmem_st8_raw(lane_base + C::A_LO + 8 * j, lo);
     pend = j;
+    if (ES == 2) signal_pending();          // at once: the worker eats the store latency, the issuer starts a sub-chunk earlier
   }
   // wait for the accumulator of GEMM gi (call once per GEMM, then acc_ld for sub-chunks 0, 1, .. in order, then done())
   __device__ __forceinline__ void wait_acc() {
@@ -381,6 +390,9 @@ struct WorkerCtx {
   __device__ __forceinline__ void acc_ld(int j, float (&v)[8]) {
     // (the registers are operands of the wait so that no use of them can be scheduled in front of it)
     asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(nx[0]), "+f"(nx[1]), "+f"(nx[2]), "+f"(nx[3]), "+f"(nx[4]), "+f"(nx[5]), "+f"(nx[6]), "+f"(nx[7]) :: "memory");
+    // the previous sub-chunk's operand stores were issued before this load was waited for: they have landed, and the
+    // issuer can start that sub-step's MMAs now rather than after this sub-chunk's arithmetic
+    if (ES == 1) signal_pending();
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = nx[i] * comp;
     if (j + 1 < C::NSUB) umma::tmem_ld8_nowait(lane_base + C::ACC0 + (BLOCKED ? 0u : (gi & 1u) * HW) + 8 * (j + 1), nx);
