@@ -85,3 +85,24 @@ def test_unknown_activation_is_relu():
     a, _ = orc.forward_port(P, cfg, t, v)
     b, _ = orc.forward_port(P, cfg2, t, v)
     assert torch.equal(a[0], b[0])
+
+
+def test_paths_oracle_matches_reference():
+    """oracle/paths_oracle.py (CPU baseline of the generator row) reproduces the reference's create_trajectory_batch
+    bit for bit: same seeds, same RNG consumption (incl. the OU generator's unused draw), same float32 ops
+    (fixture: tests/golden/aux/make_paths_golden.py)."""
+    import json
+    import os
+    from conftest import GOLDEN_DIR
+    from oracle import paths_oracle as po
+    z = np.load(os.path.join(GOLDEN_DIR, "aux", "paths_ref.npz"))
+    meta = json.loads(bytes(z["meta_json"]).decode())
+    assert set(m["process"] for m in meta.values()) == {"black_scholes", "ornstein_uhlenbeck", "heston"}
+    for name, m in meta.items():
+        bt, bv = po.trajectory_batch(m["n_traj"], m["process"], **m["kwargs"])
+        assert [len(t) for t in bt] == list(z[f"{name}|sizes"]), name
+        assert all(v.shape == (len(t), 1) for t, v in zip(bt, bv)), name
+        assert np.array_equal(torch.cat(bt).numpy().view(np.uint32), z[f"{name}|times"].view(np.uint32)), name
+        assert np.array_equal(torch.cat(bv).numpy().view(np.uint32), z[f"{name}|values"].view(np.uint32)), name
+    with pytest.raises(ValueError):
+        po.trajectory_batch(1, "no_such_process")
