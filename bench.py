@@ -220,6 +220,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None, help="override the workload's batch (global batch for strong-scaling workloads, per GPU otherwise)")
     ap.add_argument("--wave", type=int, default=None, help="trajectories per wave (workloads that run in waves)")
+    ap.add_argument("--obs-fraction", type=float, default=None, help="override the workload's observation fraction (analysis: separates per-step from per-tile cost)")
     ap.add_argument("--kernel-impl", default="auto", choices=["auto", "generic", "tiled", "rowtile", "wide"])
     ap.add_argument("--cpu-sample", type=int, default=384, help="trajectories in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -232,6 +233,8 @@ def main():
     wl = dict(WORKLOADS[name])
     if args.batch:
         wl["B"] = args.batch
+    if args.obs_fraction is not None:
+        wl["obs_fraction"] = args.obs_fraction
     if args.wave:
         wl["wave"] = args.wave
 
@@ -444,6 +447,22 @@ def main():
                 "fp32_fma_peak_tflops": peak_fma, "frac_of_fp32_fma_peak": achieved / peak_fma,
                 "whole_step_tflops": fl["total"] * (total_steps_rank / max(scheds[0].total_steps, 1)) * args.steps / (t_total_ms * 1e-3) * 1e-12,
                 "whole_step_frac_of_fp32_fma_peak": fl["total"] * (total_steps_rank / max(scheds[0].total_steps, 1)) * args.steps / (t_total_ms * 1e-3) * 1e-12 / peak_fma}
+
+    if impl == "tiled" and dom == 2 and sched.tile_rows == 128 and clocks and clocks.get("sm_mhz"):
+        # Third view, for the H=32 reverse sweep only: neither roof above is the one that binds it.  By design it moves
+        # 342 KB through shared memory per tile-step (48 SS-mode M64xN72xK8 MMAs read 206 KB of operand tiles, the row
+        # workers write 136 KB of tile stores) and the tensor core's operand fetch and the CUDA cores share
+        # the 128 B/cycle/SM port.  Design-derived bytes (NOT algorithmic): they say how close the kernel is to what this
+        # formulation allows, the tensor / HBM views say what the formulation costs.
+        tile_steps = float(scheds[0].tile_kmax.sum().item()) * n_stacks   # Euler tile-steps of one launch (every stack sweeps every tile)
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        smem_peak = 128.0 * sms * clocks["sm_mhz"] * 1e6 * 1e-9           # GB/s at the SM clock sampled under load
+        smem_bytes = tile_steps * 342.0 * 1024
+        smem_gbs = smem_bytes / (kernel_ms[dom] * 1e-3) * 1e-9
+        roofline["smem"] = {"design_bytes_per_launch": smem_bytes, "achieved_gbs": smem_gbs, "peak_gbs": smem_peak,
+                            "frac": smem_gbs / smem_peak, "tile_steps_per_launch": tile_steps,
+                            "cycles_per_tile_step": kernel_ms[dom] * 1e-3 * clocks["sm_mhz"] * 1e6 * sms / max(tile_steps, 1.0),
+                            "peak_source": "128 B/cycle/SM x SMs x median SM clock sampled during the timed region (readouts and jump-net phases of a tile not counted)"}
 
     # ---- end to end through the public API: pinned host inputs -> H2D -> schedule -> fwd/loss/bwd -> loss D2H ----
     e2e = None

@@ -413,7 +413,7 @@ enum { T_D1M_HI = 0, T_D0M_HI, T_D1M_LO, T_D0M_LO, T_ZM_HI, T_AM_HI, T_XM_HI, T_
 // TMEM columns: chain operands / accumulators, one fresh row-contraction accumulator (72 columns), and the
 // running weight-gradient sums (40 useful columns per accumulator row, see merge below)
 constexpr uint32_t B_AHI = 0, B_ALO = 32, B_DHI = 64, B_DLO = 96, B_ACCR = 128, B_ACCD = 160, B_SACC = 192,
-                   B_RUN_ODE = 288, B_RUN_OUT = 328, B_RUN_J1 = 368, B_RUN_J0 = 408, B_RUN_END = 416,
+                   B_RUN_ODE = 288, B_RUN_OUT = 328, B_RUN_J1 = 368, B_RUN_END = 408,   // (J1 rows 32-63 hold the first jump layer)
                    B_TMEM_COLS = 512;
 constexpr size_t BWD_SMEM = 1024 + (size_t)T_COUNT * TILE_F * 4 + WB_COUNT * 2 * WT_F * 4 + sizeof(SmallParams) + sizeof(Ctl) + 16 + NJODE_TRACE_SMEM_BYTES;
 
@@ -514,20 +514,19 @@ __device__ __forceinline__ void bwd_issuer(const SweepArgs& a, uint8_t* smem_raw
 #endif
     }
     issue_readout();
+    // jump net: the data-gradient chain first (its operand is in TMEM before the readout's weight-gradient MMAs are even
+    // done), then ONE row-contraction batch for both layers: [d | d0]^T x [z | aux]
     wait_ops();
     fresh();
     if (umma::elect_one()) {
       issue_chain(tmem + B_ACCD, tmem + B_DHI, tmem + B_DLO, wdesc(wbase, WB_JUMP1T, 0), wdesc(wbase, WB_JUMP1T, 1));
       umma::commit(&ctl.bar_chain);
-      issue_wgrad<40>(tmem + B_SACC, tdesc(tbase, T_D1M_HI), tdesc(tbase, T_D1M_LO), tdesc(tbase, T_AM_HI), tdesc(tbase, T_AM_LO), nks);
-      umma::commit(&ctl.bar_wgrad);
     }
     __syncwarp();
-    TRW_FLIP;
     wait_ops();
     fresh();
     if (umma::elect_one()) {
-      issue_wgrad<8>(tmem + B_SACC, tdesc(tbase, T_D1M_HI), tdesc(tbase, T_D1M_LO), tdesc(tbase, T_XM_HI), tdesc(tbase, T_XM_LO), nks);
+      issue_wgrad<40>(tmem + B_SACC, tdesc(tbase, T_D1M_HI), tdesc(tbase, T_D1M_LO), tdesc(tbase, T_AM_HI), tdesc(tbase, T_AM_LO), nks);
       umma::commit(&ctl.bar_wgrad);
     }
     __syncwarp();
@@ -645,6 +644,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
   for (int64_t round = 0; round * n_workers < a.n_tiles; ++round) {
     const int64_t tile = snake_tile(round, worker, n_workers);
     if (tile >= a.n_tiles) continue;
+    TR(17);
     const int kmax = a.tile_kmax[tile];
     has_unit_row = row < (tile < a.n_small_tiles ? a.tile_units_small : a.tile_units);
     const int u = a.perm[tile * R + row];
@@ -656,21 +656,26 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
 #pragma unroll
     for (int e = 0; e < MAX_DX; ++e) xs[e] = scale_fwd_rt(sc_kind, (e < dx && u >= 0) ? a.values[(int64_t)u * dx + e] : 0.0f);
     float g[8], hrow[8], z[8], acc[8], d[8];
+    float tn = 0.0f, tc_next = 0.0f;                  // knots of the step being reversed (loaded inside the first readout)
 #pragma unroll
     for (int j = 0; j < 8; ++j) g[j] = 0.0f;
 
     // ---- readout backward at a hidden state `hrow`; adds d loss / d hrow to g (no MMA in flight at entry) ----
-    auto out_backward = [&](const float* __restrict__ gsrc, int64_t obs, bool live) {
-      float dY[MAX_O], cw[8], cb[8];
-#pragma unroll
-      for (int o = 0; o < MAX_O; ++o) dY[o] = (live && o < O) ? gsrc[pred_index(T, obs, s, o)] : 0.0f;
+    // dY = d loss / d readout of this row (loaded by the caller well ahead: a load issued here would be waited for by the
+    // memory fence of the first hand-over, an exposed global-memory latency per readout).  `first_step` (readout at
+    // h_end only): the operands of the first Euler step of the reverse loop are requested right behind the second
+    // hand-over -- their registers are free from there on and the ~2000 cycles of MMA waits below hide the latency.
+    auto out_backward = [&](const float (&dY)[MAX_O], bool first_step) {
+      float cw[8], cb[8];
       put(hrow, true, B_AHI, B_ALO, T_AM_HI, T_AM_LO);
       static_assert(MAX_O == 4, "aux column layout assumes <= 4 readout columns");
       const float xv[8] = {1.0f, dY[0], dY[1], dY[2], dY[3], 0.0f, 0.0f, 0.0f};
 #pragma unroll
       for (int o = 0; o < MAX_O; ++o) dbo[o] += dY[o];
       put_aux(xv);
+      TR(18);
       hand_over();
+      TR(19);
       // d (readout hidden pre-activation) needs sum_o dY[o] * w_out1[o][j]: prepare while the MMA runs
       float dz[8];
 #pragma unroll
@@ -683,6 +688,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
       }
       ld8(sp.b_out0 + col0, cb);
       wait_chain();
+      TR(20);
       umma::tmem_ld8(lane_base + B_ACCR, acc);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -692,30 +698,51 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
       put(d, true, B_DHI, B_DLO, T_D1M_HI, T_D1M_LO);
       put(z, false, 0, 0, T_D0M_HI, T_D0M_LO);
       hand_over();
+      TR(21);
+      if (first_step) {
+        tn = ld_na(kn + kmax * R);
+        tc_next = kmax > 0 ? ld_na(kn + (kmax - 1) * R) : tn;
+        if (kmax > 0) {
+          ld8_cg(ck + (kmax - 1) * (2 * R * H), hrow);
+          ld8_cg(ck + (kmax - 1) * (2 * R * H) + R * H, z);
+          if (kmax > 1) {
+            prefetch_l2(ck + (kmax - 2) * (2 * R * H));
+            prefetch_l2(ck + (kmax - 2) * (2 * R * H) + R * H);
+          }
+        }
+      }
       wait_chain();
+      TR(22);
       umma::tmem_ld8(lane_base + B_ACCD, acc);
 #pragma unroll
       for (int j = 0; j < 8; ++j) g[j] += acc[j];
+      // the readout's weight-gradient MMAs are still running: the caller merges them (merge_pending) when it next needs
+      // the shared-memory tiles, and does tile-independent work until then
+    };
+    // fresh accumulator -> running sums for the batch in flight: 1 = an Euler step (rows 0-31 = d f rows: W1 block = columns
+    // 0-31; rows 32-63 = d a0 rows: W0 block = columns 32-63; columns 64.. = bias, x, t, dt gradients for either),
+    // 2 = a readout (hidden layer + readout weights)
+    auto merge_pending = [&](int kind) {
       wait_wgrad();
-      merge(B_RUN_OUT, B_SACC, B_SACC + 32, true);
+      TR(4);
+      const bool ode = kind == 1;
+      merge(ode ? B_RUN_ODE : B_RUN_OUT, B_SACC + ((ode && q >= 2) ? 32 : 0), B_SACC + (ode ? 64 : 32), true);
+    };
+    auto load_dY = [&](float (&dY)[MAX_O], const float* __restrict__ gsrc, int64_t obs, bool live) {
+#pragma unroll
+      for (int o = 0; o < MAX_O; ++o) dY[o] = (live && o < O) ? ld_na(gsrc + pred_index(T, obs, s, o)) : 0.0f;
     };
 
     // ---- preds_before[u+1] = out(h_end) ----
-    ld8_cg(ck + kmax * (2 * R * H), hrow);
-    out_backward(a.grad_preds_before, (int64_t)u + 1, u >= 0 && (ke & 1));
-
-    // ---- Euler steps, last to first ----
-    float tn = ld_na(kn + kmax * R);
-    float tc_next = kmax > 0 ? ld_na(kn + (kmax - 1) * R) : tn;
-    bool pending = false;                             // weight-gradient MMAs of the previous step still to be merged
-    if (kmax > 0) {
-      ld8_cg(ck + (kmax - 1) * (2 * R * H), hrow);
-      ld8_cg(ck + (kmax - 1) * (2 * R * H) + R * H, z);
-      if (kmax > 1) {
-        prefetch_l2(ck + (kmax - 2) * (2 * R * H));
-        prefetch_l2(ck + (kmax - 2) * (2 * R * H) + R * H);
-      }
+    {
+      float dY[MAX_O];
+      load_dY(dY, a.grad_preds_before, (int64_t)u + 1, u >= 0 && (ke & 1));
+      ld8_cg(ck + kmax * (2 * R * H), hrow);
+      out_backward(dY, true);
     }
+
+    // ---- Euler steps, last to first (tn, tc_next, hrow, z of step kmax-1: requested inside the readout above) ----
+    int pending = 2;                                  // weight-gradient MMAs still to be merged: 2 = the readout's, 1 = a step's
     for (int k = kmax - 1; k >= 0; --k) {
       TR(1);
       const float tc = tc_next;
@@ -736,13 +763,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
         prefetch_l2(ck + (k - 2) * (2 * R * H) + R * H);
       }
       // the MN tiles are free once the previous step's weight-gradient MMAs are done
-      if (pending) {
-        wait_wgrad();
-        TR(4);
-        // accumulator rows 0-31 (quadrants 0,1) are the d f rows: W1 block = columns 0-31; rows 32-63 (quadrants 2,3)
-        // are the d a0 rows: W0 block = columns 32-63; column 64.. = bias, x, t, dt gradients for either
-        merge(B_RUN_ODE, B_SACC + (q < 2 ? 0 : 32), B_SACC + 64, true);
-      }
+      merge_pending(pending);
       TR(5);
       scale8(sc_kind, hrow);
       TR(13);
@@ -768,7 +789,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
       put(d, true, B_DHI, B_DLO, T_D0M_HI, T_D0M_LO);
       TR(9);
       hand_over();                                                           // -> d s(h) = d0 * W0 ; weight gradients
-      pending = true;
+      pending = 1;
       TR(10);
       // the NEXT step's checkpoints, as soon as their registers are free: an L2 hit is ~1000 cycles away and nothing
       // on the way to their first use (the tile stores after the weight-gradient wait) may have to wait for them
@@ -780,19 +801,24 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
       if (k > 0) ld8_cg(ck + (k - 1) * (2 * R * H), hrow);
       TR(12);
     }
-    if (pending) {
-      wait_wgrad();
-      merge(B_RUN_ODE, B_SACC + (q < 2 ? 0 : 32), B_SACC + 64, true);
-    }
-
     // ---- preds[u] = out(h0), then the jump net ----
-    ld8_cg(ck, hrow);
-    out_backward(a.grad_preds, u, u >= 0);
+    // h0, the readout gradient and the observation are requested BEFORE the wait for the last step's weight-gradient
+    // MMAs (~1800 cycles with nothing else to do): by the time the merge is done they have landed
+    float x[MAX_DX];
+    {
+      float dY[MAX_O];
+      ld8_cg(ck, hrow);
+      load_dY(dY, a.grad_preds, u, u >= 0);
+#pragma unroll
+      for (int e = 0; e < MAX_DX; ++e) x[e] = (e < dx && u >= 0) ? ld_na(a.values + (int64_t)u * dx + e) : 0.0f;
+      TR(25);
+      merge_pending(pending);
+      TR(26);
+      out_backward(dY, false);
+    }
     {
       // z = first jump layer (recomputed), d = d loss / d (pre-activation of h0)
-      float x[MAX_DX], cw[8];
-#pragma unroll
-      for (int e = 0; e < MAX_DX; ++e) x[e] = (e < dx && u >= 0) ? a.values[(int64_t)u * dx + e] : 0.0f;
+      float cw[8];
       ld8(sp.b_jump0 + col0, z);
 #pragma unroll
       for (int e = 0; e < MAX_DX; ++e) if (e < dx) {
@@ -805,21 +831,28 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
         z[j] = act_fwd<ACT>(z[j]);
         d[j] = g[j] * act_grad_from_out<ACT>(hrow[j]);
       }
-      put(d, true, B_DHI, B_DLO, T_D1M_HI, T_D1M_LO);
+      put(d, true, B_DHI, B_DLO, -1, -1);
+      hand_over_tmem();                                        // -> d z = d * W_jump1 (queued behind the readout's batch)
+      TR(27);
+      merge_pending(2);                                        // the readout's weight gradients; the tiles are free now
+      put(d, false, 0, 0, T_D1M_HI, T_D1M_LO);
       put(z, false, 0, 0, T_AM_HI, T_AM_LO);
       const float xv[8] = {1.0f, x[0], x[1], 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};     // x[1] = 0 when d_x = 1
       put_aux(xv);
-      hand_over();
+      TR(28);
       wait_chain();
+      TR(29);
       umma::tmem_ld8(lane_base + B_ACCD, acc);
 #pragma unroll
       for (int j = 0; j < 8; ++j) d[j] = acc[j] * act_grad_from_out<ACT>(z[j]);
+      put(d, false, 0, 0, T_D0M_HI, T_D0M_LO);
+      hand_over();
+      TR(30);
+      // ONE batch for both layers, [d | d0]^T (M = 64) x [z | aux] (N = 40): accumulator rows 0-31 = second layer (weights
+      // and bias), rows 32-63 x aux columns = first layer (bias, x columns); both land in the B_RUN_J1 running sums
       wait_wgrad();
       merge(B_RUN_J1, B_SACC, B_SACC + 32, true);
-      put(d, false, 0, 0, T_D1M_HI, T_D1M_LO);
-      hand_over();
-      wait_wgrad();
-      merge(B_RUN_J0, 0, B_SACC, false);
+      TR(31);
     }
   }
 
@@ -864,8 +897,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
       for (int k = 0; k < 8; ++k) part[T.w_off[NET_JUMP][1] + j * H + col0 + k] = v[k];
       if (c == 0) part[T.b_off[NET_JUMP][1] + j] = v8[0];
     }
-    umma::tmem_ld8(quad_base + B_RUN_J0, v8);
-    if (has_row && i < 32 && c == 0) {
+    if (has_row && i >= 32 && c == 0) {       // first layer: d0 rows x aux columns (1, x..) of the same running sums
       part[T.b_off[NET_JUMP][0] + j] = v8[0];
       for (int e = 0; e < dx; ++e) part[T.w_off[NET_JUMP][0] + j * dx + e] = v8[1 + e];
     }

@@ -43,3 +43,17 @@ if bw:
     t0 = bw[mid][0]
     print("timeline (cycles relative, id): worker ids 1-12, issuer 64=loop top 65=ops#1 seen 66=chain1 issued 67=ops#2 seen 68=chain2+wgrad issued")
     print("  " + "  ".join(f"{t - t0}:{i}" for t, i in bw[mid:mid + 60]))
+
+# reverse-sweep worker, whole tiles (ids 17-31 mark the per-tile phases outside the Euler loop: 17 tile start, 18/19 first
+# hand-over of a readout, 20 chain 1 done, 21 second hand-over, 22 chain 2 done, 23 weight gradients done, 24 merged,
+# 25/26 around the wait for the last step's weight gradients, 27-31 jump net)
+wk = [(t, i) for i, t in rec if 1 <= i <= 31]
+if wk:
+    tail = wk[-150:]
+    t0 = tail[0][0]
+    print("worker timeline, last records (cycles relative : id):")
+    print("  " + "  ".join(f"{t - t0}:{i}" for t, i in tail))
+    starts = [t for t, i in wk if i == 17]
+    if len(starts) > 2:
+        gaps = [b - a for a, b in zip(starts, starts[1:])]
+        print("cycles per tile (17 -> 17):", gaps[-12:])
