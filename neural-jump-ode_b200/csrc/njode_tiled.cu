@@ -140,6 +140,16 @@ __device__ __forceinline__ float ld_na(const float* __restrict__ p) {
   asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
+__device__ __forceinline__ int ld_na_s32(const int32_t* __restrict__ p) {
+  int v;
+  asm volatile("ld.global.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ long long ld_na_s64(const int64_t* __restrict__ p) {
+  long long v;
+  asm volatile("ld.global.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 __device__ __forceinline__ void st8_stream(float* __restrict__ dst, const float (&v)[8]) {
   asm volatile("st.global.v8.f32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
@@ -641,17 +651,32 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
     umma::wait_st();
   };
 
+  // A tile's metadata (step count, first checkpoint slot, this row's unit) is requested ONE TILE AHEAD, in the jump phase of
+  // the previous tile, and what hangs off it (the unit's kenc / observation / readout gradient, the h_end checkpoint) is
+  // pulled into L2 at the end of that phase: at the top of a tile two dependent HBM round trips (~2000 cycles with the
+  // tensor pipe idle) become one L2 hit.
+  int kmax_pf = 0, u_pf = -1;
+  long long slot_pf = 0;
+  auto request_tile = [&](int64_t t) {
+    kmax_pf = ld_na_s32(a.tile_kmax + t);
+    slot_pf = ld_na_s64(a.tile_slot_off + t);
+    u_pf = ld_na_s32(a.perm + t * R + row);
+  };
+  if (snake_tile(0, worker, n_workers) < a.n_tiles) request_tile(snake_tile(0, worker, n_workers));
+
   for (int64_t round = 0; round * n_workers < a.n_tiles; ++round) {
     const int64_t tile = snake_tile(round, worker, n_workers);
     if (tile >= a.n_tiles) continue;
     TR(17);
-    const int kmax = a.tile_kmax[tile];
+    const int kmax = kmax_pf;
     has_unit_row = row < (tile < a.n_small_tiles ? a.tile_units_small : a.tile_units);
-    const int u = a.perm[tile * R + row];
+    const int u = u_pf;
     const int ke = u >= 0 ? a.kenc[u] : 0;
     // this thread's slice of the tile's checkpoint / knot slots (32-bit offsets per step from here on)
-    const float* ck = ckpt + (int64_t)a.tile_slot_off[tile] * (2 * R * H) + (c * R + row) * CW;
-    const float* kn = a.knots + (int64_t)a.tile_slot_off[tile] * R + row;
+    const float* ck = ckpt + (int64_t)slot_pf * (2 * R * H) + (c * R + row) * CW;
+    const float* kn = a.knots + (int64_t)slot_pf * R + row;
+    const int64_t next_tile = snake_tile(round + 1, worker, n_workers);
+    const bool has_next = next_tile < a.n_tiles;
     float xs[MAX_DX];
 #pragma unroll
     for (int e = 0; e < MAX_DX; ++e) xs[e] = scale_fwd_rt(sc_kind, (e < dx && u >= 0) ? a.values[(int64_t)u * dx + e] : 0.0f);
@@ -834,6 +859,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
       put(d, true, B_DHI, B_DLO, -1, -1);
       hand_over_tmem();                                        // -> d z = d * W_jump1 (queued behind the readout's batch)
       TR(27);
+      if (has_next) request_tile(next_tile);                   // lands under the waits below (this tile's values are dead)
       merge_pending(2);                                        // the readout's weight gradients; the tiles are free now
       put(d, false, 0, 0, T_D1M_HI, T_D1M_LO);
       put(z, false, 0, 0, T_AM_HI, T_AM_LO);
@@ -848,6 +874,15 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
       put(d, false, 0, 0, T_D0M_HI, T_D0M_LO);
       hand_over();
       TR(30);
+      if (has_next) {     // second hop of the next tile's prologue -> L2 (no destination registers)
+        prefetch_l2(ckpt + (int64_t)slot_pf * (2 * R * H) + (c * R + row) * CW + (int64_t)kmax_pf * (2 * R * H));
+        if (u_pf >= 0) {
+          prefetch_l2(a.kenc + u_pf);
+          prefetch_l2(a.values + (int64_t)u_pf * dx);
+          const int64_t ob = (int64_t)u_pf + 1 < a.N ? (int64_t)u_pf + 1 : a.N - 1;
+          prefetch_l2(a.grad_preds_before + pred_index(T, ob, s, 0));
+        }
+      }
       // ONE batch for both layers, [d | d0]^T (M = 64) x [z | aux] (N = 40): accumulator rows 0-31 = second layer (weights
       // and bias), rows 32-63 x aux columns = first layer (bias, x columns); both land in the B_RUN_J1 running sums
       wait_wgrad();
