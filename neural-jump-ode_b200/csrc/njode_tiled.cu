@@ -655,14 +655,31 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
   // the previous tile, and what hangs off it (the unit's kenc / observation / readout gradient, the h_end checkpoint) is
   // pulled into L2 at the end of that phase: at the top of a tile two dependent HBM round trips (~2000 cycles with the
   // tensor pipe idle) become one L2 hit.
-  int kmax_pf = 0, u_pf = -1;
+  int kmax_pf = 0, u_pf = -1, ke_pf = 0;
   long long slot_pf = 0;
   auto request_tile = [&](int64_t t) {
     kmax_pf = ld_na_s32(a.tile_kmax + t);
     slot_pf = ld_na_s64(a.tile_slot_off + t);
     u_pf = ld_na_s32(a.perm + t * R + row);
   };
-  if (snake_tile(0, worker, n_workers) < a.n_tiles) request_tile(snake_tile(0, worker, n_workers));
+  // ... and what the tile's first phase consumes -- the unit's step code, observation, readout gradient (un-masked: the
+  // mask is in kenc, which arrives together with it) and the h_end checkpoint -- is LOADED behind the last hand-over of the
+  // previous tile, into registers that are dead there, so the ~1300 cycles of that tile's last MMA wait hide the latency.
+  float hrow[8], dY_pf[MAX_O], x_pf[MAX_DX];
+  auto load_prologue = [&]() {
+    const int u = u_pf;
+    ke_pf = u >= 0 ? ld_na_s32(a.kenc + u) : 0;
+#pragma unroll
+    for (int e = 0; e < MAX_DX; ++e) x_pf[e] = (e < dx && u >= 0) ? ld_na(a.values + (int64_t)u * dx + e) : 0.0f;
+    const int64_t ob = (int64_t)u + 1 < a.N ? (int64_t)u + 1 : a.N - 1;          // (row u + 1 exists whenever kenc says so)
+#pragma unroll
+    for (int o = 0; o < MAX_O; ++o) dY_pf[o] = (u >= 0 && o < O) ? ld_na(a.grad_preds_before + pred_index(T, ob, s, o)) : 0.0f;
+    ld8_cg(ckpt + (int64_t)slot_pf * (2 * R * H) + (c * R + row) * CW + (int64_t)kmax_pf * (2 * R * H), hrow);
+  };
+  if (snake_tile(0, worker, n_workers) < a.n_tiles) {
+    request_tile(snake_tile(0, worker, n_workers));
+    load_prologue();
+  }
 
   for (int64_t round = 0; round * n_workers < a.n_tiles; ++round) {
     const int64_t tile = snake_tile(round, worker, n_workers);
@@ -671,7 +688,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
     const int kmax = kmax_pf;
     has_unit_row = row < (tile < a.n_small_tiles ? a.tile_units_small : a.tile_units);
     const int u = u_pf;
-    const int ke = u >= 0 ? a.kenc[u] : 0;
+    const int ke = ke_pf;
     // this thread's slice of the tile's checkpoint / knot slots (32-bit offsets per step from here on)
     const float* ck = ckpt + (int64_t)slot_pf * (2 * R * H) + (c * R + row) * CW;
     const float* kn = a.knots + (int64_t)slot_pf * R + row;
@@ -679,8 +696,9 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
     const bool has_next = next_tile < a.n_tiles;
     float xs[MAX_DX];
 #pragma unroll
-    for (int e = 0; e < MAX_DX; ++e) xs[e] = scale_fwd_rt(sc_kind, (e < dx && u >= 0) ? a.values[(int64_t)u * dx + e] : 0.0f);
-    float g[8], hrow[8], z[8], acc[8], d[8];
+    for (int e = 0; e < MAX_DX; ++e) xs[e] = scale_fwd_rt(sc_kind, x_pf[e]);
+    if (u >= 0) prefetch_l2(a.grad_preds + pred_index(T, u, s, 0));       // the second readout's gradient, for the end of the tile
+    float g[8], z[8], acc[8], d[8];
     float tn = 0.0f, tc_next = 0.0f;                  // knots of the step being reversed (loaded inside the first readout)
 #pragma unroll
     for (int j = 0; j < 8; ++j) g[j] = 0.0f;
@@ -760,9 +778,9 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
 
     // ---- preds_before[u+1] = out(h_end) ----
     {
-      float dY[MAX_O];
-      load_dY(dY, a.grad_preds_before, (int64_t)u + 1, u >= 0 && (ke & 1));
-      ld8_cg(ck + kmax * (2 * R * H), hrow);
+      float dY[MAX_O];                               // (hrow = h_end and dY_pf were loaded by load_prologue)
+#pragma unroll
+      for (int o = 0; o < MAX_O; ++o) dY[o] = (ke & 1) ? dY_pf[o] : 0.0f;
       out_backward(dY, true);
     }
 
@@ -832,10 +850,13 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
     float x[MAX_DX];
     {
       float dY[MAX_O];
-      ld8_cg(ck, hrow);
+      // h0 is the hidden state before step 0, i.e. what hrow holds after the loop (or, without steps, h_end itself) -- unless
+      // an input scaling was applied to it in place
+      const bool ident = sc_kind == NJODE_SCALE_IDENTITY;
+      if (kmax > 0 && !ident) ld8_cg(ck, hrow);
       load_dY(dY, a.grad_preds, u, u >= 0);
 #pragma unroll
-      for (int e = 0; e < MAX_DX; ++e) x[e] = (e < dx && u >= 0) ? ld_na(a.values + (int64_t)u * dx + e) : 0.0f;
+      for (int e = 0; e < MAX_DX; ++e) x[e] = ident ? xs[e] : ((e < dx && u >= 0) ? ld_na(a.values + (int64_t)u * dx + e) : 0.0f);
       TR(25);
       merge_pending(pending);
       TR(26);
@@ -874,15 +895,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
       put(d, false, 0, 0, T_D0M_HI, T_D0M_LO);
       hand_over();
       TR(30);
-      if (has_next) {     // second hop of the next tile's prologue -> L2 (no destination registers)
-        prefetch_l2(ckpt + (int64_t)slot_pf * (2 * R * H) + (c * R + row) * CW + (int64_t)kmax_pf * (2 * R * H));
-        if (u_pf >= 0) {
-          prefetch_l2(a.kenc + u_pf);
-          prefetch_l2(a.values + (int64_t)u_pf * dx);
-          const int64_t ob = (int64_t)u_pf + 1 < a.N ? (int64_t)u_pf + 1 : a.N - 1;
-          prefetch_l2(a.grad_preds_before + pred_index(T, ob, s, 0));
-        }
-      }
+      if (has_next) load_prologue();     // the next tile's first operands: they land under the wait below
       // ONE batch for both layers, [d | d0]^T (M = 64) x [z | aux] (N = 40): accumulator rows 0-31 = second layer (weights
       // and bias), rows 32-63 x aux columns = first layer (bias, x columns); both land in the B_RUN_J1 running sums
       wait_wgrad();
