@@ -676,9 +676,21 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
     for (int o = 0; o < MAX_O; ++o) dY_pf[o] = (u >= 0 && o < O) ? ld_na(a.grad_preds_before + pred_index(T, ob, s, o)) : 0.0f;
     ld8_cg(ckpt + (int64_t)slot_pf * (2 * R * H) + (c * R + row) * CW + (int64_t)kmax_pf * (2 * R * H), hrow);
   };
+  // A readout's backward starts with its hidden layer re-computed from the hidden state in hrow (chain GEMM 1).  That needs
+  // nothing but hrow, so it is started EARLY: for a tile's first readout at the end of the previous tile, for the second
+  // one before the last Euler step's weight gradients are merged -- the chain then runs in the shadow of work that has to
+  // happen anyway.  (Between two hand-overs there is always a wait for an MMA commit that the issuer only makes after it
+  // has consumed the first of them, so the workers can never complete two phases of bar_ops unseen.)
+  auto readout_begin = [&]() {
+    put(hrow, true, B_AHI, B_ALO, -1, -1);
+    TR(18);
+    hand_over_tmem();
+    TR(19);
+  };
   if (snake_tile(0, worker, n_workers) < a.n_tiles) {
     request_tile(snake_tile(0, worker, n_workers));
     load_prologue();
+    readout_begin();
   }
 
   for (int64_t round = 0; round * n_workers < a.n_tiles; ++round) {
@@ -708,17 +720,14 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
     // memory fence of the first hand-over, an exposed global-memory latency per readout).  `first_step` (readout at
     // h_end only): the operands of the first Euler step of the reverse loop are requested right behind the second
     // hand-over -- their registers are free from there on and the ~2000 cycles of MMA waits below hide the latency.
-    auto out_backward = [&](const float (&dY)[MAX_O], bool first_step) {
+    auto out_backward = [&](const float (&dY)[MAX_O], bool first_step) {      // (after readout_begin; the tiles are free)
       float cw[8], cb[8];
-      put(hrow, true, B_AHI, B_ALO, T_AM_HI, T_AM_LO);
+      put(hrow, false, 0, 0, T_AM_HI, T_AM_LO);
       static_assert(MAX_O == 4, "aux column layout assumes <= 4 readout columns");
       const float xv[8] = {1.0f, dY[0], dY[1], dY[2], dY[3], 0.0f, 0.0f, 0.0f};
 #pragma unroll
       for (int o = 0; o < MAX_O; ++o) dbo[o] += dY[o];
       put_aux(xv);
-      TR(18);
-      hand_over();
-      TR(19);
       // d (readout hidden pre-activation) needs sum_o dY[o] * w_out1[o][j]: prepare while the MMA runs
       float dz[8];
 #pragma unroll
@@ -857,6 +866,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
       load_dY(dY, a.grad_preds, u, u >= 0);
 #pragma unroll
       for (int e = 0; e < MAX_DX; ++e) x[e] = ident ? xs[e] : ((e < dx && u >= 0) ? ld_na(a.values + (int64_t)u * dx + e) : 0.0f);
+      readout_begin();
       TR(25);
       merge_pending(pending);
       TR(26);
@@ -899,6 +909,7 @@ __device__ __forceinline__ void bwd_worker(const SweepArgs& a, uint8_t* smem_raw
       // ONE batch for both layers, [d | d0]^T (M = 64) x [z | aux] (N = 40): accumulator rows 0-31 = second layer (weights
       // and bias), rows 32-63 x aux columns = first layer (bias, x columns); both land in the B_RUN_J1 running sums
       wait_wgrad();
+      if (has_next) readout_begin();     // the next tile's first chain GEMM runs under the merge and the tile's top
       merge(B_RUN_J1, B_SACC, B_SACC + 32, true);
       TR(31);
     }
