@@ -178,6 +178,23 @@ def main():
         loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct"),
         data=(nt, nv))
 
+    # hidden 32 / one layer (the tcgen05 tiled kernels) with an input scaling: the scaled hidden state feeds the ODE net and
+    # its weight gradients, the raw one the readouts -- incl. units without steps (n_i = 1, duplicate times) and d_x = 2
+    cases["h32_tanhscale_tanh_edges"] = dict(
+        model=dict(input_dim=1, hidden_dim=32, output_dim=1, dt_ode_step=0.01, num_moments=2, activation="tanh",
+                   input_scaling="tanh"),
+        loss=dict(ignore_first_continuity=True, moment_weights=[1.0, 10.0], variance_method="direct"),
+        data=(et + rt[:3], ev + rv[:3]))
+    cases["d2_shared_h32_sigscale_elu"] = dict(
+        model=dict(input_dim=2, hidden_dim=32, output_dim=2, dt_ode_step=0.05, num_moments=2, shared_network=True,
+                   activation="elu", input_scaling="sigmoid"),
+        loss=dict(ignore_first_continuity=False, moment_weights=[1.0, 2.0], variance_method="direct"),
+        data=(t2, v2))
+
+    only = [a.split("=", 1)[1].split(",") for a in sys.argv[1:] if a.startswith("--only=")]
+    if only:                                   # regenerate just the named cases (the others stay byte-identical on disk)
+        cases = {k: v for k, v in cases.items() if k in only[0]}
+
     KINKED = (torch.nn.ReLU, torch.nn.LeakyReLU, torch.nn.SELU)
 
     def kink_margin(model, bt, bv):

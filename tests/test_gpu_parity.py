@@ -146,6 +146,11 @@ CASES = [
          activation="tanh"),                                                    # BASELINE config 4 shape
     dict(input_dim=2, hidden_dim=96, output_dim=2, dt_ode_step=0.05, num_moments=2, n_hidden_layers=2,
          activation="elu", input_scaling="sigmoid", shared_network=True),
+    # hidden 32 / one layer = the tcgen05 tiled kernels, with an input scaling (the in-place scaled hidden state must not
+    # leak into the readout at h0) and with d_x = 2
+    dict(input_dim=1, hidden_dim=32, output_dim=1, dt_ode_step=0.01, num_moments=2, input_scaling="tanh"),
+    dict(input_dim=2, hidden_dim=32, output_dim=2, dt_ode_step=0.02, num_moments=2, activation="sigmoid",
+         input_scaling="sigmoid", shared_network=True),
 ]
 
 
@@ -188,13 +193,14 @@ def test_oracle_parity_random(case, impl):
     assert np.array_equal(preds.batch.step_counts(desc).cpu().numpy(), ref["K"])
 
 
-@pytest.mark.parametrize("impl,hidden", [("auto", 32), ("rowtile", 64), ("wide", 64)])
-def test_oracle_parity_many_tiles(impl, hidden):
+@pytest.mark.parametrize("impl,hidden,scaling", [("auto", 32, "identity"), ("rowtile", 64, "identity"), ("wide", 64, "identity"),
+                                                 ("auto", 32, "tanh")])
+def test_oracle_parity_many_tiles(impl, hidden, scaling):
     """More tiles than persistent CTAs (several rounds per CTA, partial last tile, deferred weight-gradient merges
     across tile boundaries): 2 500 ragged trajectories against the float64 oracle, plus run-to-run bitwise
     reproducibility of the gradients (fixed-order reductions, no atomics between owners)."""
     from neural_jump_ode import NeuralJumpODE
-    mk = dict(input_dim=1, hidden_dim=hidden, output_dim=1, dt_ode_step=0.01, num_moments=2)
+    mk = dict(input_dim=1, hidden_dim=hidden, output_dim=1, dt_ode_step=0.01, num_moments=2, input_scaling=scaling)
     torch.manual_seed(7)
     model = NeuralJumpODE(**mk)
     P = {k: v.detach().clone() for k, v in model.state_dict().items()}
