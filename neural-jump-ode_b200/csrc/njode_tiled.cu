@@ -103,6 +103,19 @@ __device__ __forceinline__ void load_wtile(float* hi, float* lo, const float* __
   }
 }
 
+// extension tile of the forward sweep's first ODE layer: B[n][k] = W0[n][H + k] for k < d_x + 2 (x.., t_cur, dt columns),
+// the bias b0[n] at k = d_x + 2, zero beyond (K-major, 128B swizzle, tf32 hi / lo like every weight tile)
+__device__ __forceinline__ void load_ext_tile(float* hi, float* lo, const ParamTable& T, const float* __restrict__ p, int nthreads) {
+  const int ld0 = H + T.d_x + 2, ne = T.d_x + 2;
+  for (int idx = threadIdx.x; idx < WT_F; idx += nthreads) {
+    const int n = idx >> 5, k = idx & 31;
+    const float v = k < ne ? p[T.w_off[NET_ODE][0] + n * ld0 + H + k] : (k == ne ? p[T.b_off[NET_ODE][0] + n] : 0.0f);
+    const float h = umma::tf32_hi(v);
+    hi[umma::swz_k(n, k)] = h;
+    lo[umma::swz_k(n, k)] = umma::tf32_hi(v - h);
+  }
+}
+
 __device__ __forceinline__ void load_small(SmallParams& sp, const ParamTable& T, const float* __restrict__ p) {
   const int t = threadIdx.x;
   if (t < 32) {
@@ -225,8 +238,13 @@ __device__ __forceinline__ int64_t snake_tile(int64_t round, int worker, int n_w
 // ------------------------------------------------------------------------------------------------
 // forward sweep
 // ------------------------------------------------------------------------------------------------
-enum { FW_ODE0 = 0, FW_ODE1, FW_JUMP1, FW_OUT0, FW_COUNT };
-constexpr uint32_t F_AHI = 0, F_ALO = 32, F_ACC = 64, F_TMEM_COLS = 128;
+// FW_EXT: a fifth k-step of the first ODE layer.  Its bias and its x / t / dt columns (jump_ode.py:57-61) are K columns 32.. of
+// the same GEMM -- A columns (s(x).., t_cur, dt, 1), written by the row's first thread -- instead of 4 shared-memory vector loads
+// and 32 FP32 instructions per thread and step in the epilogue: the forward sweep is bound by CUDA-core issue slots (2 CTAs per
+// SM, ~60 % issue utilisation), the tensor pipe is 78 % idle, and 3 more MMAs cost ~85 cycles of issue.
+enum { FW_ODE0 = 0, FW_ODE1, FW_JUMP1, FW_OUT0, FW_EXT, FW_COUNT };
+constexpr uint32_t F_AK = 40;                       // A operand columns: 32 hidden units + 8 extension columns
+constexpr uint32_t F_AHI = 0, F_ALO = F_AK, F_ACC = 2 * F_AK, F_TMEM_COLS = 128;
 constexpr size_t FWD_SMEM = 1024 + FW_COUNT * 2 * WT_F * 4 + sizeof(SmallParams) + sizeof(Ctl) + 16 + NJODE_TRACE_SMEM_BYTES;
 
 template <int ACT>
@@ -258,6 +276,7 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
   load_wtile(wt + (FW_ODE1 * 2) * WT_F, wt + (FW_ODE1 * 2 + 1) * WT_F, p + T.w_off[NET_ODE][1], H, false, NT);
   load_wtile(wt + (FW_JUMP1 * 2) * WT_F, wt + (FW_JUMP1 * 2 + 1) * WT_F, p + T.w_off[NET_JUMP][1], H, false, NT);
   load_wtile(wt + (FW_OUT0 * 2) * WT_F, wt + (FW_OUT0 * 2 + 1) * WT_F, p + T.w_off[NET_OUT][0], H, false, NT);
+  load_ext_tile(wt + (FW_EXT * 2) * WT_F, wt + (FW_EXT * 2 + 1) * WT_F, T, p, NT);
   load_small(sp, T, p);
   if (tid == 0) {
     umma::mbar_init(&ctl.bar_chain, 1);
@@ -276,12 +295,21 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
   bool ok = true;
 
   // acc = (in * W^T)[row][col0 .. col0+8)   (all 512 threads call this together)
-  auto gemm = [&](const float (&in)[8], int wid, float (&acc)[8]) {
+  // ext != nullptr (first ODE layer): the row's extension columns (s(x).., t_cur, dt, 1), appended as a fifth k-step
+  auto gemm = [&](const float (&in)[8], int wid, float (&acc)[8], const float* ext) {
     uint32_t hi[8], lo[8];
     TR(32 + 1);
     umma::split8(in, hi, lo);
     umma::tmem_st8_raw(lane_base + F_AHI, hi);
     umma::tmem_st8_raw(lane_base + F_ALO, lo);
+    if (ext != nullptr && c == 0) {
+      float e8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) e8[j] = ext[j];
+      umma::split8(e8, hi, lo);
+      umma::tmem_st8_raw(lane_base + F_AHI + 32, hi);
+      umma::tmem_st8_raw(lane_base + F_ALO + 32, lo);
+    }
     umma::wait_st();
     TR(32 + 2);
     umma::fence_before_sync();
@@ -289,7 +317,22 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
     TR(32 + 3);
     if (warp == 0 && umma::elect_one()) {
       umma::fence_after_sync();
-      issue_chain(tmem + F_ACC, tmem + F_AHI, tmem + F_ALO, wdesc(wbase, wid, 0), wdesc(wbase, wid, 1));
+      if (ext != nullptr) {
+        constexpr uint32_t idesc = umma::idesc_tf32(128, 32, 0, 0);
+        const uint64_t dbh = wdesc(wbase, wid, 0), dbl = wdesc(wbase, wid, 1), dxh = wdesc(wbase, FW_EXT, 0), dxl = wdesc(wbase, FW_EXT, 1);
+        const uint32_t a_hi = tmem + F_AHI, a_lo = tmem + F_ALO, d = tmem + F_ACC;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) umma::mma_ts(d, a_lo + 8 * ks, dbh + 2 * ks, idesc, ks > 0);
+        umma::mma_ts(d, a_lo + 32, dxh, idesc, 1);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) umma::mma_ts(d, a_hi + 8 * ks, dbl + 2 * ks, idesc, 1);
+        umma::mma_ts(d, a_hi + 32, dxl, idesc, 1);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) umma::mma_ts(d, a_hi + 8 * ks, dbh + 2 * ks, idesc, 1);
+        umma::mma_ts(d, a_hi + 32, dxh, idesc, 1);
+      } else {
+        issue_chain(tmem + F_ACC, tmem + F_AHI, tmem + F_ALO, wdesc(wbase, wid, 0), wdesc(wbase, wid, 1));
+      }
       umma::commit(&ctl.bar_chain);
     }
     TR(32 + 4);
@@ -328,7 +371,7 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) z[j] = act_fwd<ACT>(z[j]);
-    gemm(z, FW_JUMP1, acc);
+    gemm(z, FW_JUMP1, acc, nullptr);
     ld8(sp.b_jump1 + col0, cb);
 #pragma unroll
     for (int j = 0; j < 8; ++j) h[j] = act_fwd<ACT>(acc[j] + cb[j]);
@@ -336,7 +379,7 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
 
     // readout: y = out(h)                                           jump_ode.py:170 / :177, :205-212
     auto readout = [&](float* __restrict__ dst, int64_t obs, bool write) {
-      gemm(h, FW_OUT0, acc);
+      gemm(h, FW_OUT0, acc, nullptr);
       ld8(sp.b_out0 + col0, cb);
       float zz[8], y[MAX_O];
 #pragma unroll
@@ -376,25 +419,17 @@ __global__ void __launch_bounds__(NT, 2) k_tiled_forward(SweepArgs a) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) z[j] = h[j];
       scale8(sc_kind, z);
-      gemm(z, FW_ODE0, acc);
-      TR(32 + 9);
-      ld8(sp.b_ode0 + col0, cb);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) z[j] = acc[j] + cb[j];
-#pragma unroll
-      for (int e = 0; e < MAX_DX; ++e) if (e < dx) {
-        ld8(sp.ext_ode0[e] + col0, cw);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) z[j] = fmaf(cw[j], xs[e], z[j]);
+      {
+        // extension columns in the order of net.0.weight's columns H.. (x.., t_cur, dt), then the constant 1 of the bias
+        static_assert(MAX_DX == 2, "extension column layout assumes d_x <= 2");
+        const float ext[8] = {xs[0], dx > 1 ? xs[1] : tc, dx > 1 ? tc : delta, dx > 1 ? delta : 1.0f, dx > 1 ? 1.0f : 0.0f, 0.0f, 0.0f, 0.0f};
+        gemm(z, FW_ODE0, acc, ext);
       }
-      ld8(sp.ext_ode0[dx] + col0, cw);
+      TR(32 + 9);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) z[j] = fmaf(cw[j], tc, z[j]);
-      ld8(sp.ext_ode0[dx + 1] + col0, cw);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) z[j] = act_fwd<ACT>(fmaf(cw[j], delta, z[j]));
+      for (int j = 0; j < 8; ++j) z[j] = act_fwd<ACT>(acc[j]);
       if (ck) st8_stream(ck + (k * 2 + 1) * (R * H), z);
-      gemm(z, FW_ODE1, acc);
+      gemm(z, FW_ODE1, acc, nullptr);
       TR(32 + 8);
       if (k < K) {
         ld8(sp.b_ode1 + col0, cb);
