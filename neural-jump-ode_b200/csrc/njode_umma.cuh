@@ -90,20 +90,6 @@ __device__ __forceinline__ void tmem_free(uint32_t taddr, uint32_t ncols) {     
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols));
 }
 
-// 32 consecutive columns of this thread's TMEM lane  <->  32 registers
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t u[32];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-               "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
-                 "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
-                 "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
-                 "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
-               : "r"(taddr));
-  wait_ld();
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(u[i]);
-}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   uint32_t u[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -111,21 +97,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   wait_ld();
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(u[i]);
-}
-__device__ __forceinline__ void tmem_st32_raw(uint32_t taddr, const uint32_t (&u)[32]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-               "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
-               :: "r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]),
-                 "r"(u[8]), "r"(u[9]), "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15]),
-                 "r"(u[16]), "r"(u[17]), "r"(u[18]), "r"(u[19]), "r"(u[20]), "r"(u[21]), "r"(u[22]), "r"(u[23]),
-                 "r"(u[24]), "r"(u[25]), "r"(u[26]), "r"(u[27]), "r"(u[28]), "r"(u[29]), "r"(u[30]), "r"(u[31]) : "memory");
-}
-
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
-  uint32_t u[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) u[i] = __float_as_uint(v[i]);
-  tmem_st32_raw(taddr, u);
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
@@ -187,10 +158,6 @@ __device__ __forceinline__ void split1(float x, uint32_t& hi, uint32_t& lo) {
   hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
-__device__ __forceinline__ void split32(const float (&v)[32], uint32_t (&hi)[32], uint32_t (&lo)[32]) {
-#pragma unroll
-  for (int i = 0; i < 32; ++i) split1(v[i], hi[i], lo[i]);
-}
 
 // 8 / 2 columns per thread: four warps share a TMEM lane quadrant (warp % 4) and each owns an 8-column
 // slice of a 32-column operand / accumulator (tools/umma_probe4.cu validated the shared-quadrant access)
@@ -232,33 +199,6 @@ __device__ __forceinline__ void chunk_to_mn_tile(uint32_t tile_saddr, int r, int
   const uint32_t addr = tile_saddr + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 3)) * 32) + (sw ? 16u : 0u);
   st_shared_v4(addr, sw ? v[4] : v[0], sw ? v[5] : v[1], sw ? v[6] : v[2], sw ? v[7] : v[3]);
   st_shared_v4(addr ^ 16u, sw ? v[0] : v[4], sw ? v[1] : v[5], sw ? v[2] : v[6], sw ? v[3] : v[7]);
-}
-
-// this thread's row -> TMEM columns [col_hi, +32) and [col_lo, +32) of its lane (A operand of a chain GEMM)
-__device__ __forceinline__ void row_to_tmem(uint32_t lane_base, uint32_t col_hi, uint32_t col_lo,
-                                            const uint32_t (&hi)[32], const uint32_t (&lo)[32]) {
-  tmem_st32_raw(lane_base + col_hi, hi);
-  tmem_st32_raw(lane_base + col_lo, lo);
-}
-
-// this thread's row r -> MN-major tile (128-byte row, 32-byte chunks ^ r%4).  Lanes r and r+4 share r%4
-// and hit the same banks (2-way conflict); the kernels are issue-latency bound, not LSU bound, so the
-// conflict-free variant (which needs 32 SELs per row) is slower.
-__device__ __forceinline__ void row_to_mn_tile(float* tile, int r, const uint32_t (&v)[32]) {
-  uint4* row = reinterpret_cast<uint4*>(tile + r * 32);
-#pragma unroll
-  for (int c8 = 0; c8 < 4; ++c8) {
-    const int chunk = (c8 ^ (r & 3)) * 2;            // in 16-byte units
-    row[chunk] = make_uint4(v[c8 * 8 + 0], v[c8 * 8 + 1], v[c8 * 8 + 2], v[c8 * 8 + 3]);
-    row[chunk + 1] = make_uint4(v[c8 * 8 + 4], v[c8 * 8 + 5], v[c8 * 8 + 6], v[c8 * 8 + 7]);
-  }
-}
-// only the first 8 columns (one 32-byte chunk) of an MN-major tile row
-__device__ __forceinline__ void row8_to_mn_tile(float* tile, int r, const uint32_t (&v)[8]) {
-  uint4* row = reinterpret_cast<uint4*>(tile + r * 32);
-  const int chunk = (0 ^ (r & 3)) * 2;
-  row[chunk] = make_uint4(v[0], v[1], v[2], v[3]);
-  row[chunk + 1] = make_uint4(v[4], v[5], v[6], v[7]);
 }
 
 }  // namespace umma
