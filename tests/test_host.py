@@ -275,3 +275,27 @@ def test_packed_slice_and_gather():
     assert torch.equal(g.times, torch.cat([bt[3], bt[0], bt[2]])) and torch.equal(g.values, torch.cat([bv[3], bv[0], bv[2]]))
     with pytest.raises(ValueError):
         b.slice(2, 2)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/njode.h is the drop-in boundary: it must compile as C99 (no C++-isms, no torch types) and a C translation unit
+    that takes the address of every declared entry point must link against the built library."""
+    import re
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    hdr = os.path.join(ROOT, "include", "njode.h")
+    subprocess.run(["gcc", "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror", hdr], check=True)
+    names = sorted(set(re.findall(r"\b(njode_[a-z0-9_]+)\s*\(", open(hdr).read())))
+    assert len(names) >= 20
+    src = tmp_path / "bind.c"
+    src.write_text('#include "njode.h"\n#include <stdio.h>\nint main(void) {\n  const void* p[] = {' +
+                   ", ".join(f"(const void*){n}" for n in names) + "};\n  printf(\"%d\\n\", (int)(sizeof p / sizeof p[0]));\n  return 0;\n}\n")
+    lib_dir = os.path.join(ROOT, "neural-jump-ode_b200", "lib")
+    if not os.path.exists(os.path.join(lib_dir, "libnjode_b200.so")):
+        pytest.skip("library not built")
+    exe = tmp_path / "bind"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", lib_dir,
+                    "-lnjode_b200", f"-Wl,-rpath,{lib_dir}", "-Wl,--unresolved-symbols=ignore-in-shared-libs"], check=True)
