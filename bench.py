@@ -168,6 +168,32 @@ def cpu_port_baseline(wl, n_traj, repeats=1):
     return steps / best, steps, best
 
 
+def rows_cpu_baselines():
+    """CPU legs of tools/bench_rows.py (rows N1 / N2 of SURVEY.md 8f), kept HERE because bench.py's CPU-baseline legs are the
+    one measurement place that may execute oracle/: returns callables timing the eager port of the reference's training step
+    and the bit-exact restatement of its path generators."""
+    from oracle import njode_oracle as orc
+    from oracle import paths_oracle as po
+
+    def training_step(bt, bv, loss_kwargs, lr=1e-3, weight_decay=5e-4):
+        cfg = orc.make_cfg(1, 32, 1, 0.01, 2)
+        P = orc.init_params(cfg, seed=0)
+        t0 = time.perf_counter()
+        r = orc.run_port(P, cfg, bt, bv, loss_kwargs)
+        opt = torch.optim.Adam([torch.nn.Parameter(v.clone()) for v in P.values()], lr=lr, weight_decay=weight_decay)
+        for p, g in zip(opt.param_groups[0]["params"], r["grads"].values()):
+            p.grad = g
+        opt.step()
+        return time.perf_counter() - t0
+
+    def generate(process, n, n_steps, **pkw):
+        t0 = time.perf_counter()
+        po.trajectory_batch(n, process, obs_fraction=0.1, T=1.0, n_steps=n_steps, **pkw)
+        return time.perf_counter() - t0
+
+    return dict(training_step=training_step, generate=generate)
+
+
 def run_reference(args, wl, name):
     """--impl reference: the reference's algorithm on the host cores.  /root/reference (pure Python) does
     not exist on the GPU box and cannot be compiled into oracle/_ref, so the oracle port is timed."""

@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE -- CPU restatement of the reference's per-trajectory path generators and observation sampler
-(SURVEY.md section 8f, row N2).  Only tests/, tools/bench_rows.py's CPU leg and bench.py's CPU legs may import this.
+(SURVEY.md section 8f, row N2).  Only tests/ and bench.py's CPU-baseline legs (bench.rows_cpu_baselines) may import this.
 
 Follows neural_jump_ode/simulation/data_generation.py of the reference, one trajectory at a time and with the
 reference's consumption of the global torch / numpy RNG streams, so that the same seed gives the same path BIT FOR BIT:

@@ -6,7 +6,7 @@
      (d plane, activation plane, aux rows) it read -- separates its bugs from the reverse chain sweep's;
   3. end to end: every parameter gradient against the row-tiled flavour.
 
-usage: python tools/wide_debug.py [H L act B]      (prints one line per check; exit code 1 on a mismatch)
+usage: python tests/wide_debug_probe.py [H L act B]      (prints one line per check; exit code 1 on a mismatch)
 """
 import os
 import sys

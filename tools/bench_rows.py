@@ -6,7 +6,8 @@ closed-form conditional moments, N4 dense-grid inference) on one B200.  bench.py
 
 One JSON line per measurement: the GPU number (CUDA events, or host wall clock around a synchronised region where the
 row's point IS the host work), a CPU baseline timed on this box's host cores where an oracle port exists (N1: the eager
-port of the reference's training step, N2: oracle/paths_oracle.py -- pinned bit for bit to the reference), and the
+port of the reference's training step, N2: oracle/paths_oracle.py -- pinned bit for bit to the reference; both through
+bench.rows_cpu_baselines, bench.py being the one measurement script that executes oracle/), and the
 unmodified reference's own timing from the build container (profiles/r2_reference_rows_build_container.json,
 tools/ref_rows_cpu_timing.py) as labelled context where the reference code cannot travel (N3, N4).
 """
@@ -91,7 +92,7 @@ def row_n1(out, ctx):
     from neural_jump_ode.optim import FlatAdam
     from neural_jump_ode.simulation import make_packed_batch
     from neural_jump_ode.training import train_epoch_packed
-    from oracle import njode_oracle as orc
+    from bench import rows_cpu_baselines              # (the CPU legs live in bench.py: it owns every use of oracle/)
     dev = "cuda:0"
     mk = dict(input_dim=1, hidden_dim=32, output_dim=1, dt_ode_step=0.01, num_moments=2)
     data = make_packed_batch("black_scholes", 1000, 0.1, n_steps=100, T=1.0, device=dev, seed=5, **BS)
@@ -125,15 +126,7 @@ def row_n1(out, ctx):
     ms_list = wall_ms(list_epoch, warmup=1, iters=3)
 
     # CPU baseline on this box: the eager port of the reference's fwd + loss + bwd on one mini-batch of 128 + Adam
-    cfg = orc.make_cfg(1, 32, 1, 0.01, 2)
-    P = orc.init_params(cfg, seed=0)
-    t0 = time.perf_counter()
-    r = orc.run_port(P, cfg, bt[:128], bv[:128], LOSS)
-    cpu_opt = torch.optim.Adam([torch.nn.Parameter(v.clone()) for v in P.values()], lr=1e-3, weight_decay=5e-4)
-    for p, g in zip(cpu_opt.param_groups[0]["params"], r["grads"].values()):
-        p.grad = g
-    cpu_opt.step()
-    cpu_s = time.perf_counter() - t0
+    cpu_s = rows_cpu_baselines()["training_step"](bt[:128], bv[:128], LOSS)
     emit(out, dict(row="N1", what="config-1 epoch (1000 trajectories, mini-batches of 128 + 104 tail, Adam weight_decay 5e-4)",
                    metric="training epoch, host wall clock (device drained)", packed_flatadam_ms=ms, list_api_torch_adam_ms=ms_list,
                    trajectories_per_s_packed=1000 / (ms * 1e-3), trajectories_per_s_list_api=1000 / (ms_list * 1e-3),
@@ -171,15 +164,14 @@ def row_n1(out, ctx):
 def row_n2(out, ctx):
     """On-device generators + observation sampler against the per-trajectory reference loops."""
     from neural_jump_ode.simulation import make_packed_batch, make_mixed_ragged_batch
-    from oracle import paths_oracle as po
+    from bench import rows_cpu_baselines
+    cpu_generate = rows_cpu_baselines()["generate"]
     dev = "cuda:0"
     cases = (("black_scholes", 262144, 100, BS, 64), ("ornstein_uhlenbeck", 262144, 100, OU, 64), ("heston", 262144, 200, HESTON, 32))
     refc = ctx.get("N2_generators", {})
     for proc, n, n_steps, pkw, n_cpu in cases:
         ms = events_ms(lambda: make_packed_batch(proc, n, 0.1, n_steps=n_steps, T=1.0, device=dev, seed=3, **pkw), warmup=1, iters=3)
-        t0 = time.perf_counter()
-        po.trajectory_batch(n_cpu, proc, obs_fraction=0.1, T=1.0, n_steps=n_steps, **pkw)
-        cpu_s = time.perf_counter() - t0
+        cpu_s = cpu_generate(proc, n_cpu, n_steps, **pkw)
         emit(out, dict(row="N2", what=f"{proc}: {n} paths x {n_steps} grid steps + observation sampling (obs 0.1) -> PackedBatch",
                        metric="trajectories/s (CUDA events)", ms=ms, value=n / (ms * 1e-3), grid_points_per_s=n * (n_steps + 1) / (ms * 1e-3),
                        cpu_baseline=dict(kind="port", cores=1, sample=f"{n_cpu} trajectories, oracle/paths_oracle.py (bit-exact restatement)",

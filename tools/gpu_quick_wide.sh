@@ -4,7 +4,7 @@ TAG=${1:-q}
 mkdir -p gpurun_out
 for cfg in "128 3 tanh 60" "64 1 relu 60"; do
   t=$(echo $cfg | tr " " "_")
-  timeout 250 python tools/wide_debug.py $cfg > gpurun_out/wd_${TAG}_$t.log 2>&1; echo "== $cfg rc=$?"
+  timeout 250 python tests/wide_debug_probe.py $cfg > gpurun_out/wd_${TAG}_$t.log 2>&1; echo "== $cfg rc=$?"
   grep -E "vs f64|worst|status|WIDE|Error" gpurun_out/wd_${TAG}_$t.log | head -8
 done
 for w in heston_h128_l3 mixed_h64_ragged; do
