@@ -299,3 +299,23 @@ def test_header_is_plain_c(tmp_path):
     exe = tmp_path / "bind"
     subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", lib_dir,
                     "-lnjode_b200", f"-Wl,-rpath,{lib_dir}", "-Wl,--unresolved-symbols=ignore-in-shared-libs"], check=True)
+
+
+def test_bench_flop_model_matches_survey():
+    """bench.py's algorithmic flop count is SURVEY.md 8d's formula: 6 * S * MAC_ode per trajectory-step (25 728 for configs 1 / 3,
+    12 864 shared, 100 608 at hidden 64, 791 040 at hidden 128 / 3 layers) and F = 6 S [E MAC_ode + n MAC_jump + (2n - B) MAC_out]."""
+    import bench
+    sep32 = dict(input_dim=1, hidden_dim=32, output_dim=1, num_moments=2)
+    assert bench.mac_counts(sep32) == dict(S=2, ode=2144, jump=1056, out=1056)
+    assert bench.algorithmic_flops(sep32, 1, 0, 0)["per_step_ode"] == 25728
+    assert bench.algorithmic_flops(dict(sep32, shared_network=True), 1, 0, 0)["per_step_ode"] == 12864
+    assert bench.mac_counts(dict(sep32, shared_network=True))["out"] == 32 * 32 + 32 * 2
+    assert bench.algorithmic_flops(dict(sep32, hidden_dim=64), 1, 0, 0)["per_step_ode"] == 100608
+    h128 = dict(input_dim=1, hidden_dim=128, output_dim=1, num_moments=2, n_hidden_layers=3)
+    assert bench.mac_counts(h128)["ode"] == 65920
+    assert bench.algorithmic_flops(h128, 1, 0, 0)["per_step_ode"] == 791040
+    f = bench.algorithmic_flops(sep32, total_steps=1000, n_obs_total=100, n_traj=10)
+    macs = 2 * (1000 * 2144 + 100 * 1056 + (200 - 10) * 1056)
+    assert f["total"] == 6.0 * macs and f["fwd"] == 2.0 * macs and f["bwd"] == 4.0 * macs
+    assert bench.METRIC == "trajectory-ODE-steps/sec (fwd+bwd)" and bench.DEFAULT_WORKLOAD == "heston_sep_b262144"
+    assert bench.WORKLOADS[bench.DEFAULT_WORKLOAD]["B"] == 262144 and bench.WORKLOADS[bench.DEFAULT_WORKLOAD]["scaling"] == "strong"
