@@ -319,3 +319,27 @@ def test_bench_flop_model_matches_survey():
     assert f["total"] == 6.0 * macs and f["fwd"] == 2.0 * macs and f["bwd"] == 4.0 * macs
     assert bench.METRIC == "trajectory-ODE-steps/sec (fwd+bwd)" and bench.DEFAULT_WORKLOAD == "heston_sep_b262144"
     assert bench.WORKLOADS[bench.DEFAULT_WORKLOAD]["B"] == 262144 and bench.WORKLOADS[bench.DEFAULT_WORKLOAD]["scaling"] == "strong"
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the oracle port on the host cores, a bounded sample): one JSON line with the same metric /
+    unit / config.workload as the product arm, impl = reference, its own cpu_baseline block and an e2e block without copies."""
+    import json
+    import subprocess
+    import sys
+    import bench
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-sample", "3"], check=True, capture_output=True, text=True, timeout=600).stdout
+    lines = [l for l in out.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == "trajectory-ODE-steps/s"
+    assert d["config"]["workload"] == bench.DEFAULT_WORKLOAD and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] >= 3 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # under torchrun only rank 0 works and prints
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    quiet = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                            "--cpu-sample", "3"], check=True, capture_output=True, text=True, timeout=600, env=env).stdout
+    assert not [l for l in quiet.splitlines() if l.startswith("{")]
